@@ -1,0 +1,162 @@
+/*
+ * vcb200.h — C ABI of the B200-native clustering path of visioncortex.
+ *
+ * The reference (visioncortex v0.8.10, pure Rust) has no FFI of its own; the path is reached through
+ * ordinary Rust methods.  Every entry point below names the reference method it replaces (file:line under
+ * the reference tree).  A replacement crate (see rust/ and INTEGRATION.md) keeps the Rust API surface
+ * (`ColorImage`, `BinaryImage`, `color_clusters::{Runner, RunnerConfig, Clusters, ClustersView, Cluster}`,
+ * `clusters::{Clusters, Cluster}`) and forwards into these functions.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns a vcb_status (0 = OK) and never aborts or unwinds;
+ *   - a vcb_ctx owns one CUDA device, its streams and a workspace arena; it is NOT thread-safe, distinct
+ *     contexts may be used from distinct threads; result handles are immutable once returned;
+ *   - accessors copy into caller-owned buffers (sizes come from vcb_clusters_info / vcb_bin_clusters_info);
+ *   - there is no CPU fallback: if the device or the CUDA runtime is unavailable, vcb_ctx_create fails.
+ */
+#ifndef VCB200_H
+#define VCB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum vcb_status {
+    VCB_OK = 0,
+    VCB_ERR_INVALID_ARG = 1,     /* mirrors assert!(is_same_color_a < 8) (color_clusters/runner.rs:78), size mismatch, batch_size == 0 */
+    VCB_ERR_LABEL_OVERFLOW = 2,  /* mirrors panic!("overflow") (clusters.rs:322-324) */
+    VCB_ERR_UNSUPPORTED = 3,     /* order-dependent quirk input detected on device (DESIGN.md "fenced inputs") */
+    VCB_ERR_CUDA = 4,
+    VCB_ERR_NCCL = 5,
+    VCB_ERR_NOMEM = 6
+} vcb_status;
+
+/* KeyingAction (color_clusters/builder.rs:6-11) */
+enum { VCB_KEYING_KEEP = 0, VCB_KEYING_DISCARD = 1 };
+
+/* HIERARCHICAL_MAX (color_clusters/builder.rs:46) */
+#define VCB_HIERARCHICAL_MAX 0xFFFFFFFFu
+
+/* RunnerConfig (color_clusters/runner.rs:9-21); field meaning identical. */
+typedef struct vcb_runner_config {
+    int32_t  diagonal;
+    uint32_t hierarchical;
+    int32_t  batch_size;
+    uint64_t good_min_area;
+    uint64_t good_max_area;
+    int32_t  is_same_color_a;
+    int32_t  is_same_color_b;
+    int32_t  deepen_diff;
+    uint64_t hollow_neighbours;
+    uint8_t  key_color[4];       /* r,g,b,a; (0,0,0,0) = no key (Color::default()) */
+    int32_t  keying_action;
+} vcb_runner_config;
+
+/* One slot of `Clusters.clusters` (color_clusters/cluster.rs:7-17).  area() == indices_len. */
+typedef struct vcb_cluster_rec {
+    uint32_t sum[5];             /* ColorSum r,g,b,a,counter (color.rs:40-47), u32 wrapping */
+    uint32_t residue_sum[5];
+    int32_t  rect[4];            /* BoundingRect left,top,right,bottom (bound.rs:15-21) */
+    uint32_t num_holes;
+    uint32_t depth;
+    uint32_t merged_into;
+    uint32_t indices_len;
+    uint64_t indices_off;        /* offset into the indices pool */
+    uint64_t holes_off;          /* offset into the holes pool */
+    uint32_t holes_len;
+    uint32_t _pad;
+} vcb_cluster_rec;
+
+typedef struct vcb_clusters_info {
+    uint32_t width, height;
+    uint32_t num_slots;          /* clusters.len(), dead slots included */
+    uint32_t num_outputs;        /* clusters_output.len() */
+    uint64_t indices_total;      /* sum of indices_len over all slots */
+    uint64_t holes_total;
+} vcb_clusters_info;
+
+/* clusters::Cluster (clusters.rs:7-11) */
+typedef struct vcb_bin_cluster_rec {
+    int32_t  rect[4];
+    uint64_t points_off;         /* offset (in points) into the points pool */
+    uint32_t points_len;
+    uint32_t _pad;
+} vcb_bin_cluster_rec;
+
+typedef struct vcb_bin_clusters_info {
+    uint32_t width, height;
+    uint32_t num_clusters;       /* clusters.len() after the empty-slot filter (clusters.rs:345) */
+    uint32_t _pad;
+    uint64_t points_total;
+    int32_t  rect[4];            /* Clusters.rect (clusters.rs:14-18,302) */
+} vcb_bin_clusters_info;
+
+typedef struct vcb_ctx vcb_ctx;
+typedef struct vcb_clusters vcb_clusters;
+typedef struct vcb_bin_clusters vcb_bin_clusters;
+
+/* library */
+const char *vcb_strerror(int status);
+const char *vcb_last_error(const vcb_ctx *ctx);      /* detail text of the last failure on this context */
+uint32_t    vcb_abi_version(void);
+
+/* RunnerConfig::default() (color_clusters/runner.rs:23-39) */
+void vcb_runner_config_default(vcb_runner_config *cfg);
+
+/* context: one device, streams, workspace arena */
+int  vcb_ctx_create(int device, vcb_ctx **out);
+void vcb_ctx_destroy(vcb_ctx *ctx);
+int  vcb_ctx_device(const vcb_ctx *ctx);
+
+/* Runner::new(config, image).run() (color_clusters/runner.rs:52-57,104-106): host RGBA8 row-major in, result handle out. */
+int vcb_runner_run(vcb_ctx *ctx, const vcb_runner_config *cfg, const uint8_t *rgba,
+                   uint32_t width, uint32_t height, vcb_clusters **out);
+
+/* The same call for n independent images (how a vtracer-style caller batches).  out[] receives n handles.
+ * Images are pipelined over the context's streams; there is no cross-image communication. */
+int vcb_runner_run_batch(vcb_ctx *ctx, const vcb_runner_config *cfg, const uint8_t *const *rgba,
+                         const uint32_t *width, const uint32_t *height, size_t n, vcb_clusters **out);
+
+/* Device-resident variant: d_rgba points to n images of identical size stored back to back in device memory
+ * of ctx's device.  Results stay on the device until an accessor is called. */
+int vcb_runner_run_device(vcb_ctx *ctx, const vcb_runner_config *cfg, const uint8_t *d_rgba,
+                          uint32_t width, uint32_t height, size_t n, vcb_clusters **out);
+
+/* Clusters / ClustersView (color_clusters/container.rs:4-117) */
+int  vcb_clusters_info_get(const vcb_clusters *c, vcb_clusters_info *info);
+int  vcb_clusters_cluster_indices(const vcb_clusters *c, uint32_t *out /* width*height */);
+int  vcb_clusters_outputs(const vcb_clusters *c, uint32_t *out /* num_outputs */);
+int  vcb_clusters_records(const vcb_clusters *c, vcb_cluster_rec *out /* num_slots */);
+int  vcb_clusters_indices_pool(const vcb_clusters *c, uint32_t *out /* indices_total */);
+int  vcb_clusters_holes_pool(const vcb_clusters *c, uint32_t *out /* holes_total */);
+/* ClustersView::to_color_image (color_clusters/container.rs:104-116) */
+int  vcb_clusters_to_color_image(const vcb_clusters *c, uint8_t *rgba_out /* width*height*4 */);
+/* device pointer of the label map (width*height u32) for callers that stay on the GPU; NULL if released */
+const uint32_t *vcb_clusters_device_labels(const vcb_clusters *c);
+void vcb_clusters_free(vcb_clusters *c);
+
+/* BinaryImage::to_clusters(diagonal) (clusters.rs:270-349).  bits = bit_vec::BitVec storage: u32 blocks,
+ * pixel i = y*width+x lives in block i/32 at bit i%32 (LSB first); ceil(width*height/32) blocks. */
+int  vcb_binary_to_clusters(vcb_ctx *ctx, const uint32_t *bits, uint32_t width, uint32_t height,
+                            int diagonal, vcb_bin_clusters **out);
+int  vcb_binary_to_clusters_device(vcb_ctx *ctx, const uint32_t *d_bits, uint32_t width, uint32_t height,
+                                   int diagonal, vcb_bin_clusters **out);
+int  vcb_bin_clusters_info_get(const vcb_bin_clusters *c, vcb_bin_clusters_info *info);
+int  vcb_bin_clusters_records(const vcb_bin_clusters *c, vcb_bin_cluster_rec *out /* num_clusters */);
+int  vcb_bin_clusters_points(const vcb_bin_clusters *c, int32_t *xy_out /* 2*points_total, PointI32{x,y} */);
+void vcb_bin_clusters_free(vcb_bin_clusters *c);
+
+/* measurement hooks used by bench.py (not part of the reference surface) */
+int  vcb_ctx_synchronize(vcb_ctx *ctx);
+uint64_t vcb_ctx_kernel_launches(const vcb_ctx *ctx);            /* kernels launched by this context so far */
+/* device time (ms) of the dominant kernel, accumulated by CUDA events on its launching stream since the last reset */
+int  vcb_ctx_profile_reset(vcb_ctx *ctx, int enable);
+int  vcb_ctx_profile_read(vcb_ctx *ctx, const char *kernel_name, double *total_ms, uint64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCB200_H */

@@ -1,0 +1,112 @@
+"""Synthetic inputs for the BASELINE.json configurations.
+
+Integer-only, stateless-hash based, index-addressable: the same (W, H, seed) always gives the same image.
+  G1  binary noise                                  -> C1 (BinaryImage::to_clusters)
+  G2  jittered-grid Voronoi "RGBA scene" with noise -> C2 / C4 (Runner)
+  G3  posterised Voronoi, optional key-colour cells -> C3 / C5
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _mix(x: np.ndarray) -> np.ndarray:
+    """splitmix64 finaliser on uint64 arrays (wrapping)."""
+    with np.errstate(over="ignore"):
+        x = (x + np.uint64(0x9E3779B97F4A7C15)) & _M64
+        x = ((x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+        x = ((x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+        x = x ^ (x >> np.uint64(31))
+    return x
+
+
+def _h(seed: int, stream: int, i: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        base = _mix(np.array([np.uint64(seed) ^ (np.uint64(stream) << np.uint64(56))], dtype=np.uint64))
+        return _mix(base + i.astype(np.uint64))
+
+
+def g1_binary(width: int, height: int, p: float, seed: int) -> np.ndarray:
+    """bool (h, w): bit i set iff (h(seed,1,i) >> 32) < floor(p * 2^32)."""
+    n = width * height
+    thr = np.uint64(int(p * (1 << 32)))
+    bits = (_h(seed, 1, np.arange(n, dtype=np.uint64)) >> np.uint64(32)) < thr
+    return bits.reshape(height, width)
+
+
+def _voronoi_ids(width: int, height: int, seed: int, cell: int):
+    gx = (width + cell - 1) // cell
+    gy = (height + cell - 1) // cell
+    ids = np.arange(gx * gy, dtype=np.uint64)
+    cx = (ids % np.uint64(gx)).astype(np.int64)
+    cy = (ids // np.uint64(gx)).astype(np.int64)
+    sx = cx * cell + (_h(seed, 2, ids) % np.uint64(cell)).astype(np.int64)
+    sy = cy * cell + (_h(seed, 3, ids) % np.uint64(cell)).astype(np.int64)
+    ys, xs = np.mgrid[0:height, 0:width].astype(np.int64)
+    pcx, pcy = xs // cell, ys // cell
+    best_d = np.full((height, width), np.iinfo(np.int64).max, dtype=np.int64)
+    best_id = np.zeros((height, width), dtype=np.int64)
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            qx, qy = pcx + dx, pcy + dy
+            ok = (qx >= 0) & (qx < gx) & (qy >= 0) & (qy < gy)
+            qid = np.where(ok, qy * gx + qx, 0)
+            d = (xs - sx[qid]) ** 2 + (ys - sy[qid]) ** 2
+            d = np.where(ok, d, np.iinfo(np.int64).max)
+            better = (d < best_d) | ((d == best_d) & (qid < best_id))
+            best_d = np.where(better, d, best_d)
+            best_id = np.where(better, qid, best_id)
+    return best_id, gx * gy
+
+
+def g2_scene(width: int, height: int, seed: int, cell: int = 48, amp: int = 3) -> np.ndarray:
+    """uint8 (h, w, 4) RGBA: Voronoi cells, diagonal shading, +-amp per-channel noise, alpha 255."""
+    best_id, ncell = _voronoi_ids(width, height, seed, cell)
+    col24 = (_h(seed, 4, np.arange(ncell, dtype=np.uint64)) & np.uint64(0xFFFFFF)).astype(np.int64)
+    ys, xs = np.mgrid[0:height, 0:width].astype(np.int64)
+    shade = ((xs + 2 * ys) >> 5) & 15
+    out = np.empty((height, width, 4), dtype=np.uint8)
+    pix = (ys * width + xs).astype(np.uint64)
+    for ch in range(3):
+        base = (col24[best_id] >> (8 * ch)) & 0xFF
+        v = base + shade
+        if amp > 0:
+            noise = (_h(seed, 5, pix * np.uint64(4) + np.uint64(ch)) % np.uint64(2 * amp + 1)).astype(np.int64) - amp
+            v = v + noise
+        out[..., ch] = np.clip(v, 0, 255).astype(np.uint8)
+    out[..., 3] = 255
+    return out
+
+
+def g3_posterised(width: int, height: int, seed: int, cell: int = 96, key=None) -> np.ndarray:
+    """uint8 (h, w, 4): G2 geometry, no noise/shading, channels quantised to {0,85,170,255};
+    with ``key`` (r,g,b,a) every cell with h(seed,6,id)%10==0 is filled with the key colour."""
+    best_id, ncell = _voronoi_ids(width, height, seed, cell)
+    ids = np.arange(ncell, dtype=np.uint64)
+    col24 = (_h(seed, 4, ids) & np.uint64(0xFFFFFF)).astype(np.int64)
+    out = np.empty((height, width, 4), dtype=np.uint8)
+    for ch in range(3):
+        base = (col24 >> (8 * ch)) & 0xFF
+        q = (base >> 6) * 85
+        out[..., ch] = q[best_id].astype(np.uint8)
+    out[..., 3] = 255
+    if key is not None:
+        keyed = (_h(seed, 6, ids) % np.uint64(10)) == 0
+        m = keyed[best_id]
+        out[m] = np.array(key, dtype=np.uint8)
+    return out
+
+
+def random_blocky(rng: np.random.Generator, width: int, height: int, ncolors: int = 3, step: int = 24,
+                  block: int = 2) -> np.ndarray:
+    """Small adversarial test images: low-cardinality blocky noise so that every stage-1 quirk fires."""
+    bh, bw = (height + block - 1) // block, (width + block - 1) // block
+    pal = rng.integers(0, 256 // step, size=(ncolors, 3)) * step
+    idx = rng.integers(0, ncolors, size=(bh, bw))
+    img = pal[idx].repeat(block, axis=0).repeat(block, axis=1)[:height, :width]
+    out = np.empty((height, width, 4), dtype=np.uint8)
+    out[..., :3] = img.astype(np.uint8)
+    out[..., 3] = 255
+    return out

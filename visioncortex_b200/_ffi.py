@@ -184,10 +184,10 @@ class Library:
             raise VcbError(status, msg)
 
     # ------------------------------------------------------------------ result extraction (shared by both libs)
-    def read_clusters(self, handle, *, pools: bool = True, free: bool = True) -> dict:
+    def read_clusters(self, handle, *, pools: bool = True, free: bool = True, ctx=None) -> dict:
         f = self.fn
         info = ClustersInfoC()
-        self.check(f("clusters_info_get")(handle, C.byref(info)))
+        self.check(f("clusters_info_get")(handle, C.byref(info)), ctx)
         n = info.width * info.height
         res = {
             "width": info.width,
@@ -197,14 +197,14 @@ class Library:
             "clusters_output": np.empty(info.num_outputs, dtype=np.uint32),
             "records": np.zeros(info.num_slots, dtype=CLUSTER_REC_DTYPE),
         }
-        self.check(f("clusters_cluster_indices")(handle, _ptr(res["cluster_indices"])))
-        self.check(f("clusters_outputs")(handle, _ptr(res["clusters_output"])))
-        self.check(f("clusters_records")(handle, _ptr(res["records"])))
+        self.check(f("clusters_cluster_indices")(handle, _ptr(res["cluster_indices"])), ctx)
+        self.check(f("clusters_outputs")(handle, _ptr(res["clusters_output"])), ctx)
+        self.check(f("clusters_records")(handle, _ptr(res["records"])), ctx)
         if pools:
             res["indices_pool"] = np.empty(info.indices_total, dtype=np.uint32)
             res["holes_pool"] = np.empty(info.holes_total, dtype=np.uint32)
-            self.check(f("clusters_indices_pool")(handle, _ptr(res["indices_pool"])))
-            self.check(f("clusters_holes_pool")(handle, _ptr(res["holes_pool"])))
+            self.check(f("clusters_indices_pool")(handle, _ptr(res["indices_pool"])), ctx)
+            self.check(f("clusters_holes_pool")(handle, _ptr(res["holes_pool"])), ctx)
         if free:
             f("clusters_free")(handle)
         return res

@@ -1,0 +1,216 @@
+// engine.cuh — host-side orchestration of the kernels: workspace arena, stage-1 pipeline, result objects.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "records.cuh"
+
+struct vcb_ctx {
+    int device = 0;
+    int sms = 1;
+    rt::Stream st;
+    std::string err;
+    // workspace arena (grow-only, sized by the largest batch seen)
+    size_t capN = 0;
+    vcb::Bufs b{};
+    u32 *chunksum = nullptr;          // scan scratch
+    u32 *rs_table = nullptr;          // radix sort digit table
+    u64 *sk0 = nullptr, *sk1 = nullptr;
+    u32 *sv0 = nullptr, *sv1 = nullptr;
+    u32 *d_small = nullptr;           // small device scratch (counts, slot_base ...)
+    size_t cap_img = 0;
+    void *h_pinned = nullptr;         // pinned staging for small D2H reads
+    size_t h_pinned_cap = 0;
+    u8 *d_stage = nullptr;            // device staging of host inputs
+    size_t d_stage_cap = 0;
+};
+
+namespace vcb {
+
+struct BatchResult {
+    vcb_ctx *ctx = nullptr;
+    Dims d{};
+    bool binary = false;
+    vcb_runner_config cfg{};
+    u32 *labels = nullptr;            // N
+    vcb_cluster_rec *rec = nullptr;   // total_slots
+    u32 *outputs = nullptr;           // total_slots (per image: [slot_base, slot_base + nout))
+    u32 *d_slot_base = nullptr;       // nimg + 1
+    u32 *d_slot_img = nullptr;        // total_slots
+    std::vector<u32> slot_base, nout;
+    std::vector<u64> indices_total, holes_total;
+    u32 total_slots = 0;
+    ~BatchResult() {
+        rt::dev_free(labels); rt::dev_free(rec); rt::dev_free(outputs); rt::dev_free(d_slot_base); rt::dev_free(d_slot_img);
+    }
+};
+
+inline int grid_for(const vcb_ctx *c, u64 items, int threads, int per_sm = 8) {
+    u64 g = (items + threads - 1) / threads;
+    const u64 cap = (u64)c->sms * per_sm;
+    if (g > cap) g = cap;
+    if (g == 0) g = 1;
+    return (int)g;
+}
+
+template <class T> inline bool grow(T *&p, size_t n) {
+    rt::dev_free(p);
+    p = (T *)rt::dev_malloc(n * sizeof(T));
+    return p != nullptr;
+}
+
+inline int ensure_workspace(vcb_ctx *c, size_t N, size_t nimg) {
+    if (N > c->capN) {
+        const size_t cap = N + 64;
+        bool ok = true;
+        ok &= grow(c->b.flags, cap); ok &= grow(c->b.pc, cap); ok &= grow(c->b.la, cap); ok &= grow(c->b.ls, cap);
+        ok &= grow(c->b.lr, cap); ok &= grow(c->b.ev, cap); ok &= grow(c->b.cand, cap); ok &= grow(c->b.newlist, cap);
+        ok &= grow(c->b.attr, cap);
+        const size_t chunks = cap / 2048 + 4;
+        ok &= grow(c->chunksum, 256 * chunks / 2048 + chunks + 1024);
+        ok &= grow(c->rs_table, 256 * chunks + 16);
+        ok &= grow(c->sk0, cap + nimg + 16); ok &= grow(c->sk1, cap + nimg + 16);
+        ok &= grow(c->sv0, cap + nimg + 16); ok &= grow(c->sv1, cap + nimg + 16);
+        if (!c->b.ctr) ok &= grow(c->b.ctr, 1);
+        if (!ok) { c->capN = 0; return VCB_ERR_NOMEM; }
+        c->capN = N;
+    }
+    if (nimg > c->cap_img) {
+        bool ok = grow(c->b.meta, nimg + 1);
+        ok &= grow(c->d_small, 4 * (nimg + 4));
+        if (!ok) { c->cap_img = 0; return VCB_ERR_NOMEM; }
+        c->cap_img = nimg;
+    }
+    const size_t need = (nimg + 4) * sizeof(ImgMeta) + 4096;
+    if (need > c->h_pinned_cap) {
+        rt::host_free(c->h_pinned);
+        c->h_pinned = rt::host_malloc(need);
+        c->h_pinned_cap = c->h_pinned ? need : 0;
+        if (!c->h_pinned) return VCB_ERR_NOMEM;
+    }
+    return VCB_OK;
+}
+
+__global__ void k_meta_init(Dims d, Bufs b) {
+    const u32 img = blockIdx.x * blockDim.x + threadIdx.x;
+    if (img == 0) { Counters z{}; *b.ctr = z; }
+    if (img >= d.nimg) return;
+    ImgMeta m{};
+    m.key_rect[0] = 0x7fffffff; m.key_rect[1] = -1; m.key_rect[2] = 0x7fffffff; m.key_rect[3] = -1;
+    b.meta[img] = m;
+}
+
+// Runs K1..K8 for `nimg` equally sized images resident on the device and builds the per-slot records.
+// base = 1 for the colour path (slot 0 = ZERO, builder.rs:44-45,189), 0 for the binary path.
+template <class P>
+inline int run_stage1(vcb_ctx *c, const Dims &d, const P &pol, u32 base, bool want_attr, int keep_key, BatchResult *res,
+                      std::vector<ImgMeta> &meta_out, Counters &ctr_out) {
+    rt::Stream &st = c->st;
+    Bufs b = c->b;
+    const int g_img = (int)((d.nimg + 127) / 128);
+    rt::launch(st, "k_meta_init", rt::SEQ, k_meta_init, dim3(g_img), dim3(128), 0, d, b);
+
+    const u32 tiles = ((d.w + TW - 1) / TW) * ((d.h + TH - 1) / TH) * d.nimg;
+    rt::launch(st, "k_edges_tile", rt::THR, k_edges_tile<P>, dim3(tiles), dim3(K1_THREADS), K1_SMEM, d, pol, b);
+    rt::launch(st, "k_flatten_events", rt::THR, k_flatten_events, dim3(grid_for(c, d.N, K2_THREADS, 16)), dim3(K2_THREADS), 0, d, b);
+    {
+        static int coop_blocks = 0;
+        if (!coop_blocks) coop_blocks = rt::max_coop_blocks((const void *)k_boruvka, K3_THREADS, 0, c->device);
+        int g = coop_blocks;
+        const int want = (int)((d.N / 4 + K3_THREADS - 1) / K3_THREADS);
+        if (g > want) g = want < 1 ? 1 : want;
+        rt::launch(st, "k_boruvka", rt::COOP, k_boruvka, dim3(g), dim3(K3_THREADS), 0, b);
+    }
+    rt::launch(st, "k_chain_insert", rt::SEQ, k_chain_insert, dim3(grid_for(c, d.N / 2, K4_THREADS, 16)), dim3(K4_THREADS), 0, d, b);
+    prims::scan(st, "scan_new", NewScan{d, b}, c->chunksum, d.N, c->sms * 8);
+    {
+        // rows per segment: enough threads to fill the machine, as few restarts as possible
+        const u64 wpad = (d.w + 31) & ~31u;
+        const u64 target = (u64)c->sms * 2048;
+        u32 nseg = (u32)((target + wpad * d.nimg - 1) / (wpad * d.nimg));
+        if (nseg < 1) nseg = 1;
+        if (nseg > d.h) nseg = d.h;
+        u32 rows = (d.h + nseg - 1) / nseg;
+        if (rows < 8 && d.h >= 8) rows = 8;
+        const u64 threads = (u64)d.nimg * ((d.h + rows - 1) / rows) * wpad;
+        const int g = grid_for(c, threads, K5_THREADS, 16);
+        if (want_attr)
+            rt::launch(st, "k_attribute", rt::THR, k_attribute<P, true>, dim3(g), dim3(K5_THREADS), 0, d, pol, b, rows, keep_key);
+        else
+            rt::launch(st, "k_attribute", rt::THR, k_attribute<P, false>, dim3(g), dim3(K5_THREADS), 0, d, pol, b, rows, keep_key);
+    }
+    rt::launch(st, "k_tournament", rt::SEQ, k_tournament, dim3(grid_for(c, d.N / 4, K6_THREADS, 16)), dim3(K6_THREADS), 0, d, b);
+    prims::scan(st, "scan_label", LabelScan{d, b}, c->chunksum, d.N, c->sms * 8);
+    rt::launch(st, "k_image_meta", rt::SEQ, k_image_meta, dim3(g_img), dim3(128), 0, d, b, base);
+    rt::launch(st, "k_leaf_labels", rt::SEQ, k_leaf_labels, dim3(grid_for(c, d.N / 4, K8_THREADS, 16)), dim3(K8_THREADS), 0, d, b, base);
+    rt::launch(st, "k_leaf_final", rt::SEQ, k_leaf_final, dim3(grid_for(c, d.N / 4, K8_THREADS, 16)), dim3(K8_THREADS), 0, d, b);
+    if (res->labels)
+        rt::launch(st, "k_labels", rt::SEQ, k_labels, dim3(grid_for(c, d.N, K8_THREADS, 16)), dim3(K8_THREADS), 0, d, b, res->labels);
+
+    // one small read-back: per-image slot counts (sizes of the result) and the error flags
+    ImgMeta *hm = (ImgMeta *)c->h_pinned;
+    Counters *hc = (Counters *)((char *)c->h_pinned + (d.nimg + 1) * sizeof(ImgMeta));
+    rt::copy_d2h(st, hm, b.meta, d.nimg * sizeof(ImgMeta));
+    rt::copy_d2h(st, hc, b.ctr, sizeof(Counters));
+    if (rt::stream_sync(st) != 0 || st.last_error) {
+        c->err = st.last_error ? st.last_error_text : std::string("stream synchronize failed");
+        st.last_error = 0;
+        return VCB_ERR_CUDA;
+    }
+    meta_out.assign(hm, hm + d.nimg);
+    ctr_out = *hc;
+    return VCB_OK;
+}
+
+// records + (optionally) the hierarchical == 0 output list
+inline int build_records(vcb_ctx *c, const Dims &d, const std::vector<ImgMeta> &meta, BatchResult *res, bool flat_outputs,
+                         bool keep_key) {
+    rt::Stream &st = c->st;
+    Bufs b = c->b;
+    res->slot_base.assign(d.nimg + 1, 0);
+    for (u32 i = 0; i < d.nimg; ++i) res->slot_base[i + 1] = res->slot_base[i] + meta[i].slots;
+    const u32 total = res->slot_base[d.nimg];
+    res->total_slots = total;
+    res->rec = (vcb_cluster_rec *)rt::dev_malloc((size_t)total * sizeof(vcb_cluster_rec));
+    res->d_slot_base = (u32 *)rt::dev_malloc((d.nimg + 1) * sizeof(u32));
+    res->d_slot_img = (u32 *)rt::dev_malloc((size_t)total * sizeof(u32));
+    res->outputs = (u32 *)rt::dev_malloc((size_t)total * sizeof(u32));
+    if (!res->rec || !res->d_slot_base || !res->d_slot_img || !res->outputs) return VCB_ERR_NOMEM;
+    rt::copy_h2d(st, res->d_slot_base, res->slot_base.data(), (d.nimg + 1) * sizeof(u32));
+    const int g = grid_for(c, total, REC_THREADS, 16);
+    rt::launch(st, "k_rec_init", rt::SEQ, k_rec_init, dim3(g), dim3(REC_THREADS), 0, res->rec, total);
+    rt::launch(st, "k_slot_img", rt::SEQ, k_slot_img, dim3(d.nimg), dim3(REC_THREADS), 0, res->d_slot_img, res->d_slot_base, d.nimg);
+    rt::launch(st, "k_rec_accum", rt::SEQ, k_rec_accum, dim3(grid_for(c, d.N / 4, REC_THREADS, 16)), dim3(REC_THREADS), 0, d, b, res->rec, res->d_slot_base);
+    if (keep_key)
+        rt::launch(st, "k_rec_key", rt::SEQ, k_rec_key, dim3((d.nimg + 127) / 128), dim3(128), 0, d, b, res->rec, res->d_slot_base);
+    rt::launch(st, "k_rec_final", rt::SEQ, k_rec_final, dim3(g), dim3(REC_THREADS), 0, res->rec, total);
+    prims::scan(st, "scan_off", OffScan{res->rec, res->d_slot_base, res->d_slot_img, total, nullptr}, c->chunksum, total, c->sms * 8);
+    rt::launch(st, "k_off_rebase", rt::SEQ, k_off_rebase, dim3(g), dim3(REC_THREADS), 0, res->rec, res->d_slot_base, res->d_slot_img, total);
+    rt::launch(st, "k_off_rebase0", rt::SEQ, k_off_rebase0, dim3((d.nimg + 127) / 128), dim3(128), 0, res->rec, res->d_slot_base, d.nimg);
+
+    res->nout.assign(d.nimg, 0);
+    res->indices_total.assign(d.nimg, 0);
+    res->holes_total.assign(d.nimg, 0);
+    u32 *d_live = c->d_small;            // nimg counters
+    u32 *d_total = c->d_small + d.nimg + 1;
+    if (flat_outputs) {
+        int key_bits = 1;
+        while ((1ull << key_bits) <= (u64)d.n * 65535ull + d.n + 1) ++key_bits;
+        int img_bits = 1;
+        while ((1u << img_bits) < d.nimg) ++img_bits;
+        rt::fill(st, d_live, 0, (d.nimg + 2) * sizeof(u32));
+        rt::copy_h2d(st, d_total, &res->total_slots, sizeof(u32));
+        rt::launch(st, "k_out_keys", rt::SEQ, k_out_keys, dim3(g), dim3(REC_THREADS), 0, res->rec, res->d_slot_base,
+                   res->d_slot_img, total, key_bits, c->sk0, c->sv0, d_live);
+        const bool flipped = prims::radix_sort(st, c->sk0, c->sv0, c->sk1, c->sv1, d_total, total, key_bits + (d.nimg > 1 ? img_bits : 0),
+                                               c->rs_table, c->chunksum, c->sms * 8);
+        rt::copy_d2d(st, res->outputs, flipped ? c->sv1 : c->sv0, (size_t)total * sizeof(u32));
+        rt::copy_d2h(st, c->h_pinned, d_live, d.nimg * sizeof(u32));
+        if (rt::stream_sync(st) != 0 || st.last_error) { c->err = st.last_error_text; st.last_error = 0; return VCB_ERR_CUDA; }
+        for (u32 i = 0; i < d.nimg; ++i) res->nout[i] = ((u32 *)c->h_pinned)[i];
+    }
+    return VCB_OK;
+}
+
+}  // namespace vcb

@@ -1,0 +1,602 @@
+// ids.cuh — stage 1 of the clustering path as data-parallel kernels (colour: color_clusters/builder.rs:273-364;
+// binary: clusters.rs:270-349).  The reference scans pixels in raster order and merges clusters by *dynamic* area, so
+// its cluster ids are not those of a textbook connected-component labeling.  DESIGN.md ("id model") explains the
+// decomposition implemented here; in short, with time = raster index:
+//   K1  k_edges_tile      static per-pixel join code J and merge flag M (pure functions of 4 pixels), tile-local
+//                          resolution of the J forest in shared memory, leaf (= provisional cluster) records
+//   K2  k_flatten_events  global resolution of the J forest; candidate merge events (M set, endpoints in different PCs)
+//   K3  k_boruvka         which candidate events are *effective* = minimum spanning forest under weight = time
+//   K4  k_chain_insert    Kruskal reconstruction tree (parent of every leaf / effective event), lock-free
+//   K5  k_attribute       every pixel is attributed to the tree node alive when it joined; per-node counts,
+//                          the up-side child of every event, per-leaf colour sums / rects
+//   K6  k_tournament      bottom-up: areas at merge time -> winners -> carriers -> label deaths
+//   K7  numbering         prefix-scan compaction of NEW events minus immediately-reused slots (builder.rs:315-317)
+//   K8  k_labels          final cluster_indices
+#pragma once
+#include "prims.cuh"
+
+namespace vcb {
+
+constexpr u32 NONE = 0xFFFFFFFFu;
+constexpr u32 TAG = 0x80000000u;   // node ids: leaf = TAG | pixel, event = pixel; also "dead" mark in the candidate list
+
+enum : u32 { J_NEW = 0, J_UP = 1, J_LEFT = 2, J_UPLEFT = 3, J_NONE = 4, J_MASK = 7,
+             F_M = 8, F_CAND = 16, F_MSF = 32, F_KEYED = 64, F_LWIN = 128 };
+
+struct Dims { u32 w, h, n, nimg, N; };
+
+// one 32-byte sector per record; records are indexed by *pixel* (sparse): only NEW pixels own a leaf record and only
+// candidate-event pixels own an event record, and each is initialised by the kernel that creates it (no memsets).
+struct LeafA { u32 ufp, best0, best1, parL, cnt, death, label, flabel; };
+struct LeafS { u32 sum[4]; u32 npx; u32 pad[3]; };
+struct LeafR { i32 minx, maxx, miny, maxy; };
+struct EvRec { u32 parE, cnt, childU, arrive, a_wl, b_wu, carL, carU; };
+
+struct ImgMeta {
+    u32 leaf_begin;        // index of the image's first leaf in newlist
+    u32 notd_base;         // scan value (leaves not in D) at leaf_begin
+    u32 slots;             // clusters.len()
+    u32 live;              // slots with area > 0
+    u32 key_sum[4]; u32 key_cnt; i32 key_rect[4];   // clusters[0] under KeyingAction::Keep (builder.rs:330-334)
+    u32 pad[3];
+};
+
+struct Counters {
+    u32 ncand;             // candidate events
+    u32 live[2];           // boruvka: any live edge this round
+    u32 err;               // bit 0: unclean key colour, bit 1: stale-upleft resurrection
+    u32 kt;                // total leaves (all images)
+    u32 rounds;            // boruvka rounds executed
+    u32 pad[2];
+};
+
+struct Bufs {
+    u8 *flags; u32 *pc; LeafA *la; LeafS *ls; LeafR *lr; EvRec *ev;
+    u32 *cand; u32 *newlist; u32 *attr; ImgMeta *meta; Counters *ctr;
+};
+
+// --------------------------------------------------------------------------------------------------------------
+// pixel policies for K1
+struct ColorPolicy {
+    const u32 *rgba;       // RGBA8 packed little-endian: r | g<<8 | b<<16 | a<<24 (image/format.rs:29-33)
+    int shift, thres, diagonal, has_key;
+    u32 key;
+
+    __device__ __forceinline__ u32 load(u32 g) const { return __ldg(rgba + g); }
+    // color_same (color_clusters/runner.rs:116-129): alpha ignored
+    __device__ __forceinline__ bool same(u32 a, u32 b) const {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int x = (int)((a >> (8 * c)) & 255u) >> shift, y = (int)((b >> (8 * c)) & 255u) >> shift;
+            const int dlt = x - y;
+            if ((dlt < 0 ? -dlt : dlt) > thres) return false;
+        }
+        return true;
+    }
+    // builder.rs:286-354 restated as static predicates
+    __device__ __forceinline__ u32 classify(u32 c, u32 up, u32 left, u32 ul, bool vu, bool vl, u32 *err) const {
+        const bool vul = vu && vl;
+        const bool kc = has_key && c == key;
+        u32 f = 0;
+        if (has_key && !kc && same(c, key)) *err |= 1u;          // unclean key: order-dependent in the reference
+        const bool s_cu = vu && same(c, up), s_cl = vl && same(c, left), s_cul = vul && same(c, ul);
+        if (vul) {
+            const bool ku = has_key && up == key, kl = has_key && left == key;
+            if (!ku && !kl && same(left, up) && (diagonal || (s_cl && s_cu))) f |= F_M;
+        }
+        if (kc) return f | J_NONE | F_KEYED;
+        if (s_cu && s_cul) return f | J_UP;
+        if (s_cl && s_cul) return f | J_LEFT;
+        if (diagonal && s_cul) return f | J_UPLEFT;
+        return f | J_NEW;
+    }
+    __device__ __forceinline__ void stats(u32 c, u32 *s) const {
+        s[0] = c & 255u; s[1] = (c >> 8) & 255u; s[2] = (c >> 16) & 255u; s[3] = c >> 24;
+    }
+};
+
+struct BinaryPolicy {
+    const u32 *bits;       // bit_vec::BitVec storage, pixel i at word i/32 bit i%32; one image = ceil(n/32) words
+    u32 n, words_per_img;
+    int diagonal;
+    __device__ __forceinline__ u32 load(u32 g) const {
+        const u32 img = g / n, i = g - img * n;
+        return (__ldg(bits + (size_t)img * words_per_img + (i >> 5)) >> (i & 31)) & 1u;
+    }
+    // clusters.rs:279-326 as static predicates
+    __device__ __forceinline__ u32 classify(u32 v, u32 up, u32 left, u32 ul, bool vu, bool vl, u32 *) const {
+        const bool b_u = vu && up, b_l = vl && left, b_ul = vu && vl && ul;
+        u32 f = 0;
+        if ((v || diagonal) && b_u && b_l) f |= F_M;
+        if (!v) return f | J_NONE;
+        if (b_u) return f | J_UP;
+        if (b_l) return f | J_LEFT;
+        if (b_ul && diagonal) return f | J_UPLEFT;
+        return f | J_NEW;
+    }
+    __device__ __forceinline__ void stats(u32, u32 *s) const { s[0] = s[1] = s[2] = s[3] = 0; }
+};
+
+// --------------------------------------------------------------------------------------------------------------
+// K1: one CTA per TW x TH tile.
+constexpr int TW = 64, TH = 32, K1_THREADS = 256, K1_PPT = TW * TH / K1_THREADS;
+constexpr size_t K1_SMEM = (size_t)(TH + 1) * (TW + 1) * 4 + (size_t)TW * TH * 2 + (size_t)TW * TH;
+
+template <class P> __global__ void __launch_bounds__(K1_THREADS) k_edges_tile(Dims d, P pol, Bufs b) {
+    VCB_SMEM(u32, pix);
+    u16 *lp = (u16 *)(pix + (TH + 1) * (TW + 1));
+    u8 *fl = (u8 *)(lp + TW * TH);
+    const u32 tiles_x = (d.w + TW - 1) / TW, tiles_y = (d.h + TH - 1) / TH;
+    const u32 tile = blockIdx.x;
+    const u32 img = tile / (tiles_x * tiles_y), tr = tile % (tiles_x * tiles_y);
+    const u32 x0 = (tr % tiles_x) * TW, y0 = (tr / tiles_x) * TH;
+    const u32 base = img * d.n;
+
+    for (int idx = threadIdx.x; idx < (TH + 1) * (TW + 1); idx += K1_THREADS) {
+        const int ly = idx / (TW + 1), lx = idx % (TW + 1);
+        const i64 gy = (i64)y0 - 1 + ly, gx = (i64)x0 - 1 + lx;
+        u32 v = 0;
+        if (gy >= 0 && gx >= 0 && gy < d.h && gx < d.w) v = pol.load(base + (u32)gy * d.w + (u32)gx);
+        pix[idx] = v;
+    }
+    __syncthreads();
+
+    u32 err = 0;
+#pragma unroll
+    for (int k = 0; k < K1_PPT; ++k) {
+        const int i = threadIdx.x + k * K1_THREADS;
+        const int ly = i / TW, lx = i % TW;
+        const u32 gx = x0 + lx, gy = y0 + ly;
+        u32 f = J_NONE;
+        u16 l = (u16)i;
+        if (gx < d.w && gy < d.h) {
+            const u32 c = pix[(ly + 1) * (TW + 1) + lx + 1], up = pix[ly * (TW + 1) + lx + 1];
+            const u32 left = pix[(ly + 1) * (TW + 1) + lx], ul = pix[ly * (TW + 1) + lx];
+            f = pol.classify(c, up, left, ul, gy > 0, gx > 0, &err);
+            const u32 j = f & J_MASK;
+            if (j == J_UP && ly > 0) l = (u16)(i - TW);
+            else if (j == J_LEFT && lx > 0) l = (u16)(i - 1);
+            else if (j == J_UPLEFT && ly > 0 && lx > 0) l = (u16)(i - TW - 1);
+        }
+        fl[i] = (u8)f;
+        lp[i] = l;
+    }
+    __syncthreads();
+    // pointer jumping inside the tile: chains are at most TW+TH-1 long
+#pragma unroll 1
+    for (int it = 0; it < 7; ++it) {
+        u16 nv[K1_PPT];
+#pragma unroll
+        for (int k = 0; k < K1_PPT; ++k) {
+            const int i = threadIdx.x + k * K1_THREADS;
+            nv[k] = lp[lp[i]];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < K1_PPT; ++k) lp[threadIdx.x + k * K1_THREADS] = nv[k];
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < K1_PPT; ++k) {
+        const int i = threadIdx.x + k * K1_THREADS;
+        const int ly = i / TW, lx = i % TW;
+        const u32 gx = x0 + lx, gy = y0 + ly;
+        if (gx >= d.w || gy >= d.h) continue;
+        const u32 g = base + gy * d.w + gx;
+        const u32 f = fl[i], j = f & J_MASK;
+        b.flags[g] = (u8)f;
+        u32 root = NONE;
+        if (j != J_NONE) {
+            const int r = lp[i];
+            const u32 jr = fl[r] & J_MASK;
+            const u32 gr = base + (y0 + r / TW) * d.w + x0 + r % TW;
+            root = jr == J_NEW ? gr : jr == J_UP ? gr - d.w : jr == J_LEFT ? gr - 1 : gr - d.w - 1;
+        }
+        b.pc[g] = root;
+        if (j == J_NEW) {
+            LeafA a; a.ufp = g; a.best0 = NONE; a.best1 = NONE; a.parL = NONE; a.cnt = 1; a.death = NONE; a.label = 0; a.flabel = 0;
+            b.la[g] = a;
+            LeafS s; pol.stats(pix[(ly + 1) * (TW + 1) + lx + 1], s.sum); s.npx = 1; s.pad[0] = s.pad[1] = s.pad[2] = 0;
+            b.ls[g] = s;
+            LeafR r; r.minx = r.maxx = (i32)gx; r.miny = r.maxy = (i32)gy;
+            b.lr[g] = r;
+        }
+    }
+    if (err) atomicOr(&b.ctr->err, err);
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// K2: one thread per pixel.  pc[] -> provisional-cluster root (leaf id); candidate events.
+__device__ static __forceinline__ u32 pc_root(const u32 *pc, u32 q) {
+    u32 r = ldcg(pc + q);
+    while (true) {
+        const u32 t = ldcg(pc + r);
+        if (t == r) return r;
+        r = t;
+    }
+}
+
+constexpr int K2_THREADS = 256;
+__global__ void __launch_bounds__(K2_THREADS) k_flatten_events(Dims d, Bufs b) {
+    const u32 stride = gridDim.x * K2_THREADS;
+    const int lane = threadIdx.x & 31;
+    const u32 nloop = (d.N + stride - 1) / stride;
+    for (u32 it = 0; it < nloop; ++it) {
+        const u32 g = it * stride + blockIdx.x * K2_THREADS + threadIdx.x;
+        bool is_cand = false;
+        u32 ea = 0, eb = 0;
+        if (g < d.N) {
+            const u32 f = b.flags[g];
+            if ((f & J_MASK) != J_NONE) {
+                const u32 r = pc_root(b.pc, g);
+                stcg(b.pc + g, r);
+            }
+            if (f & F_M) {
+                // duplicate filter: the event one row up joined the same pair of provisional clusters earlier
+                const u32 fl = b.flags[g - 1], fu = b.flags[g - d.w];
+                const bool dup = (fl & J_MASK) == J_UP && (fu & J_MASK) == J_UP && (fu & F_M);
+                if (!dup) {
+                    ea = pc_root(b.pc, g - 1);
+                    eb = pc_root(b.pc, g - d.w);
+                    is_cand = ea != eb;
+                }
+            }
+        }
+        const u32 m = __ballot_sync(0xffffffffu, is_cand);
+        if (m) {
+            u32 pos = 0;
+            if (lane == __ffs((int)m) - 1) pos = atomicAdd(&b.ctr->ncand, (u32)__popc(m));
+            pos = __shfl_sync(0xffffffffu, pos, __ffs((int)m) - 1);
+            if (is_cand) {
+                b.cand[pos + __popc(m & ((1u << lane) - 1u))] = g;
+                EvRec e; e.parE = NONE; e.cnt = 0; e.childU = NONE; e.arrive = 0; e.a_wl = ea; e.b_wu = eb; e.carL = NONE; e.carU = NONE;
+                b.ev[g] = e;
+                b.flags[g] = (u8)(b.flags[g] | F_CAND);
+            }
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// K3: Boruvka minimum spanning forest over (leaves, candidate events), weight = event pixel index (= time; unique).
+// An event of the reference is effective (its two sides are different clusters when the scan reaches it) iff it is
+// an MSF edge.  Cooperative kernel: two grid syncs per round, O(log K) rounds.
+__device__ static __forceinline__ u32 uf_find(LeafA *la, u32 x) {
+    while (true) {
+        const u32 p = ldcg(&la[x].ufp);
+        if (p == x) return x;
+        const u32 gp = ldcg(&la[p].ufp);
+        if (gp == p) return p;
+        stcg(&la[x].ufp, gp);
+        x = gp;
+    }
+}
+
+constexpr int K3_THREADS = 256;
+__global__ void __launch_bounds__(K3_THREADS) k_boruvka(Bufs b) {
+    const u32 ncand = ldcg(&b.ctr->ncand);
+    const u32 tid = blockIdx.x * K3_THREADS + threadIdx.x, stride = gridDim.x * K3_THREADS;
+    u32 round = 0;
+    while (true) {
+        const int par = (int)(round & 1u);
+        if (tid == 0) stcg(&b.ctr->live[par ^ 1], 0u);
+        bool any = false;
+        for (u32 e = tid; e < ncand; e += stride) {
+            const u32 p = ldcg(b.cand + e);
+            if (p & TAG) continue;
+            EvRec *ev = b.ev + p;
+            const u32 ra = uf_find(b.la, ev->a_wl), rb = uf_find(b.la, ev->b_wu);
+            if (ra == rb) { b.cand[e] = p | TAG; continue; }
+            ev->a_wl = ra; ev->b_wu = rb;
+            u32 *ba = par ? &b.la[ra].best1 : &b.la[ra].best0, *bb = par ? &b.la[rb].best1 : &b.la[rb].best0;
+            atomicMin(ba, p); atomicMin(bb, p);
+            stcg(par ? &b.la[ra].best0 : &b.la[ra].best1, NONE);
+            stcg(par ? &b.la[rb].best0 : &b.la[rb].best1, NONE);
+            any = true;
+        }
+        if (any) stcg(&b.ctr->live[par], 1u);
+        __threadfence();
+        VCB_GRID_SYNC();
+        if (ldcg(&b.ctr->live[par]) == 0) break;
+        for (u32 e = tid; e < ncand; e += stride) {
+            const u32 p = ldcg(b.cand + e);
+            if (p & TAG) continue;
+            EvRec *ev = b.ev + p;
+            const u32 ra = ev->a_wl, rb = ev->b_wu;
+            const bool sa = ldcg(par ? &b.la[ra].best1 : &b.la[ra].best0) == p;
+            const bool sb = ldcg(par ? &b.la[rb].best1 : &b.la[rb].best0) == p;
+            if (sa || sb) {
+                if (sa && sb) { const u32 hi = ra > rb ? ra : rb, lo = ra > rb ? rb : ra; stcg(&b.la[hi].ufp, lo); }
+                else if (sa) stcg(&b.la[ra].ufp, rb);
+                else stcg(&b.la[rb].ufp, ra);
+                b.flags[p] = (u8)(b.flags[p] | F_MSF);
+                b.cand[e] = p | TAG;
+            }
+        }
+        __threadfence();
+        VCB_GRID_SYNC();
+        ++round;
+    }
+    if (tid == 0) b.ctr->rounds = round;
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// K4: Kruskal reconstruction tree by lock-free sorted-chain insertion.  Fact(f -> g): event g is an ancestor of node
+// f.  Every effective event g = (a, b) contributes Fact(leaf a -> g) and Fact(leaf b -> g).  par[f] always holds the
+// lightest ancestor of f known so far; inserting g above f either walks up (par[f] < g: g is also an ancestor of
+// par[f]) or installs g and re-inserts the displaced ancestor above g.  At quiescence par[] is the tree.
+__device__ static __forceinline__ void chain_insert(Bufs b, u32 leaf, u32 g) {
+    u32 *slot = &b.la[leaf].parL;
+    while (true) {
+        const u32 cur = ldcg(slot);
+        if (cur == g) return;
+        if (cur > g) {                                   // includes NONE
+            const u32 old = atomicMin(slot, g);
+            if (old == g) return;
+            if (old > g) {                               // installed g below `old`
+                if (old == NONE) return;
+                slot = &b.ev[g].parE; g = old;           // now insert `old` above g
+            } else {
+                slot = &b.ev[old].parE;                  // somebody installed a lighter ancestor first: walk up
+            }
+        } else {
+            slot = &b.ev[cur].parE;
+        }
+    }
+}
+
+constexpr int K4_THREADS = 256;
+__global__ void __launch_bounds__(K4_THREADS) k_chain_insert(Dims d, Bufs b) {
+    const u32 ncand = ldcg(&b.ctr->ncand);
+    const u32 stride = gridDim.x * K4_THREADS;
+    for (u32 t = blockIdx.x * K4_THREADS + threadIdx.x; t < 2 * ncand; t += stride) {
+        const u32 p = b.cand[t >> 1] & ~TAG;
+        if (!(b.flags[p] & F_MSF)) continue;
+        const u32 leaf = (t & 1u) ? b.pc[p - d.w] : b.pc[p - 1];
+        chain_insert(b, leaf, p);
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// K5: attribution.  One thread per (image, row segment, column); a warp covers 32 adjacent columns and walks down
+// its rows in lock step.  g(p) = highest ancestor of leaf(pc[p]) born no later than p; it is reached by climbing from
+// the node of the pixel's J-parent (the pixel above: kept in a register; the pixel to the left: warp shuffle).
+__device__ static __forceinline__ u32 node_par(const Bufs &b, u32 node) {
+    return (node & TAG) ? ldcg(&b.la[node & ~TAG].parL) : ldcg(&b.ev[node].parE);
+}
+__device__ static __forceinline__ u32 climb(const Bufs &b, u32 node, u32 bound) {   // parents born <= bound
+    while (true) {
+        const u32 q = node_par(b, node);
+        if (q > bound) return node;                      // NONE > anything
+        node = q;
+    }
+}
+
+struct LeafRun {
+    u32 leaf; u32 s[4]; u32 n; i32 miny, maxy;
+    __device__ __forceinline__ void flush(const Bufs &b, i32 x) {
+        if (leaf == NONE || n == 0) return;
+        LeafS *ls = b.ls + leaf;
+        if (s[0]) atomicAdd(&ls->sum[0], s[0]);
+        if (s[1]) atomicAdd(&ls->sum[1], s[1]);
+        if (s[2]) atomicAdd(&ls->sum[2], s[2]);
+        if (s[3]) atomicAdd(&ls->sum[3], s[3]);
+        atomicAdd(&ls->npx, n);
+        LeafR *lr = b.lr + leaf;
+        atomicMin(&lr->minx, x); atomicMax(&lr->maxx, x);
+        atomicMin(&lr->miny, miny); atomicMax(&lr->maxy, maxy);
+        n = 0;
+    }
+};
+
+constexpr int K5_THREADS = 128;
+template <class P, bool WRITE_ATTR>
+__global__ void __launch_bounds__(K5_THREADS) k_attribute(Dims d, P pol, Bufs b, u32 rows_per_seg, int keep_key) {
+    const u32 wpad = (d.w + 31) & ~31u;
+    const u32 nseg = (d.h + rows_per_seg - 1) / rows_per_seg;
+    const u64 total = (u64)d.nimg * nseg * wpad;
+    const u64 stride = (u64)gridDim.x * K5_THREADS;
+    const int lane = threadIdx.x & 31;
+    for (u64 t0 = (u64)blockIdx.x * K5_THREADS + threadIdx.x - lane; t0 < total; t0 += stride) {
+        const u64 t = t0 + lane;
+        const u32 x = (u32)(t % wpad);
+        const u32 seg = (u32)((t / wpad) % nseg), img = (u32)(t / ((u64)wpad * nseg));
+        const bool valid = x < d.w;
+        const u32 y0 = seg * rows_per_seg, y1 = (y0 + rows_per_seg < d.h) ? y0 + rows_per_seg : d.h;
+        u32 gprev = NONE;                                // node of the pixel above (NONE: unknown / keyed)
+        u32 run_node = NONE, run_cnt = 0;
+        LeafRun lr; lr.leaf = NONE; lr.n = 0; lr.s[0] = lr.s[1] = lr.s[2] = lr.s[3] = 0; lr.miny = 0; lr.maxy = 0;
+        u32 ks[4] = {0, 0, 0, 0}, kn = 0; i32 kminy = 0x7fffffff, kmaxy = -1;
+        for (u32 y = y0; y < y1; ++y) {
+            const u32 p = img * d.n + y * d.w + (valid ? x : 0);
+            const u32 f = valid ? b.flags[p] : (u32)J_NONE;
+            const u32 j = f & J_MASK;
+            u32 g = NONE;
+            // the up-side child of an effective event at p: climb the chain of pixel p-w to just below p
+            u32 upnode = gprev;
+            if (valid && (f & F_MSF)) {
+                if (upnode == NONE) upnode = b.pc[p - d.w] | TAG;
+                upnode = climb(b, upnode, p - 1);
+                stcg(&b.ev[p].childU, upnode);
+            }
+            const u32 gprev_left = __shfl_up_sync(0xffffffffu, gprev, 1);   // node of pixel (x-1, y-1), for UPLEFT
+            bool resolved = true;
+            if (valid && j != J_NONE) {
+                if (j == J_NEW) g = p | TAG;
+                else if (j == J_UP) g = climb(b, upnode != NONE ? upnode : (b.pc[p] | TAG), p);
+                else if (j == J_UPLEFT) g = climb(b, (lane > 0 && gprev_left != NONE) ? gprev_left : (b.pc[p] | TAG), p);
+                else if (lane == 0) g = climb(b, b.pc[p] | TAG, p);         // J_LEFT across the warp edge
+                else resolved = false;                                       // J_LEFT: wait for the lane to the left
+            }
+            while (true) {
+                const u32 gl = __shfl_up_sync(0xffffffffu, g, 1);
+                const int rl = __shfl_up_sync(0xffffffffu, (int)resolved, 1);
+                if (!resolved && rl) { g = climb(b, gl, p); resolved = true; }
+                if (__all_sync(0xffffffffu, resolved)) break;
+            }
+            if (valid) {
+                if (j == J_NONE) {
+                    if ((f & F_KEYED) && keep_key) {
+                        u32 s[4]; pol.stats(pol.load(p), s);
+                        ks[0] += s[0]; ks[1] += s[1]; ks[2] += s[2]; ks[3] += s[3]; kn++;
+                        if ((i32)y < kminy) kminy = (i32)y;
+                        kmaxy = (i32)y;
+                    }
+                } else {
+                    if (WRITE_ATTR) b.attr[p] = g;
+                    if (j != J_NEW) {
+                        if (g == run_node) run_cnt++;
+                        else {
+                            if (run_cnt) atomicAdd((run_node & TAG) ? &b.la[run_node & ~TAG].cnt : &b.ev[run_node].cnt, run_cnt);
+                            run_node = g; run_cnt = 1;
+                        }
+                        const u32 leaf = b.pc[p];
+                        if (leaf != lr.leaf) { lr.flush(b, (i32)x); lr.leaf = leaf; lr.miny = (i32)y; lr.s[0] = lr.s[1] = lr.s[2] = lr.s[3] = 0; }
+                        u32 s[4]; pol.stats(pol.load(p), s);
+                        lr.s[0] += s[0]; lr.s[1] += s[1]; lr.s[2] += s[2]; lr.s[3] += s[3]; lr.n++; lr.maxy = (i32)y;
+                    }
+                }
+            }
+            gprev = g;
+        }
+        if (run_cnt) atomicAdd((run_node & TAG) ? &b.la[run_node & ~TAG].cnt : &b.ev[run_node].cnt, run_cnt);
+        lr.flush(b, (i32)x);
+        if (kn) {
+            ImgMeta *m = b.meta + img;
+            atomicAdd(&m->key_sum[0], ks[0]); atomicAdd(&m->key_sum[1], ks[1]);
+            atomicAdd(&m->key_sum[2], ks[2]); atomicAdd(&m->key_sum[3], ks[3]);
+            atomicAdd(&m->key_cnt, kn);
+            atomicMin(&m->key_rect[0], (i32)x); atomicMax(&m->key_rect[1], (i32)x);
+            atomicMin(&m->key_rect[2], kminy); atomicMax(&m->key_rect[3], kmaxy);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// ordered compaction of NEW pixels (scan functor) -> newlist, per-image leaf_begin
+struct NewScan {
+    Dims d; Bufs b;
+    __device__ u32 count() const { return d.N; }
+    __device__ u32 value(u32 i) const { return (b.flags[i] & J_MASK) == J_NEW ? 1u : 0u; }
+    __device__ void emit(u32 i, u32 ex, u32 v) const {
+        if (v) b.newlist[ex] = i;
+        if (i % d.n == 0) b.meta[i / d.n].leaf_begin = ex;
+        if (i == d.N - 1) b.ctr->kt = ex + v;
+    }
+};
+
+// --------------------------------------------------------------------------------------------------------------
+// K6: tournament, bottom-up over the reconstruction tree (one thread per leaf; at every event the first arriving
+// child parks its (area, carrier) and leaves, the second one decides the winner and carries on).
+// builder.rs:313-325: `if area(left) <= area(up) { combine(left -> up) } else { combine(up -> left) }`.
+constexpr int K6_THREADS = 256;
+__global__ void __launch_bounds__(K6_THREADS) k_tournament(Dims d, Bufs b) {
+    const u32 kt = ldcg(&b.ctr->kt);
+    const u32 stride = gridDim.x * K6_THREADS;
+    for (u32 k = blockIdx.x * K6_THREADS + threadIdx.x; k < kt; k += stride) {
+        const u32 leaf = b.newlist[k];
+        u32 child = leaf | TAG, W = ldcg(&b.la[leaf].cnt), car = leaf;
+        u32 v = ldcg(&b.la[leaf].parL);
+        while (v != NONE) {
+            EvRec *e = b.ev + v;
+            const bool up = ldcg(&e->childU) == child;
+            if (up) { stcg(&e->b_wu, W); stcg(&e->carU, car); } else { stcg(&e->a_wl, W); stcg(&e->carL, car); }
+            __threadfence();
+            const u32 old = atomicAdd(&e->arrive, 1u);
+            if (old == 0) break;
+            __threadfence();
+            const u32 WL = up ? ldcg(&e->a_wl) : W, WU = up ? W : ldcg(&e->b_wu);
+            const u32 cL = up ? ldcg(&e->carL) : car, cU = up ? car : ldcg(&e->carU);
+            if (WL <= WU) {                               // left loses: its label dies as the left side
+                stcg(&b.la[cL].death, v | TAG);
+                car = cU;
+            } else {
+                stcg(&b.la[cU].death, v);
+                car = cL;
+                b.flags[v] = (u8)(b.flags[v] | F_LWIN);
+            }
+            // (a_wl, b_wu now hold both child areas; the listing pass reads them)
+            W = WL + WU + ldcg(&e->cnt);
+            child = v;
+            v = ldcg(&e->parE);
+        }
+        if (v == NONE) {                                  // reached the root of a final cluster
+            const u32 root = uf_find(b.la, leaf);
+            stcg(&b.la[root].best0, car);                 // carrier of the component (best0 is free after K3)
+            stcg(&b.la[root].best1, W);                   // final area
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// K7: numbering.  D = leaves whose label dies as the left side no later than the next NEW event (builder.rs:315-317:
+// the freed slot is handed to the next new cluster).  label = base + #{earlier leaves of the image not in D}.
+struct LabelScan {
+    Dims d; Bufs b;
+    __device__ u32 count() const { return ldcg(&b.ctr->kt); }
+    __device__ u32 value(u32 k) const {
+        const u32 p = b.newlist[k];
+        const u32 death = b.la[p].death;
+        if (death == NONE || !(death & TAG)) return 1u;
+        const u32 kt = ldcg(&b.ctr->kt);
+        const u32 img = p / d.n;
+        const bool has_next = k + 1 < kt && b.newlist[k + 1] / d.n == img;
+        if (!has_next) return 0u;
+        return (death & ~TAG) <= b.newlist[k + 1] ? 0u : 1u;
+    }
+    __device__ void emit(u32 k, u32 ex, u32 v) const {
+        const u32 p = b.newlist[k];
+        b.la[p].label = ex;
+        b.la[p].flabel = v;                               // not-in-D flag, consumed by k_image_meta
+        const u32 img = p / d.n;
+        if (k == b.meta[img].leaf_begin) b.meta[img].notd_base = ex;
+    }
+};
+
+// per image: slot count: base + #(leaves not in D) + [last leaf in D]
+__global__ void k_image_meta(Dims d, Bufs b, u32 base) {
+    const u32 img = blockIdx.x * blockDim.x + threadIdx.x;
+    if (img >= d.nimg) return;
+    const u32 kt = b.ctr->kt;
+    const u32 lb = b.meta[img].leaf_begin;
+    const u32 le = img + 1 < d.nimg ? b.meta[img + 1].leaf_begin : kt;
+    u32 slots = base;
+    if (le > lb) {
+        const u32 last = b.newlist[le - 1];
+        const u32 last_ex = b.la[last].label, last_notd = b.la[last].flabel;
+        slots = base + (last_ex + last_notd - b.meta[img].notd_base) + (last_notd ? 0u : 1u);
+    }
+    b.meta[img].slots = slots;
+}
+
+// per leaf: image-relative label
+constexpr int K8_THREADS = 256;
+__global__ void __launch_bounds__(K8_THREADS) k_leaf_labels(Dims d, Bufs b, u32 base) {
+    const u32 kt = ldcg(&b.ctr->kt);
+    const u32 stride = gridDim.x * K8_THREADS;
+    for (u32 k = blockIdx.x * K8_THREADS + threadIdx.x; k < kt; k += stride) {
+        const u32 p = b.newlist[k];
+        b.la[p].label = base + b.la[p].label - b.meta[p / d.n].notd_base;
+    }
+}
+// per leaf: label of the carrier of its final cluster
+__global__ void __launch_bounds__(K8_THREADS) k_leaf_final(Dims d, Bufs b) {
+    const u32 kt = ldcg(&b.ctr->kt);
+    const u32 stride = gridDim.x * K8_THREADS;
+    for (u32 k = blockIdx.x * K8_THREADS + threadIdx.x; k < kt; k += stride) {
+        const u32 p = b.newlist[k];
+        const u32 root = uf_find(b.la, p);
+        const u32 car = ldcg(&b.la[root].best0);
+        b.la[p].flabel = ldcg(&b.la[car].label);
+    }
+}
+// per pixel: cluster_indices (builder.rs:161; label 0 for keyed pixels, builder.rs:330-334)
+__global__ void __launch_bounds__(K8_THREADS) k_labels(Dims d, Bufs b, u32 *labels) {
+    const u32 stride = gridDim.x * K8_THREADS;
+    for (u32 g = blockIdx.x * K8_THREADS + threadIdx.x; g < d.N; g += stride) {
+        const u32 leaf = b.pc[g];
+        labels[g] = leaf == NONE ? 0u : b.la[leaf].flabel;
+    }
+}
+
+}  // namespace vcb

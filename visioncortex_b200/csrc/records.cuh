@@ -1,0 +1,123 @@
+// records.cuh — per-cluster records (north_star stage (3): area, bounding rect, colour sums), `clusters_output` for
+// hierarchical == 0 (color_clusters/builder.rs:366-377) and ClustersView::to_color_image (container.rs:104-116).
+#pragma once
+#include "../../include/vcb200.h"
+#include "ids.cuh"
+
+namespace vcb {
+
+constexpr int REC_THREADS = 256;
+
+// per slot: zero, rect sentinels for the atomic min/max accumulation
+__global__ void __launch_bounds__(REC_THREADS) k_rec_init(vcb_cluster_rec *rec, u32 total) {
+    const u32 stride = gridDim.x * REC_THREADS;
+    for (u32 s = blockIdx.x * REC_THREADS + threadIdx.x; s < total; s += stride) {
+        vcb_cluster_rec r;
+        for (int k = 0; k < 5; ++k) { r.sum[k] = 0; r.residue_sum[k] = 0; }
+        r.rect[0] = 0x7fffffff; r.rect[1] = 0x7fffffff; r.rect[2] = -1; r.rect[3] = -1;
+        r.num_holes = 0; r.depth = 0; r.merged_into = 0; r.indices_len = 0; r.indices_off = 0; r.holes_off = 0;
+        r.holes_len = 0; r._pad = 0;
+        rec[s] = r;
+    }
+}
+
+// per leaf: fold the provisional cluster's sums / rect into the slot of its final cluster (ColorSum::merge color.rs:278-284,
+// BoundingRect::merge bound.rs:204-219; both order-independent)
+__global__ void __launch_bounds__(REC_THREADS) k_rec_accum(Dims d, Bufs b, vcb_cluster_rec *rec, const u32 *slot_base) {
+    const u32 kt = ldcg(&b.ctr->kt);
+    const u32 stride = gridDim.x * REC_THREADS;
+    for (u32 k = blockIdx.x * REC_THREADS + threadIdx.x; k < kt; k += stride) {
+        const u32 p = b.newlist[k];
+        vcb_cluster_rec *r = rec + slot_base[p / d.n] + b.la[p].flabel;
+        const LeafS s = b.ls[p];
+        const LeafR q = b.lr[p];
+        if (s.sum[0]) atomicAdd(&r->sum[0], s.sum[0]);
+        if (s.sum[1]) atomicAdd(&r->sum[1], s.sum[1]);
+        if (s.sum[2]) atomicAdd(&r->sum[2], s.sum[2]);
+        if (s.sum[3]) atomicAdd(&r->sum[3], s.sum[3]);
+        atomicAdd(&r->sum[4], s.npx);
+        atomicMin(&r->rect[0], q.minx); atomicMin(&r->rect[1], q.miny);
+        atomicMax(&r->rect[2], q.maxx); atomicMax(&r->rect[3], q.maxy);
+    }
+}
+
+// per image: clusters[0] receives the keyed pixels under KeyingAction::Keep (builder.rs:330-334)
+__global__ void k_rec_key(Dims d, Bufs b, vcb_cluster_rec *rec, const u32 *slot_base) {
+    const u32 img = blockIdx.x * blockDim.x + threadIdx.x;
+    if (img >= d.nimg) return;
+    const ImgMeta m = b.meta[img];
+    if (m.key_cnt == 0) return;
+    vcb_cluster_rec *r = rec + slot_base[img];
+    for (int k = 0; k < 4; ++k) r->sum[k] = m.key_sum[k];
+    r->sum[4] = m.key_cnt;
+    r->rect[0] = m.key_rect[0]; r->rect[1] = m.key_rect[2]; r->rect[2] = m.key_rect[1]; r->rect[3] = m.key_rect[3];
+}
+
+// per slot: half-open rect, residue_sum = sum (prepare_stage_2, builder.rs:380-382), indices_len = area
+__global__ void __launch_bounds__(REC_THREADS) k_rec_final(vcb_cluster_rec *rec, u32 total) {
+    const u32 stride = gridDim.x * REC_THREADS;
+    for (u32 s = blockIdx.x * REC_THREADS + threadIdx.x; s < total; s += stride) {
+        vcb_cluster_rec *r = rec + s;
+        if (r->sum[4] == 0) { r->rect[0] = r->rect[1] = r->rect[2] = r->rect[3] = 0; }
+        else { r->rect[2] += 1; r->rect[3] += 1; }
+        for (int k = 0; k < 5; ++k) r->residue_sum[k] = r->sum[k];
+        r->indices_len = r->sum[4];
+    }
+}
+
+// indices_off: exclusive scan of indices_len inside each image; live count per image
+struct OffScan {
+    vcb_cluster_rec *rec; const u32 *slot_base; const u32 *slot_img; u32 total; u64 *img_off;
+    __device__ u32 count() const { return total; }
+    __device__ u32 value(u32 s) const { return rec[s].indices_len; }
+    __device__ void emit(u32 s, u32 ex, u32) const { rec[s].indices_off = ex; }   // global; rebased by k_off_rebase
+};
+__global__ void __launch_bounds__(REC_THREADS) k_off_rebase(vcb_cluster_rec *rec, const u32 *slot_base, const u32 *slot_img, u32 total) {
+    const u32 stride = gridDim.x * REC_THREADS;
+    for (u32 s = blockIdx.x * REC_THREADS + threadIdx.x; s < total; s += stride) {
+        const u32 first = slot_base[slot_img[s]];
+        if (s != first) rec[s].indices_off -= rec[first].indices_off;
+    }
+    // the first slot of every image is rebased last, by k_off_rebase0
+}
+__global__ void k_off_rebase0(vcb_cluster_rec *rec, const u32 *slot_base, u32 nimg) {
+    const u32 img = blockIdx.x * blockDim.x + threadIdx.x;
+    if (img < nimg) rec[slot_base[img]].indices_off = 0;
+}
+__global__ void __launch_bounds__(REC_THREADS) k_slot_img(u32 *slot_img, const u32 *slot_base, u32 nimg) {
+    // slot_img[s] = image owning slot s
+    const u32 img = blockIdx.x;
+    if (img >= nimg) return;
+    for (u32 s = slot_base[img] + threadIdx.x; s < slot_base[img + 1]; s += REC_THREADS) slot_img[s] = img;
+}
+
+// stage_1_output (builder.rs:366-377): slots with area > 0, stable sort by area * 65535 + index
+__global__ void __launch_bounds__(REC_THREADS) k_out_keys(const vcb_cluster_rec *rec, const u32 *slot_base, const u32 *slot_img,
+                                                          u32 total, int key_bits, u64 *keys, u32 *vals, u32 *live) {
+    const u32 stride = gridDim.x * REC_THREADS;
+    for (u32 s = blockIdx.x * REC_THREADS + threadIdx.x; s < total; s += stride) {
+        const u32 img = slot_img[s], idx = s - slot_base[img];
+        const u64 area = rec[s].indices_len;
+        u64 key = area ? area * 65535ull + idx : ((1ull << key_bits) - 1ull);
+        keys[s] = ((u64)img << key_bits) | key;
+        vals[s] = idx;
+        if (area) atomicAdd(&live[img], 1u);
+    }
+}
+
+// ClustersView::to_color_image for hierarchical == 0: every pixel belongs to exactly one output cluster (its own);
+// residue_color = residue_sum.average() (cluster.rs:42-44, color.rs:295-302).  Keyed pixels under Discard stay 0.
+__global__ void __launch_bounds__(REC_THREADS) k_color_image_flat(u32 n, const u32 *labels, const vcb_cluster_rec *rec, u32 *out) {
+    const u32 stride = gridDim.x * REC_THREADS;
+    for (u32 g = blockIdx.x * REC_THREADS + threadIdx.x; g < n; g += stride) {
+        const vcb_cluster_rec *r = rec + labels[g];
+        u32 c = 0;
+        const u32 cnt = r->residue_sum[4];
+        if (r->indices_len && cnt)
+            c = ((r->residue_sum[0] / cnt) & 255u) | (((r->residue_sum[1] / cnt) & 255u) << 8) |
+                (((r->residue_sum[2] / cnt) & 255u) << 16) | (((r->residue_sum[3] / cnt) & 255u) << 24);
+        out[g] = c;
+    }
+}
+
+}  // namespace vcb

@@ -1,0 +1,137 @@
+// rt.h — thin runtime layer under the kernels: CUDA runtime for the product build (nvcc, sm_100a); the test-only
+// host simulator (tests/hostsim/cudasim.h, -DVCB_HOSTSIM) for debugging the same kernel sources without a GPU.
+// The product library is only ever built WITHOUT VCB_HOSTSIM; there is no CPU execution path in it.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <tuple>
+#include <utility>
+#include <vector>
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int32_t i32;
+typedef int64_t i64;
+
+#ifdef VCB_HOSTSIM
+#include "cudasim.h"
+typedef int cudaError_t;
+typedef struct SimStream *cudaStream_t;
+#define cudaSuccess 0
+#define VCB_SMEM(T, name) T *name = (T *)sim::smem_ptr()
+#define VCB_GRID_SYNC() sim::tc.grid_bar->arrive_and_wait()
+template <class T> __device__ static inline T ldcg(const T *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+template <class T> __device__ static inline void stcg(T *p, T v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
+__device__ static inline u8 ldcg8(const u8 *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+#else
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#define VCB_SMEM(T, name)                                      \
+    extern __shared__ __align__(16) unsigned char _vcb_smem[]; \
+    T *name = reinterpret_cast<T *>(_vcb_smem)
+#define VCB_GRID_SYNC() cooperative_groups::this_grid().sync()
+template <class T> __device__ static __forceinline__ T ldcg(const T *p) { return __ldcg(p); }
+template <class T> __device__ static __forceinline__ void stcg(T *p, T v) { __stcg(p, v); }
+__device__ static __forceinline__ u8 ldcg8(const u8 *p) { return __ldcg(p); }
+#endif
+
+namespace rt {
+
+enum LaunchMode { SEQ = 0, THR = 1, COOP = 2 };   // only meaningful to the simulator (COOP also selects a cooperative launch)
+
+struct ProfEntry {
+    const char *name;
+#ifndef VCB_HOSTSIM
+    cudaEvent_t e0, e1;
+#endif
+};
+
+struct Stream {
+    cudaStream_t s = nullptr;
+    u64 launches = 0;
+    bool profiling = false;
+    std::vector<ProfEntry> prof;
+    int last_error = 0;
+    std::string last_error_text;
+};
+
+#ifdef VCB_HOSTSIM
+inline int device_count() { return 1; }
+inline int set_device(int) { return 0; }
+inline int sm_count(int) { return 2; }
+inline void *dev_malloc(size_t n) { return std::malloc(n ? n : 1); }
+inline void dev_free(void *p) { std::free(p); }
+inline void *host_malloc(size_t n) { return std::malloc(n ? n : 1); }
+inline void host_free(void *p) { std::free(p); }
+inline int stream_create(Stream &) { return 0; }
+inline void stream_destroy(Stream &) {}
+inline int stream_sync(Stream &) { return 0; }
+inline int copy_h2d(Stream &, void *d, const void *h, size_t n) { std::memcpy(d, h, n); return 0; }
+inline int copy_d2h(Stream &, void *h, const void *d, size_t n) { std::memcpy(h, d, n); return 0; }
+inline int copy_d2d(Stream &, void *d, const void *s, size_t n) { std::memcpy(d, s, n); return 0; }
+inline int fill(Stream &, void *d, int byte, size_t n) { std::memset(d, byte, n); return 0; }
+inline const char *error_string(int) { return "sim"; }
+inline int max_coop_blocks(const void *, int, size_t, int) { return 2; }
+
+template <class... KArgs, class... Args>
+inline void launch(Stream &st, const char *name, LaunchMode mode, void (*k)(KArgs...), dim3 grid, dim3 block,
+                   size_t smem, Args... args) {
+    (void)name;
+    st.launches++;
+    std::tuple<KArgs...> t(args...);
+    static const bool force_thr = std::getenv("VCB_SIM_FORCE_THR") != nullptr;   // exercise real races in the simulator
+    if (force_thr && mode == SEQ) mode = THR;
+    sim::launch(grid, block, smem, (int)mode, [&] { std::apply(k, t); });
+}
+#else
+inline int device_count() { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+inline int set_device(int d) { return (int)cudaSetDevice(d); }
+inline int sm_count(int d) { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }
+inline void *dev_malloc(size_t n) { void *p = nullptr; if (cudaMalloc(&p, n ? n : 1) != cudaSuccess) return nullptr; return p; }
+inline void dev_free(void *p) { if (p) cudaFree(p); }
+inline void *host_malloc(size_t n) { void *p = nullptr; if (cudaMallocHost(&p, n ? n : 1) != cudaSuccess) return nullptr; return p; }
+inline void host_free(void *p) { if (p) cudaFreeHost(p); }
+inline int stream_create(Stream &st) { return (int)cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking); }
+inline void stream_destroy(Stream &st) { if (st.s) cudaStreamDestroy(st.s); st.s = nullptr; }
+inline int stream_sync(Stream &st) { return (int)cudaStreamSynchronize(st.s); }
+inline int copy_h2d(Stream &st, void *d, const void *h, size_t n) { return (int)cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, st.s); }
+inline int copy_d2h(Stream &st, void *h, const void *d, size_t n) { return (int)cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, st.s); }
+inline int copy_d2d(Stream &st, void *d, const void *s, size_t n) { return (int)cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st.s); }
+inline int fill(Stream &st, void *d, int byte, size_t n) { return (int)cudaMemsetAsync(d, byte, n, st.s); }
+inline const char *error_string(int e) { return cudaGetErrorString((cudaError_t)e); }
+inline int max_coop_blocks(const void *k, int threads, size_t smem, int dev) {
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem);
+    return per_sm * sm_count(dev);
+}
+
+template <class... KArgs, class... Args>
+inline void launch(Stream &st, const char *name, LaunchMode mode, void (*k)(KArgs...), dim3 grid, dim3 block,
+                   size_t smem, Args... args) {
+    st.launches++;
+    ProfEntry pe{name, nullptr, nullptr};
+    if (st.profiling) {
+        cudaEventCreate(&pe.e0); cudaEventCreate(&pe.e1);
+        cudaEventRecord(pe.e0, st.s);
+    }
+    if (mode == COOP) {
+        std::tuple<KArgs...> t(args...);
+        void *ptrs[sizeof...(KArgs) ? sizeof...(KArgs) : 1];
+        size_t i = 0;
+        std::apply([&](auto &...a) { ((ptrs[i++] = (void *)&a), ...); }, t);
+        cudaError_t e = cudaLaunchCooperativeKernel((const void *)k, grid, block, ptrs, smem, st.s);
+        if (e != cudaSuccess && !st.last_error) { st.last_error = (int)e; st.last_error_text = std::string(name) + ": " + cudaGetErrorString(e); }
+    } else {
+        k<<<grid, block, smem, st.s>>>(KArgs(args)...);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess && !st.last_error) { st.last_error = (int)e; st.last_error_text = std::string(name) + ": " + cudaGetErrorString(e); }
+    }
+    if (st.profiling) { cudaEventRecord(pe.e1, st.s); st.prof.push_back(pe); }
+}
+#endif
+
+}  // namespace rt

@@ -1,0 +1,351 @@
+// vcb200.cu — the C ABI of include/vcb200.h over the sm_100a kernels.  No CPU compute path exists in this library:
+// every entry point that produces results launches kernels on the context's device and fails if there is none.
+#include "engine.cuh"
+
+#include <algorithm>
+#include <mutex>
+#include <new>
+
+using namespace vcb;
+
+struct vcb_clusters {
+    std::shared_ptr<BatchResult> br;
+    u32 img = 0;
+    // lazily fetched host copies
+    std::vector<vcb_cluster_rec> h_rec;
+    bool have_rec = false;
+};
+
+struct vcb_bin_clusters {
+    std::shared_ptr<BatchResult> br;
+    u32 img = 0;
+};
+
+namespace {
+
+int fail(vcb_ctx *c, int code, const std::string &msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+int check_stream(vcb_ctx *c) {
+    if (rt::stream_sync(c->st) != 0 || c->st.last_error) {
+        c->err = c->st.last_error ? c->st.last_error_text : std::string("stream synchronize failed");
+        c->st.last_error = 0;
+        return VCB_ERR_CUDA;
+    }
+    return VCB_OK;
+}
+
+int validate_cfg(vcb_ctx *c, const vcb_runner_config *cfg) {
+    if (!cfg) return fail(c, VCB_ERR_INVALID_ARG, "null config");
+    // assert!(is_same_color_a < 8) (runner.rs:78); a negative shift would be an overflow panic in the reference
+    if (cfg->is_same_color_a < 0 || cfg->is_same_color_a >= 8) return fail(c, VCB_ERR_INVALID_ARG, "is_same_color_a must be in 0..8");
+    if (cfg->batch_size == 0) return fail(c, VCB_ERR_INVALID_ARG, "batch_size == 0 never terminates in the reference");
+    return VCB_OK;
+}
+
+int fetch_records(vcb_clusters *h) {
+    if (h->have_rec) return VCB_OK;
+    BatchResult *br = h->br.get();
+    vcb_ctx *c = br->ctx;
+    const u32 s0 = br->slot_base[h->img], s1 = br->slot_base[h->img + 1];
+    h->h_rec.resize(s1 - s0);
+    rt::copy_d2h(c->st, h->h_rec.data(), br->rec + s0, (size_t)(s1 - s0) * sizeof(vcb_cluster_rec));
+    const int e = check_stream(c);
+    if (e) return e;
+    h->have_rec = true;
+    return VCB_OK;
+}
+
+// colour path on device-resident images
+int run_color_device(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w, u32 h, size_t nimg,
+                     vcb_clusters **out) {
+    int e = validate_cfg(c, cfg);
+    if (e) return e;
+    if (!out) return fail(c, VCB_ERR_INVALID_ARG, "null output");
+    if (nimg == 0) return VCB_OK;
+    const u64 n64 = (u64)w * h;
+    if (n64 == 0 || n64 * nimg >= 0x7fffff00ull) return fail(c, VCB_ERR_INVALID_ARG, "width*height*n must be in 1..2^31");
+    if (!d_rgba) return fail(c, VCB_ERR_INVALID_ARG, "null image");
+    if (cfg->diagonal) return fail(c, VCB_ERR_UNSUPPORTED, "diagonal=true colour clustering (stale-upleft quirk) is fenced, see DESIGN.md");
+    if (cfg->hierarchical != 0) return fail(c, VCB_ERR_UNSUPPORTED, "hierarchical stage not built yet");
+    rt::set_device(c->device);
+    Dims d{w, h, (u32)n64, (u32)nimg, (u32)(n64 * nimg)};
+    e = ensure_workspace(c, d.N, d.nimg);
+    if (e) return fail(c, e, "device out of memory (workspace)");
+
+    auto br = std::make_shared<BatchResult>();
+    br->ctx = c; br->d = d; br->cfg = *cfg;
+    br->labels = (u32 *)rt::dev_malloc((size_t)d.N * sizeof(u32));
+    if (!br->labels) return fail(c, VCB_ERR_NOMEM, "device out of memory (labels)");
+
+    ColorPolicy pol;
+    pol.rgba = (const u32 *)d_rgba;
+    pol.shift = cfg->is_same_color_a; pol.thres = cfg->is_same_color_b; pol.diagonal = cfg->diagonal != 0;
+    pol.key = (u32)cfg->key_color[0] | ((u32)cfg->key_color[1] << 8) | ((u32)cfg->key_color[2] << 16) | ((u32)cfg->key_color[3] << 24);
+    pol.has_key = pol.key != 0;
+    const bool keep = pol.has_key && cfg->keying_action == VCB_KEYING_KEEP;
+
+    std::vector<ImgMeta> meta;
+    Counters ctr{};
+    e = run_stage1(c, d, pol, 1u, false, keep ? 1 : 0, br.get(), meta, ctr);
+    if (e) return e;
+    if (ctr.err & 1u) return fail(c, VCB_ERR_UNSUPPORTED, "key colour is not clean: a non-key pixel is color_same to the key (order-dependent in the reference)");
+    e = build_records(c, d, meta, br.get(), cfg->hierarchical == 0, keep);
+    if (e) return e;
+    for (size_t i = 0; i < nimg; ++i) {
+        vcb_clusters *hd = new (std::nothrow) vcb_clusters();
+        if (!hd) return fail(c, VCB_ERR_NOMEM, "host out of memory");
+        hd->br = br; hd->img = (u32)i;
+        out[i] = hd;
+    }
+    return VCB_OK;
+}
+
+u8 *stage_input(vcb_ctx *c, size_t bytes) {
+    if (bytes > c->d_stage_cap) {
+        rt::dev_free(c->d_stage);
+        c->d_stage = (u8 *)rt::dev_malloc(bytes);
+        c->d_stage_cap = c->d_stage ? bytes : 0;
+    }
+    return c->d_stage;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *vcb_strerror(int status) {
+    switch (status) {
+        case VCB_OK: return "ok";
+        case VCB_ERR_INVALID_ARG: return "invalid argument";
+        case VCB_ERR_LABEL_OVERFLOW: return "overflow";
+        case VCB_ERR_UNSUPPORTED: return "unsupported input";
+        case VCB_ERR_CUDA: return "CUDA error";
+        case VCB_ERR_NCCL: return "NCCL error";
+        case VCB_ERR_NOMEM: return "out of memory";
+        default: return "unknown status";
+    }
+}
+
+const char *vcb_last_error(const vcb_ctx *ctx) { return ctx ? ctx->err.c_str() : ""; }
+uint32_t vcb_abi_version(void) { return 1; }
+
+void vcb_runner_config_default(vcb_runner_config *cfg) {   // runner.rs:23-39
+    if (!cfg) return;
+    cfg->diagonal = 0; cfg->hierarchical = VCB_HIERARCHICAL_MAX; cfg->batch_size = 25600;
+    cfg->good_min_area = 16; cfg->good_max_area = 256 * 256;
+    cfg->is_same_color_a = 4; cfg->is_same_color_b = 1; cfg->deepen_diff = 64; cfg->hollow_neighbours = 1;
+    cfg->key_color[0] = cfg->key_color[1] = cfg->key_color[2] = cfg->key_color[3] = 0;
+    cfg->keying_action = VCB_KEYING_KEEP;
+}
+
+int vcb_ctx_create(int device, vcb_ctx **out) {
+    if (!out) return VCB_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (device < 0 || device >= rt::device_count()) return VCB_ERR_CUDA;   // no device, no library: there is no CPU path
+    if (rt::set_device(device) != 0) return VCB_ERR_CUDA;
+    vcb_ctx *c = new (std::nothrow) vcb_ctx();
+    if (!c) return VCB_ERR_NOMEM;
+    c->device = device;
+    c->sms = rt::sm_count(device);
+    if (rt::stream_create(c->st) != 0) { delete c; return VCB_ERR_CUDA; }
+    *out = c;
+    return VCB_OK;
+}
+
+void vcb_ctx_destroy(vcb_ctx *c) {
+    if (!c) return;
+    rt::set_device(c->device);
+    rt::stream_sync(c->st);
+    Bufs &b = c->b;
+    rt::dev_free(b.flags); rt::dev_free(b.pc); rt::dev_free(b.la); rt::dev_free(b.ls); rt::dev_free(b.lr); rt::dev_free(b.ev);
+    rt::dev_free(b.cand); rt::dev_free(b.newlist); rt::dev_free(b.attr); rt::dev_free(b.meta); rt::dev_free(b.ctr);
+    rt::dev_free(c->chunksum); rt::dev_free(c->rs_table); rt::dev_free(c->sk0); rt::dev_free(c->sk1);
+    rt::dev_free(c->sv0); rt::dev_free(c->sv1); rt::dev_free(c->d_small); rt::dev_free(c->d_stage);
+    rt::host_free(c->h_pinned);
+    rt::stream_destroy(c->st);
+    delete c;
+}
+
+int vcb_ctx_device(const vcb_ctx *c) { return c ? c->device : -1; }
+
+int vcb_runner_run_device(vcb_ctx *c, const vcb_runner_config *cfg, const uint8_t *d_rgba, uint32_t width,
+                          uint32_t height, size_t n, vcb_clusters **out) {
+    if (!c) return VCB_ERR_INVALID_ARG;
+    return run_color_device(c, cfg, d_rgba, width, height, n, out);
+}
+
+int vcb_runner_run(vcb_ctx *c, const vcb_runner_config *cfg, const uint8_t *rgba, uint32_t width, uint32_t height,
+                   vcb_clusters **out) {
+    if (!c) return VCB_ERR_INVALID_ARG;
+    if (!out) return fail(c, VCB_ERR_INVALID_ARG, "null output");
+    *out = nullptr;
+    int e = validate_cfg(c, cfg);
+    if (e) return e;
+    const size_t bytes = (size_t)width * height * 4;
+    if (bytes == 0 || !rgba) return fail(c, VCB_ERR_INVALID_ARG, "empty image");
+    rt::set_device(c->device);
+    u8 *d = stage_input(c, bytes);
+    if (!d) return fail(c, VCB_ERR_NOMEM, "device out of memory (input)");
+    rt::copy_h2d(c->st, d, rgba, bytes);
+    return run_color_device(c, cfg, d, width, height, 1, out);
+}
+
+int vcb_runner_run_batch(vcb_ctx *c, const vcb_runner_config *cfg, const uint8_t *const *rgba, const uint32_t *width,
+                         const uint32_t *height, size_t n, vcb_clusters **out) {
+    if (!c) return VCB_ERR_INVALID_ARG;
+    if (!rgba || !width || !height || !out) return fail(c, VCB_ERR_INVALID_ARG, "null argument");
+    int e = validate_cfg(c, cfg);
+    if (e) return e;
+    rt::set_device(c->device);
+    // runs of equally sized images are processed as one device batch
+    size_t i = 0;
+    while (i < n) {
+        size_t j = i + 1;
+        const size_t bytes = (size_t)width[i] * height[i] * 4;
+        while (j < n && width[j] == width[i] && height[j] == height[i] && (j - i + 1) * (bytes / 4) < 0x30000000ull) ++j;
+        if (bytes == 0) return fail(c, VCB_ERR_INVALID_ARG, "empty image");
+        u8 *d = stage_input(c, bytes * (j - i));
+        if (!d) return fail(c, VCB_ERR_NOMEM, "device out of memory (input)");
+        for (size_t k = i; k < j; ++k) {
+            if (!rgba[k]) return fail(c, VCB_ERR_INVALID_ARG, "null image");
+            rt::copy_h2d(c->st, d + (k - i) * bytes, rgba[k], bytes);
+        }
+        e = run_color_device(c, cfg, d, width[i], height[i], j - i, out + i);
+        if (e) return e;
+        i = j;
+    }
+    return VCB_OK;
+}
+
+int vcb_clusters_info_get(const vcb_clusters *hc, vcb_clusters_info *info) {
+    if (!hc || !info) return VCB_ERR_INVALID_ARG;
+    vcb_clusters *h = const_cast<vcb_clusters *>(hc);
+    int e = fetch_records(h);
+    if (e) return e;
+    const BatchResult *br = h->br.get();
+    info->width = br->d.w; info->height = br->d.h;
+    info->num_slots = (u32)h->h_rec.size();
+    info->num_outputs = br->nout[h->img];
+    u64 it = 0, ht = 0;
+    if (!h->h_rec.empty()) {
+        const vcb_cluster_rec &l = h->h_rec.back();
+        it = l.indices_off + l.indices_len; ht = l.holes_off + l.holes_len;
+    }
+    info->indices_total = it; info->holes_total = ht;
+    return VCB_OK;
+}
+
+int vcb_clusters_cluster_indices(const vcb_clusters *h, uint32_t *out) {
+    if (!h || !out) return VCB_ERR_INVALID_ARG;
+    const BatchResult *br = h->br.get();
+    rt::copy_d2h(br->ctx->st, out, br->labels + (size_t)h->img * br->d.n, (size_t)br->d.n * 4);
+    return check_stream(br->ctx);
+}
+
+int vcb_clusters_outputs(const vcb_clusters *h, uint32_t *out) {
+    if (!h) return VCB_ERR_INVALID_ARG;
+    const BatchResult *br = h->br.get();
+    const u32 n = br->nout[h->img];
+    if (n == 0) return VCB_OK;
+    if (!out) return VCB_ERR_INVALID_ARG;
+    rt::copy_d2h(br->ctx->st, out, br->outputs + br->slot_base[h->img], (size_t)n * 4);
+    return check_stream(br->ctx);
+}
+
+int vcb_clusters_records(const vcb_clusters *hc, vcb_cluster_rec *out) {
+    if (!hc || !out) return VCB_ERR_INVALID_ARG;
+    vcb_clusters *h = const_cast<vcb_clusters *>(hc);
+    int e = fetch_records(h);
+    if (e) return e;
+    std::copy(h->h_rec.begin(), h->h_rec.end(), out);
+    return VCB_OK;
+}
+
+int vcb_clusters_indices_pool(const vcb_clusters *h, uint32_t *out) {
+    if (!h || !out) return VCB_ERR_INVALID_ARG;
+    return fail(h->br->ctx, VCB_ERR_UNSUPPORTED, "indices pool not built yet");
+}
+
+int vcb_clusters_holes_pool(const vcb_clusters *h, uint32_t *out) {
+    if (!h) return VCB_ERR_INVALID_ARG;
+    (void)out;
+    return VCB_OK;   // hierarchical == 0: no holes
+}
+
+int vcb_clusters_to_color_image(const vcb_clusters *h, uint8_t *rgba_out) {
+    if (!h || !rgba_out) return VCB_ERR_INVALID_ARG;
+    const BatchResult *br = h->br.get();
+    vcb_ctx *c = br->ctx;
+    rt::set_device(c->device);
+    const u32 n = br->d.n;
+    u8 *d = stage_input(c, (size_t)n * 4);
+    if (!d) return fail(c, VCB_ERR_NOMEM, "device out of memory");
+    rt::launch(c->st, "k_color_image_flat", rt::SEQ, k_color_image_flat, dim3(grid_for(c, n, REC_THREADS, 16)), dim3(REC_THREADS), 0,
+               n, (const u32 *)(br->labels + (size_t)h->img * n), (const vcb_cluster_rec *)(br->rec + br->slot_base[h->img]), (u32 *)d);
+    rt::copy_d2h(c->st, rgba_out, d, (size_t)n * 4);
+    return check_stream(c);
+}
+
+const uint32_t *vcb_clusters_device_labels(const vcb_clusters *h) {
+    if (!h) return nullptr;
+    return h->br->labels + (size_t)h->img * h->br->d.n;
+}
+
+void vcb_clusters_free(vcb_clusters *h) { delete h; }
+
+int vcb_binary_to_clusters_device(vcb_ctx *c, const uint32_t *d_bits, uint32_t width, uint32_t height, int diagonal,
+                                  vcb_bin_clusters **out) {
+    (void)d_bits; (void)width; (void)height; (void)diagonal; (void)out;
+    return fail(c, VCB_ERR_UNSUPPORTED, "binary path not built yet");
+}
+
+int vcb_binary_to_clusters(vcb_ctx *c, const uint32_t *bits, uint32_t width, uint32_t height, int diagonal,
+                           vcb_bin_clusters **out) {
+    (void)bits; (void)width; (void)height; (void)diagonal; (void)out;
+    return fail(c, VCB_ERR_UNSUPPORTED, "binary path not built yet");
+}
+
+int vcb_bin_clusters_info_get(const vcb_bin_clusters *h, vcb_bin_clusters_info *info) { (void)h; (void)info; return VCB_ERR_UNSUPPORTED; }
+int vcb_bin_clusters_records(const vcb_bin_clusters *h, vcb_bin_cluster_rec *out) { (void)h; (void)out; return VCB_ERR_UNSUPPORTED; }
+int vcb_bin_clusters_points(const vcb_bin_clusters *h, int32_t *xy) { (void)h; (void)xy; return VCB_ERR_UNSUPPORTED; }
+void vcb_bin_clusters_free(vcb_bin_clusters *h) { delete h; }
+
+int vcb_ctx_synchronize(vcb_ctx *c) {
+    if (!c) return VCB_ERR_INVALID_ARG;
+    return check_stream(c);
+}
+
+uint64_t vcb_ctx_kernel_launches(const vcb_ctx *c) { return c ? c->st.launches : 0; }
+
+int vcb_ctx_profile_reset(vcb_ctx *c, int enable) {
+    if (!c) return VCB_ERR_INVALID_ARG;
+    rt::stream_sync(c->st);
+#ifndef VCB_HOSTSIM
+    for (auto &p : c->st.prof) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+#endif
+    c->st.prof.clear();
+    c->st.profiling = enable != 0;
+    return VCB_OK;
+}
+
+int vcb_ctx_profile_read(vcb_ctx *c, const char *kernel_name, double *total_ms, uint64_t *launches) {
+    if (!c || !total_ms || !launches) return VCB_ERR_INVALID_ARG;
+    rt::stream_sync(c->st);
+    double t = 0; uint64_t n = 0;
+#ifndef VCB_HOSTSIM
+    for (auto &p : c->st.prof) {
+        if (kernel_name && kernel_name[0] && std::strcmp(kernel_name, p.name) != 0) continue;
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) { t += ms; ++n; }
+    }
+#else
+    (void)kernel_name;
+#endif
+    *total_ms = t; *launches = n;
+    return VCB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,109 @@
+"""Context / result wrappers over the C ABI (include/vcb200.h).
+
+`Context(device)` opens the CUDA product library (``csrc/libvcb200.so``) on one GPU.  There is no CPU fallback: if the
+library is missing or no CUDA device can be opened this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import BinClustersInfoC, ClustersInfoC, Library, RunnerConfigC, VcbError, pack_bits
+
+
+def make_config(**kw) -> RunnerConfigC:
+    """RunnerConfig::default() (color_clusters/runner.rs:23-39) with overrides."""
+    cfg = RunnerConfigC()
+    cfg.diagonal = 0
+    cfg.hierarchical = _ffi.HIERARCHICAL_MAX
+    cfg.batch_size = 25600
+    cfg.good_min_area = 16
+    cfg.good_max_area = 256 * 256
+    cfg.is_same_color_a = 4
+    cfg.is_same_color_b = 1
+    cfg.deepen_diff = 64
+    cfg.hollow_neighbours = 1
+    cfg.keying_action = _ffi.KEEP
+    for k, v in kw.items():
+        if k == "key_color":
+            for i in range(4):
+                cfg.key_color[i] = int(v[i])
+        else:
+            if not hasattr(cfg, k):
+                raise TypeError(f"unknown RunnerConfig field {k}")
+            setattr(cfg, k, v)
+    return cfg
+
+
+class Context:
+    def __init__(self, device: int = 0, lib: Library | None = None):
+        self.lib = lib or Library()
+        self.handle = C.c_void_p()
+        st = self.lib.fn("ctx_create")(int(device), C.byref(self.handle))
+        if st != 0:
+            raise VcbError(st, self.lib.strerror(st) + f": cannot open CUDA device {device} (there is no CPU fallback)")
+
+    def close(self):
+        if self.handle:
+            self.lib.fn("ctx_destroy")(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- color_clusters::Runner::run
+    def runner_run_handle(self, rgba: np.ndarray, cfg: RunnerConfigC):
+        rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+        h, w = rgba.shape[:2]
+        out = C.c_void_p()
+        st = self.lib.fn("runner_run")(self.handle, C.byref(cfg), rgba.ctypes.data_as(C.c_void_p), w, h, C.byref(out))
+        self.lib.check(st, self.handle)
+        return out
+
+    def runner_run(self, rgba: np.ndarray, cfg: RunnerConfigC, pools: bool = True, color_image: bool = False) -> dict:
+        handle = self.runner_run_handle(rgba, cfg)
+        try:
+            res = self.lib.read_clusters(handle, pools=pools, free=False, ctx=self.handle)
+            if color_image:
+                h, w = rgba.shape[:2]
+                img = np.empty((h, w, 4), dtype=np.uint8)
+                self.lib.check(self.lib.fn("clusters_to_color_image")(handle, img.ctypes.data_as(C.c_void_p)), self.handle)
+                res["color_image"] = img
+        finally:
+            self.lib.fn("clusters_free")(handle)
+        return res
+
+    def runner_run_batch(self, images, cfg: RunnerConfigC, pools: bool = False) -> list:
+        imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+        n = len(imgs)
+        ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+        ws = (C.c_uint32 * n)(*[im.shape[1] for im in imgs])
+        hs = (C.c_uint32 * n)(*[im.shape[0] for im in imgs])
+        outs = (C.c_void_p * n)()
+        st = self.lib.fn("runner_run_batch")(self.handle, C.byref(cfg), ptrs, ws, hs, n, outs)
+        self.lib.check(st, self.handle)
+        res = []
+        for k in range(n):
+            res.append(self.lib.read_clusters(C.c_void_p(outs[k]), pools=pools, free=True, ctx=self.handle))
+        return res
+
+    # ---- BinaryImage::to_clusters
+    def to_clusters(self, mask: np.ndarray, diagonal: bool) -> dict:
+        mask = np.ascontiguousarray(mask, dtype=bool)
+        h, w = mask.shape
+        bits = pack_bits(mask)
+        out = C.c_void_p()
+        st = self.lib.fn("binary_to_clusters")(self.handle, bits.ctypes.data_as(C.c_void_p), w, h, int(diagonal), C.byref(out))
+        self.lib.check(st, self.handle)
+        return self.lib.read_bin_clusters(out)
+
+    def synchronize(self):
+        self.lib.check(self.lib.fn("ctx_synchronize")(self.handle), self.handle)
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.fn("ctx_kernel_launches")(self.handle))

@@ -9,13 +9,26 @@ from visioncortex_b200._ffi import Library, RunnerConfigC, VcbError, pack_bits
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
-ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle.so")
+
+
+def _cpu_tag() -> str:
+    """-march=native output is only valid on the CPU model it was built on: key the library by the host's flags."""
+    import hashlib
+
+    try:
+        flags = next(l for l in open("/proc/cpuinfo") if l.startswith("flags"))
+    except Exception:
+        flags = "unknown"
+    return hashlib.sha1(flags.encode()).hexdigest()[:10]
+
+
+ORACLE_SO = os.path.join(ORACLE_DIR, f"liboracle-{_cpu_tag()}.so")
 
 
 def build_oracle():
     src = os.path.join(ORACLE_DIR, "vc_oracle.cpp")
     if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s", f"OUT={os.path.basename(ORACLE_SO)}"])
     return ORACLE_SO
 
 

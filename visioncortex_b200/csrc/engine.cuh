@@ -24,6 +24,9 @@ struct vcb_ctx {
     size_t h_pinned_cap = 0;
     u8 *d_stage = nullptr;            // device staging of host inputs
     size_t d_stage_cap = 0;
+#ifndef VCB_HOSTSIM
+    cudaEvent_t events[16] = {};
+#endif
 };
 
 namespace vcb {

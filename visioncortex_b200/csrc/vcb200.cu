@@ -348,4 +348,27 @@ int vcb_ctx_profile_read(vcb_ctx *c, const char *kernel_name, double *total_ms, 
     return VCB_OK;
 }
 
+int vcb_ctx_event_record(vcb_ctx *c, int slot) {
+    if (!c || slot < 0 || slot >= 16) return VCB_ERR_INVALID_ARG;
+#ifndef VCB_HOSTSIM
+    rt::set_device(c->device);
+    if (!c->events[slot] && cudaEventCreate(&c->events[slot]) != cudaSuccess) return VCB_ERR_CUDA;
+    if (cudaEventRecord(c->events[slot], c->st.s) != cudaSuccess) return VCB_ERR_CUDA;
+#endif
+    return VCB_OK;
+}
+
+int vcb_ctx_event_elapsed_ms(vcb_ctx *c, int a, int b, double *ms) {
+    if (!c || !ms || a < 0 || b < 0 || a >= 16 || b >= 16) return VCB_ERR_INVALID_ARG;
+    *ms = 0;
+#ifndef VCB_HOSTSIM
+    if (!c->events[a] || !c->events[b]) return VCB_ERR_INVALID_ARG;
+    if (cudaEventSynchronize(c->events[b]) != cudaSuccess) return VCB_ERR_CUDA;
+    float f = 0;
+    if (cudaEventElapsedTime(&f, c->events[a], c->events[b]) != cudaSuccess) return VCB_ERR_CUDA;
+    *ms = f;
+#endif
+    return VCB_OK;
+}
+
 }  // extern "C"

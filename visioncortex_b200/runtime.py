@@ -107,3 +107,31 @@ class Context:
 
     def kernel_launches(self) -> int:
         return int(self.lib.fn("ctx_kernel_launches")(self.handle))
+
+    # ---- device-resident batch (bench / GPU-resident callers)
+    def runner_run_device(self, d_ptr: int, width: int, height: int, n: int, cfg: RunnerConfigC):
+        """d_ptr: device pointer to n RGBA8 images stored back to back.  Returns a list of raw result handles."""
+        outs = (C.c_void_p * n)()
+        st = self.lib.fn("runner_run_device")(self.handle, C.byref(cfg), C.c_void_p(d_ptr), width, height, n, outs)
+        self.lib.check(st, self.handle)
+        return [C.c_void_p(outs[k]) for k in range(n)]
+
+    def free_handles(self, handles):
+        for h in handles:
+            self.lib.fn("clusters_free")(h)
+
+    def profile_reset(self, enable: bool):
+        self.lib.check(self.lib.fn("ctx_profile_reset")(self.handle, int(enable)), self.handle)
+
+    def profile_read(self, name: str = ""):
+        ms, n = C.c_double(), C.c_uint64()
+        self.lib.check(self.lib.fn("ctx_profile_read")(self.handle, name.encode(), C.byref(ms), C.byref(n)), self.handle)
+        return ms.value, n.value
+
+    def event_record(self, slot: int):
+        self.lib.check(self.lib.fn("ctx_event_record")(self.handle, slot), self.handle)
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_double()
+        self.lib.check(self.lib.fn("ctx_event_elapsed_ms")(self.handle, a, b, C.byref(ms)), self.handle)
+        return ms.value

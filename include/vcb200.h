@@ -110,6 +110,10 @@ void vcb_runner_config_default(vcb_runner_config *cfg);
 int  vcb_ctx_create(int device, vcb_ctx **out);
 void vcb_ctx_destroy(vcb_ctx *ctx);
 int  vcb_ctx_device(const vcb_ctx *ctx);
+/* options.  VCB_OPT_MATERIALIZE_INDICES (default 0): build the ordered `Cluster.indices` pool (color_clusters/cluster.rs:8)
+ * during the run; when 0 it is built on the first vcb_clusters_indices_pool call from the retained image. */
+enum { VCB_OPT_MATERIALIZE_INDICES = 1 };
+int  vcb_ctx_set_option(vcb_ctx *ctx, int option, int64_t value);
 
 /* Runner::new(config, image).run() (color_clusters/runner.rs:52-57,104-106): host RGBA8 row-major in, result handle out. */
 int vcb_runner_run(vcb_ctx *ctx, const vcb_runner_config *cfg, const uint8_t *rgba,
@@ -136,6 +140,8 @@ int  vcb_clusters_holes_pool(const vcb_clusters *c, uint32_t *out /* holes_total
 int  vcb_clusters_to_color_image(const vcb_clusters *c, uint8_t *rgba_out /* width*height*4 */);
 /* device pointer of the label map (width*height u32) for callers that stay on the GPU; NULL if released */
 const uint32_t *vcb_clusters_device_labels(const vcb_clusters *c);
+/* Clusters::take_image (container.rs:34-40): the retained RGBA8 input, copied to the caller */
+int  vcb_clusters_take_image(const vcb_clusters *c, uint8_t *rgba_out /* width*height*4 */);
 void vcb_clusters_free(vcb_clusters *c);
 
 /* BinaryImage::to_clusters(diagonal) (clusters.rs:270-349).  bits = bit_vec::BitVec storage: u32 blocks,

@@ -85,3 +85,77 @@ def test_edge_shapes(gpu, oracle):
         ref = oracle.runner_run(img, cfg, pools=False)
         got = gpu.runner_run(img, cfg, pools=False)
         assert_same_clusters(got, ref, pools=False, ctx=f"shape {w}x{h}")
+
+
+# ---------------------------------------------------------------- ordered Cluster.indices (color_clusters/cluster.rs:8)
+def test_indices_pool_small(gpu, oracle):
+    rng = np.random.default_rng(31)
+    for k in range(60):
+        img, cfg = random_case(rng, max_side=64, keyed=(k % 3 == 2))
+        ref = oracle.runner_run(img, cfg, pools=True, color_image=True)
+        got = gpu.runner_run(img, cfg, pools=True, color_image=True)
+        assert_same_clusters(got, ref, pools=True, ctx=f"pool case {k} {img.shape}")
+
+
+def test_indices_pool_c2(gpu, oracle):
+    img = synth.g2_scene(1920, 1080, seed=2)
+    cfg = c2_config(1920, 1080)
+    ref = oracle.runner_run(img, cfg, pools=True)
+    got = gpu.runner_run(img, cfg, pools=True)
+    assert_same_clusters(got, ref, pools=True, ctx="C2 pools")
+
+
+# ---------------------------------------------------------------- BinaryImage::to_clusters (clusters.rs:270-349)
+from parity import assert_same_bin_clusters  # noqa: E402
+
+
+def test_binary_reference_kats(gpu):
+    img = np.zeros((3, 3), dtype=bool)
+    img[0, 0] = img[1, 1] = img[2, 2] = True
+    res = gpu.to_clusters(img, False)                      # clusters.rs:355-377
+    assert len(res["records"]) == 3 and res["points"].tolist() == [[0, 0], [1, 1], [2, 2]]
+    assert tuple(res["records"][2]["rect"]) == (2, 2, 3, 3)
+    res = gpu.to_clusters(img, True)                       # clusters.rs:379-392 (point order)
+    assert len(res["records"]) == 1 and res["points"].tolist() == [[0, 0], [1, 1], [2, 2]]
+    img = np.zeros((4, 4), dtype=bool)
+    img[1:3, 1:3] = True
+    res = gpu.to_clusters(img, False)                      # clusters.rs:394-418
+    assert len(res["records"]) == 1 and tuple(res["records"][0]["rect"]) == (1, 1, 3, 3)
+
+
+def test_binary_random(gpu, oracle):
+    rng = np.random.default_rng(41)
+    for k in range(120):
+        w, h = int(rng.integers(1, 90)), int(rng.integers(1, 90))
+        mask = rng.random((h, w)) < rng.choice([0.05, 0.3, 0.5, 0.7, 0.9, 1.0])
+        diag = bool(k % 2)
+        assert_same_bin_clusters(gpu.to_clusters(mask, diag), oracle.to_clusters(mask, diag), ctx=f"bin {k} {w}x{h} {diag}")
+
+
+@pytest.mark.parametrize("diag", [False, True])
+def test_c1_binary_noise_1024(gpu, oracle, diag):
+    """BASELINE config 1: G1(1024, 1024, p=0.70, seed=1)."""
+    mask = synth.g1_binary(1024, 1024, 0.70, 1)
+    assert_same_bin_clusters(gpu.to_clusters(mask, diag), oracle.to_clusters(mask, diag), ctx=f"C1 diag={diag}")
+
+
+def test_c1_binary_overflow_parity(gpu, oracle):
+    """p = 0.5 noise makes the reference panic!("overflow") (clusters.rs:322-324): error parity."""
+    from visioncortex_b200._ffi import VcbError
+
+    mask = synth.g1_binary(1024, 1024, 0.50, 1)
+    with pytest.raises(VcbError) as eo:
+        oracle.to_clusters(mask, False)
+    with pytest.raises(VcbError) as eg:
+        gpu.to_clusters(mask, False)
+    assert eo.value.status == eg.value.status == 2
+
+
+def test_binary_empty_inputs(gpu, oracle):
+    for mask in (np.zeros((0, 0), dtype=bool), np.zeros((9, 13), dtype=bool), np.ones((33, 65), dtype=bool)):
+        for diag in (False, True):
+            if mask.size == 0:
+                res = gpu.to_clusters(mask, diag)
+                assert len(res["records"]) == 0 and tuple(res["rect"]) == (0, 0, 0, 0)
+            else:
+                assert_same_bin_clusters(gpu.to_clusters(mask, diag), oracle.to_clusters(mask, diag))

@@ -1,0 +1,70 @@
+"""CPU-side check of the kernel *logic*: the product kernel sources compiled against the host CUDA simulator
+(tests/hostsim, TEST INFRASTRUCTURE) and compared with the oracle on small inputs.  This is not a product path: the
+product library has no CPU build; the real parity tests are the `-m gpu` ones."""
+import numpy as np
+import pytest
+
+from parity import assert_same_bin_clusters, assert_same_clusters, random_case
+from test_oracle_kat import from_string
+from visioncortex_b200._ffi import VcbError
+
+
+@pytest.fixture(scope="module")
+def sim():
+    from sim_lib import load_sim
+
+    return load_sim()
+
+
+def test_sim_colour_stage1(sim, oracle):
+    rng = np.random.default_rng(21)
+    done = 0
+    for k in range(12):
+        img, cfg = random_case(rng, max_side=28, keyed=(k % 3 == 2))
+        ref = oracle.runner_run(img, cfg, pools=True, color_image=True)
+        got = sim.runner_run(img, cfg, pools=True, color_image=True)
+        assert_same_clusters(got, ref, pools=True, ctx=f"case {k}")
+        done += 1
+    assert done == 12
+
+
+def test_sim_binary(sim, oracle):
+    rng = np.random.default_rng(22)
+    for k in range(12):
+        w, h = int(rng.integers(1, 30)), int(rng.integers(1, 30))
+        mask = rng.random((h, w)) < rng.choice([0.3, 0.5, 0.7, 0.9])
+        diag = bool(k % 2)
+        assert_same_bin_clusters(sim.to_clusters(mask, diag), oracle.to_clusters(mask, diag), ctx=f"case {k}")
+
+
+def test_sim_binary_reference_kats(sim):
+    # clusters.rs:355-392
+    img = np.zeros((3, 3), dtype=bool)
+    img[0, 0] = img[1, 1] = img[2, 2] = True
+    res = sim.to_clusters(img, False)
+    assert len(res["records"]) == 3 and res["points"].tolist() == [[0, 0], [1, 1], [2, 2]]
+    res = sim.to_clusters(img, True)
+    assert len(res["records"]) == 1 and res["points"].tolist() == [[0, 0], [1, 1], [2, 2]]
+    # clusters.rs:394-418
+    img = np.zeros((4, 4), dtype=bool)
+    img[1:3, 1:3] = True
+    res = sim.to_clusters(img, False)
+    assert len(res["records"]) == 1 and tuple(res["records"][0]["rect"]) == (1, 1, 3, 3)
+    assert tuple(res["rect"]) == (1, 1, 3, 3)
+
+
+def test_sim_empty_and_full(sim, oracle):
+    for mask in (np.zeros((5, 7), dtype=bool), np.ones((6, 4), dtype=bool)):
+        for diag in (False, True):
+            assert_same_bin_clusters(sim.to_clusters(mask, diag), oracle.to_clusters(mask, diag))
+
+
+def test_sim_unclean_key_is_fenced(sim):
+    from visioncortex_b200.runtime import make_config
+
+    img = np.full((4, 4, 4), 100, dtype=np.uint8)
+    img[1, 1] = (101, 100, 100, 255)
+    cfg = make_config(hierarchical=0, is_same_color_a=0, is_same_color_b=2, key_color=(101, 100, 100, 255))
+    with pytest.raises(VcbError) as e:
+        sim.runner_run(img, cfg, pools=False)
+    assert e.value.status == 3

@@ -88,7 +88,7 @@ DEFAULT_LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "
 # every symbol include/vcb200.h declares (tests assert the library exports all of them)
 EXPORTED_SYMBOLS = [
     "vcb_strerror", "vcb_last_error", "vcb_abi_version", "vcb_runner_config_default",
-    "vcb_ctx_create", "vcb_ctx_destroy", "vcb_ctx_device",
+    "vcb_ctx_create", "vcb_ctx_destroy", "vcb_ctx_device", "vcb_ctx_set_option", "vcb_clusters_take_image",
     "vcb_runner_run", "vcb_runner_run_batch", "vcb_runner_run_device",
     "vcb_clusters_info_get", "vcb_clusters_cluster_indices", "vcb_clusters_outputs", "vcb_clusters_records",
     "vcb_clusters_indices_pool", "vcb_clusters_holes_pool", "vcb_clusters_to_color_image",
@@ -158,6 +158,8 @@ class Library:
             f("ctx_destroy").argtypes = [p]
             f("ctx_destroy").restype = None
             f("ctx_device").argtypes = [p]
+            f("ctx_set_option").argtypes = [p, C.c_int, C.c_int64]
+            f("clusters_take_image").argtypes = [p, p]
             f("runner_run_batch").argtypes = [p, C.POINTER(RunnerConfigC), p, p, p, C.c_size_t, p]
             f("runner_run_device").argtypes = [p, C.POINTER(RunnerConfigC), p, C.c_uint32, C.c_uint32, C.c_size_t, p]
             f("clusters_device_labels").argtypes = [p]

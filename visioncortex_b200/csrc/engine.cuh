@@ -4,7 +4,7 @@
 #include <string>
 #include <vector>
 
-#include "records.cuh"
+#include "listing.cuh"
 
 struct vcb_ctx {
     int device = 0;
@@ -24,6 +24,7 @@ struct vcb_ctx {
     size_t h_pinned_cap = 0;
     u8 *d_stage = nullptr;            // device staging of host inputs
     size_t d_stage_cap = 0;
+    int opt_materialize = 0;          // VCB_OPT_MATERIALIZE_INDICES
 #ifndef VCB_HOSTSIM
     cudaEvent_t events[16] = {};
 #endif
@@ -41,11 +42,15 @@ struct BatchResult {
     u32 *outputs = nullptr;           // total_slots (per image: [slot_base, slot_base + nout))
     u32 *d_slot_base = nullptr;       // nimg + 1
     u32 *d_slot_img = nullptr;        // total_slots
-    std::vector<u32> slot_base, nout;
+    u32 *pool = nullptr;              // concatenated Cluster.indices of all images (exact order), when materialised
+    u8 *pixels = nullptr;             // retained copy of the input (Clusters.pixels, container.rs:8; take_image :34-40)
+    std::vector<u32> slot_base, nout, pool_base;
     std::vector<u64> indices_total, holes_total;
     u32 total_slots = 0;
+    bool keep_key = false;
     ~BatchResult() {
         rt::dev_free(labels); rt::dev_free(rec); rt::dev_free(outputs); rt::dev_free(d_slot_base); rt::dev_free(d_slot_img);
+        rt::dev_free(pool); rt::dev_free(pixels);
     }
 };
 
@@ -81,7 +86,7 @@ inline int ensure_workspace(vcb_ctx *c, size_t N, size_t nimg) {
     }
     if (nimg > c->cap_img) {
         bool ok = grow(c->b.meta, nimg + 1);
-        ok &= grow(c->d_small, 4 * (nimg + 4));
+        ok &= grow(c->d_small, 4 * (nimg + 4) + 16);
         if (!ok) { c->cap_img = 0; return VCB_ERR_NOMEM; }
         c->cap_img = nimg;
     }
@@ -213,6 +218,33 @@ inline int build_records(vcb_ctx *c, const Dims &d, const std::vector<ImgMeta> &
         if (rt::stream_sync(st) != 0 || st.last_error) { c->err = st.last_error_text; st.last_error = 0; return VCB_ERR_CUDA; }
         for (u32 i = 0; i < d.nimg; ++i) res->nout[i] = ((u32 *)c->h_pinned)[i];
     }
+    return VCB_OK;
+}
+
+// Cluster.indices / points in the reference's exact order (listing.cuh).  Requires k_attribute<.., true> to have run.
+inline int materialize_pool(vcb_ctx *c, const Dims &d, BatchResult *res, bool keep_key) {
+    rt::Stream &st = c->st;
+    Bufs b = c->b;
+    const int g = grid_for(c, d.N / 2, LST_THREADS, 16);
+    rt::launch(st, "k_list_init", rt::SEQ, k_list_init, dim3(g), dim3(LST_THREADS), 0, b);
+    rt::launch(st, "k_list_jump", rt::SEQ, k_list_jump, dim3(g), dim3(LST_THREADS), 0, b);
+    u32 *d_pool_base = c->d_small + 2 * (d.nimg + 2);
+    u32 *d_count = c->d_small + 3 * (d.nimg + 2) + 2;
+    rt::launch(st, "k_pool_base", rt::SEQ, k_pool_base, dim3(1), dim3(32), 0, (const vcb_cluster_rec *)res->rec,
+               (const u32 *)res->d_slot_base, d.nimg, d_pool_base);
+    rt::launch(st, "k_list_keys", rt::SEQ, k_list_keys, dim3(grid_for(c, d.N, LST_THREADS, 16)), dim3(LST_THREADS), 0, d, b,
+               (const vcb_cluster_rec *)res->rec, (const u32 *)res->d_slot_base, (const u32 *)d_pool_base, keep_key ? 1 : 0, c->sk0, c->sv0);
+    rt::copy_h2d(st, d_count, &d.N, sizeof(u32));
+    int nbits = 1;
+    while (((1ull << nbits) - 1ull) <= (u64)d.N) ++nbits;
+    const bool flipped = prims::radix_sort(st, c->sk0, c->sv0, c->sk1, c->sv1, d_count, d.N, nbits, c->rs_table, c->chunksum, c->sms * 8);
+    rt::copy_d2h(st, c->h_pinned, d_pool_base, (d.nimg + 1) * sizeof(u32));
+    if (rt::stream_sync(st) != 0 || st.last_error) { c->err = st.last_error_text; st.last_error = 0; return VCB_ERR_CUDA; }
+    res->pool_base.assign((u32 *)c->h_pinned, (u32 *)c->h_pinned + d.nimg + 1);
+    const u32 total = res->pool_base[d.nimg];
+    res->pool = (u32 *)rt::dev_malloc((size_t)total * sizeof(u32) + 4);
+    if (!res->pool) return VCB_ERR_NOMEM;
+    rt::copy_d2d(st, res->pool, flipped ? c->sv1 : c->sv0, (size_t)total * sizeof(u32));
     return VCB_OK;
 }
 

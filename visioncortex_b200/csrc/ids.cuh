@@ -38,7 +38,8 @@ struct ImgMeta {
     u32 slots;             // clusters.len()
     u32 live;              // slots with area > 0
     u32 key_sum[4]; u32 key_cnt; i32 key_rect[4];   // clusters[0] under KeyingAction::Keep (builder.rs:330-334)
-    u32 pad[3];
+    u32 maxlabel;          // label of the image's last leaf = the largest label ever handed out (clusters.rs:320-324)
+    u32 pad[2];
 };
 
 struct Counters {
@@ -560,13 +561,15 @@ __global__ void k_image_meta(Dims d, Bufs b, u32 base) {
     const u32 kt = b.ctr->kt;
     const u32 lb = b.meta[img].leaf_begin;
     const u32 le = img + 1 < d.nimg ? b.meta[img + 1].leaf_begin : kt;
-    u32 slots = base;
+    u32 slots = base, maxlabel = 0;
     if (le > lb) {
         const u32 last = b.newlist[le - 1];
         const u32 last_ex = b.la[last].label, last_notd = b.la[last].flabel;
         slots = base + (last_ex + last_notd - b.meta[img].notd_base) + (last_notd ? 0u : 1u);
+        maxlabel = base + last_ex - b.meta[img].notd_base;
     }
     b.meta[img].slots = slots;
+    b.meta[img].maxlabel = maxlabel;
 }
 
 // per leaf: image-relative label

@@ -1,5 +1,6 @@
 // vcb200.cu — the C ABI of include/vcb200.h over the sm_100a kernels.  No CPU compute path exists in this library:
 // every entry point that produces results launches kernels on the context's device and fails if there is none.
+#include "binary.cuh"
 #include "engine.cuh"
 
 #include <algorithm>
@@ -17,8 +18,9 @@ struct vcb_clusters {
 };
 
 struct vcb_bin_clusters {
-    std::shared_ptr<BatchResult> br;
-    u32 img = 0;
+    vcb_bin_clusters_info info{};
+    std::vector<vcb_bin_cluster_rec> rec;
+    std::vector<int32_t> xy;
 };
 
 namespace {
@@ -59,12 +61,10 @@ int fetch_records(vcb_clusters *h) {
 }
 
 // colour path on device-resident images
-int run_color_device(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w, u32 h, size_t nimg,
-                     vcb_clusters **out) {
+int run_color(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w, u32 h, size_t nimg, bool want_pool,
+              bool retain, std::shared_ptr<BatchResult> &out_br) {
     int e = validate_cfg(c, cfg);
     if (e) return e;
-    if (!out) return fail(c, VCB_ERR_INVALID_ARG, "null output");
-    if (nimg == 0) return VCB_OK;
     const u64 n64 = (u64)w * h;
     if (n64 == 0 || n64 * nimg >= 0x7fffff00ull) return fail(c, VCB_ERR_INVALID_ARG, "width*height*n must be in 1..2^31");
     if (!d_rgba) return fail(c, VCB_ERR_INVALID_ARG, "null image");
@@ -79,6 +79,11 @@ int run_color_device(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba,
     br->ctx = c; br->d = d; br->cfg = *cfg;
     br->labels = (u32 *)rt::dev_malloc((size_t)d.N * sizeof(u32));
     if (!br->labels) return fail(c, VCB_ERR_NOMEM, "device out of memory (labels)");
+    if (retain) {
+        br->pixels = (u8 *)rt::dev_malloc((size_t)d.N * 4);
+        if (!br->pixels) return fail(c, VCB_ERR_NOMEM, "device out of memory (image copy)");
+        rt::copy_d2d(c->st, br->pixels, d_rgba, (size_t)d.N * 4);
+    }
 
     ColorPolicy pol;
     pol.rgba = (const u32 *)d_rgba;
@@ -86,13 +91,29 @@ int run_color_device(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba,
     pol.key = (u32)cfg->key_color[0] | ((u32)cfg->key_color[1] << 8) | ((u32)cfg->key_color[2] << 16) | ((u32)cfg->key_color[3] << 24);
     pol.has_key = pol.key != 0;
     const bool keep = pol.has_key && cfg->keying_action == VCB_KEYING_KEEP;
+    br->keep_key = keep;
 
     std::vector<ImgMeta> meta;
     Counters ctr{};
-    e = run_stage1(c, d, pol, 1u, false, keep ? 1 : 0, br.get(), meta, ctr);
+    e = run_stage1(c, d, pol, 1u, want_pool, keep ? 1 : 0, br.get(), meta, ctr);
     if (e) return e;
     if (ctr.err & 1u) return fail(c, VCB_ERR_UNSUPPORTED, "key colour is not clean: a non-key pixel is color_same to the key (order-dependent in the reference)");
     e = build_records(c, d, meta, br.get(), cfg->hierarchical == 0, keep);
+    if (e) return e;
+    if (want_pool) {
+        e = materialize_pool(c, d, br.get(), keep);
+        if (e) return fail(c, e, "materialising the indices pool failed");
+    }
+    out_br = br;
+    return VCB_OK;
+}
+
+int run_color_device(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w, u32 h, size_t nimg,
+                     vcb_clusters **out) {
+    if (!out) return fail(c, VCB_ERR_INVALID_ARG, "null output");
+    if (nimg == 0) return VCB_OK;
+    std::shared_ptr<BatchResult> br;
+    int e = run_color(c, cfg, d_rgba, w, h, nimg, c->opt_materialize != 0, true, br);
     if (e) return e;
     for (size_t i = 0; i < nimg; ++i) {
         vcb_clusters *hd = new (std::nothrow) vcb_clusters();
@@ -101,6 +122,19 @@ int run_color_device(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba,
         out[i] = hd;
     }
     return VCB_OK;
+}
+
+// first request for Cluster.indices on a result computed without them: recompute from the retained image
+int ensure_pool(BatchResult *br) {
+    if (br->pool) return VCB_OK;
+    vcb_ctx *c = br->ctx;
+    if (!br->pixels) return fail(c, VCB_ERR_INVALID_ARG, "result holds no image to rebuild the indices from");
+    std::shared_ptr<BatchResult> tmp;
+    int e = run_color(c, &br->cfg, br->pixels, br->d.w, br->d.h, br->d.nimg, true, false, tmp);
+    if (e) return e;
+    std::swap(br->pool, tmp->pool);
+    br->pool_base = tmp->pool_base;
+    return check_stream(c);
 }
 
 u8 *stage_input(vcb_ctx *c, size_t bytes) {
@@ -265,8 +299,29 @@ int vcb_clusters_records(const vcb_clusters *hc, vcb_cluster_rec *out) {
 }
 
 int vcb_clusters_indices_pool(const vcb_clusters *h, uint32_t *out) {
-    if (!h || !out) return VCB_ERR_INVALID_ARG;
-    return fail(h->br->ctx, VCB_ERR_UNSUPPORTED, "indices pool not built yet");
+    if (!h) return VCB_ERR_INVALID_ARG;
+    BatchResult *br = h->br.get();
+    int e = ensure_pool(br);
+    if (e) return e;
+    const u32 n = br->pool_base[h->img + 1] - br->pool_base[h->img];
+    if (n == 0) return VCB_OK;
+    if (!out) return VCB_ERR_INVALID_ARG;
+    rt::copy_d2h(br->ctx->st, out, br->pool + br->pool_base[h->img], (size_t)n * 4);
+    return check_stream(br->ctx);
+}
+
+int vcb_clusters_take_image(const vcb_clusters *h, uint8_t *rgba_out) {
+    if (!h || !rgba_out) return VCB_ERR_INVALID_ARG;
+    const BatchResult *br = h->br.get();
+    if (!br->pixels) return fail(br->ctx, VCB_ERR_INVALID_ARG, "result holds no image");
+    rt::copy_d2h(br->ctx->st, rgba_out, br->pixels + (size_t)h->img * br->d.n * 4, (size_t)br->d.n * 4);
+    return check_stream(br->ctx);
+}
+
+int vcb_ctx_set_option(vcb_ctx *c, int option, int64_t value) {
+    if (!c) return VCB_ERR_INVALID_ARG;
+    if (option == VCB_OPT_MATERIALIZE_INDICES) { c->opt_materialize = value != 0; return VCB_OK; }
+    return fail(c, VCB_ERR_INVALID_ARG, "unknown option");
 }
 
 int vcb_clusters_holes_pool(const vcb_clusters *h, uint32_t *out) {
@@ -298,19 +353,93 @@ void vcb_clusters_free(vcb_clusters *h) { delete h; }
 
 int vcb_binary_to_clusters_device(vcb_ctx *c, const uint32_t *d_bits, uint32_t width, uint32_t height, int diagonal,
                                   vcb_bin_clusters **out) {
-    (void)d_bits; (void)width; (void)height; (void)diagonal; (void)out;
-    return fail(c, VCB_ERR_UNSUPPORTED, "binary path not built yet");
+    if (!c) return VCB_ERR_INVALID_ARG;
+    if (!out) return fail(c, VCB_ERR_INVALID_ARG, "null output");
+    *out = nullptr;
+    const u64 n64 = (u64)width * height;
+    if (n64 >= 0x7fffff00ull) return fail(c, VCB_ERR_INVALID_ARG, "width*height must be below 2^31");
+    vcb_bin_clusters *hb = new (std::nothrow) vcb_bin_clusters();
+    if (!hb) return fail(c, VCB_ERR_NOMEM, "host out of memory");
+    hb->info.width = width; hb->info.height = height;
+    if (n64 == 0) { *out = hb; return VCB_OK; }                 // empty image: no clusters, default rect
+    if (!d_bits) { delete hb; return fail(c, VCB_ERR_INVALID_ARG, "null image"); }
+    rt::set_device(c->device);
+    Dims d{width, height, (u32)n64, 1u, (u32)n64};
+    int e = ensure_workspace(c, d.N, 1);
+    if (e) { delete hb; return fail(c, e, "device out of memory (workspace)"); }
+    BatchResult br;
+    br.ctx = c; br.d = d; br.binary = true;
+    BinaryPolicy pol;
+    pol.bits = d_bits; pol.n = d.n; pol.words_per_img = (d.n + 31) / 32; pol.diagonal = diagonal != 0;
+    std::vector<ImgMeta> meta;
+    Counters ctr{};
+    e = run_stage1(c, d, pol, 0u, true, 0, &br, meta, ctr);
+    if (e) { delete hb; return e; }
+    // panic!("overflow") (clusters.rs:322-324): the running label counter reaches 65535, i.e. some new cluster gets label 65534
+    if (meta[0].slots > 0 && meta[0].maxlabel >= 65534u) { delete hb; return fail(c, VCB_ERR_LABEL_OVERFLOW, "overflow"); }
+    e = build_records(c, d, meta, &br, false, false);
+    if (!e) e = materialize_pool(c, d, &br, false);
+    if (e) { delete hb; return e; }
+    const u32 total = br.total_slots, npts = br.pool_base[1];
+    vcb_bin_cluster_rec *d_out = (vcb_bin_cluster_rec *)rt::dev_malloc((size_t)(total + 1) * sizeof(vcb_bin_cluster_rec));
+    i32 *d_xy = (i32 *)rt::dev_malloc((size_t)npts * 8 + 8);
+    i32 *d_overall = (i32 *)c->d_small;
+    u32 *d_count = c->d_small + 4;
+    if (!d_out || !d_xy) { rt::dev_free(d_out); rt::dev_free(d_xy); delete hb; return fail(c, VCB_ERR_NOMEM, "device out of memory"); }
+    const i32 init[5] = {0x7fffffff, 0x7fffffff, -1, -1, 0};
+    rt::copy_h2d(c->st, d_overall, init, sizeof(init));
+    if (total)
+        prims::scan(c->st, "scan_bin", BinCompact{br.rec, total, d_out, d_overall, d_count}, c->chunksum, total, c->sms * 8);
+    rt::launch(c->st, "k_bin_points", rt::SEQ, k_bin_points, dim3(grid_for(c, npts, 256, 16)), dim3(256), 0,
+               (const u32 *)br.pool, npts, width, d_xy);
+    i32 h_small[5];
+    rt::copy_d2h(c->st, h_small, d_overall, sizeof(h_small));
+    e = check_stream(c);
+    if (!e) {
+        const u32 ncl = total ? (u32)h_small[4] : 0;
+        hb->rec.resize(ncl);
+        hb->xy.resize((size_t)npts * 2);
+        rt::copy_d2h(c->st, hb->rec.data(), d_out, (size_t)ncl * sizeof(vcb_bin_cluster_rec));
+        rt::copy_d2h(c->st, hb->xy.data(), d_xy, (size_t)npts * 8);
+        e = check_stream(c);
+        hb->info.num_clusters = ncl; hb->info.points_total = npts;
+        if (ncl) { for (int k = 0; k < 4; ++k) hb->info.rect[k] = h_small[k]; }
+    }
+    rt::dev_free(d_out); rt::dev_free(d_xy);
+    if (e) { delete hb; return e; }
+    *out = hb;
+    return VCB_OK;
 }
 
 int vcb_binary_to_clusters(vcb_ctx *c, const uint32_t *bits, uint32_t width, uint32_t height, int diagonal,
                            vcb_bin_clusters **out) {
-    (void)bits; (void)width; (void)height; (void)diagonal; (void)out;
-    return fail(c, VCB_ERR_UNSUPPORTED, "binary path not built yet");
+    if (!c) return VCB_ERR_INVALID_ARG;
+    const u64 n64 = (u64)width * height;
+    if (n64 == 0) return vcb_binary_to_clusters_device(c, nullptr, width, height, diagonal, out);
+    if (!bits) return fail(c, VCB_ERR_INVALID_ARG, "null image");
+    rt::set_device(c->device);
+    const size_t bytes = (size_t)((n64 + 31) / 32) * 4;
+    u8 *d = stage_input(c, bytes);
+    if (!d) return fail(c, VCB_ERR_NOMEM, "device out of memory (input)");
+    rt::copy_h2d(c->st, d, bits, bytes);
+    return vcb_binary_to_clusters_device(c, (const uint32_t *)d, width, height, diagonal, out);
 }
 
-int vcb_bin_clusters_info_get(const vcb_bin_clusters *h, vcb_bin_clusters_info *info) { (void)h; (void)info; return VCB_ERR_UNSUPPORTED; }
-int vcb_bin_clusters_records(const vcb_bin_clusters *h, vcb_bin_cluster_rec *out) { (void)h; (void)out; return VCB_ERR_UNSUPPORTED; }
-int vcb_bin_clusters_points(const vcb_bin_clusters *h, int32_t *xy) { (void)h; (void)xy; return VCB_ERR_UNSUPPORTED; }
+int vcb_bin_clusters_info_get(const vcb_bin_clusters *h, vcb_bin_clusters_info *info) {
+    if (!h || !info) return VCB_ERR_INVALID_ARG;
+    *info = h->info;
+    return VCB_OK;
+}
+int vcb_bin_clusters_records(const vcb_bin_clusters *h, vcb_bin_cluster_rec *out) {
+    if (!h || (!out && !h->rec.empty())) return VCB_ERR_INVALID_ARG;
+    std::copy(h->rec.begin(), h->rec.end(), out);
+    return VCB_OK;
+}
+int vcb_bin_clusters_points(const vcb_bin_clusters *h, int32_t *xy) {
+    if (!h || (!xy && !h->xy.empty())) return VCB_ERR_INVALID_ARG;
+    std::copy(h->xy.begin(), h->xy.end(), xy);
+    return VCB_OK;
+}
 void vcb_bin_clusters_free(vcb_bin_clusters *h) { delete h; }
 
 int vcb_ctx_synchronize(vcb_ctx *c) {

@@ -4,7 +4,7 @@
 #include <string>
 #include <vector>
 
-#include "listing.cuh"
+#include "stage2.cuh"
 
 struct vcb_ctx {
     int device = 0;
@@ -25,6 +25,13 @@ struct vcb_ctx {
     u8 *d_stage = nullptr;            // device staging of host inputs
     size_t d_stage_cap = 0;
     int opt_materialize = 0;          // VCB_OPT_MATERIALIZE_INDICES
+    // stage-2 workspace
+    size_t cap_s2_slots = 0, cap_s2_adj = 0;
+    u32 *s2_fw = nullptr, *s2_mnext = nullptr, *s2_mtail = nullptr, *s2_mark = nullptr, *s2_adj_off = nullptr,
+        *s2_cursor = nullptr, *s2_adj = nullptr;
+    u64 *s2_over = nullptr;
+    vcb::S2ImgState *s2_ist = nullptr;
+    size_t cap_s2_img = 0;
 #ifndef VCB_HOSTSIM
     cudaEvent_t events[16] = {};
 #endif
@@ -42,6 +49,9 @@ struct BatchResult {
     u32 *outputs = nullptr;           // total_slots (per image: [slot_base, slot_base + nout))
     u32 *d_slot_base = nullptr;       // nimg + 1
     u32 *d_slot_img = nullptr;        // total_slots
+    u32 *labels1 = nullptr;           // stage-1 labels when a hierarchical stage ran (labels then holds the final ones)
+    u32 *mpar = nullptr, *outpos = nullptr;   // stage-2 merge forest / first output position per slot
+    bool hier = false;
     u32 *pool = nullptr;              // concatenated Cluster.indices of all images (exact order), when materialised
     u8 *pixels = nullptr;             // retained copy of the input (Clusters.pixels, container.rs:8; take_image :34-40)
     std::vector<u32> slot_base, nout, pool_base;
@@ -50,7 +60,7 @@ struct BatchResult {
     bool keep_key = false;
     ~BatchResult() {
         rt::dev_free(labels); rt::dev_free(rec); rt::dev_free(outputs); rt::dev_free(d_slot_base); rt::dev_free(d_slot_img);
-        rt::dev_free(pool); rt::dev_free(pixels);
+        rt::dev_free(pool); rt::dev_free(pixels); rt::dev_free(labels1); rt::dev_free(mpar); rt::dev_free(outpos);
     }
 };
 
@@ -86,11 +96,11 @@ inline int ensure_workspace(vcb_ctx *c, size_t N, size_t nimg) {
     }
     if (nimg > c->cap_img) {
         bool ok = grow(c->b.meta, nimg + 1);
-        ok &= grow(c->d_small, 4 * (nimg + 4) + 16);
+        ok &= grow(c->d_small, 4 * (nimg + 4) + 32);
         if (!ok) { c->cap_img = 0; return VCB_ERR_NOMEM; }
         c->cap_img = nimg;
     }
-    const size_t need = (nimg + 4) * sizeof(ImgMeta) + 4096;
+    const size_t need = (nimg + 4) * (sizeof(ImgMeta) + sizeof(S2ImgState)) + 4096;
     if (need > c->h_pinned_cap) {
         rt::host_free(c->h_pinned);
         c->h_pinned = rt::host_malloc(need);
@@ -245,6 +255,82 @@ inline int materialize_pool(vcb_ctx *c, const Dims &d, BatchResult *res, bool ke
     res->pool = (u32 *)rt::dev_malloc((size_t)total * sizeof(u32) + 4);
     if (!res->pool) return VCB_ERR_NOMEM;
     rt::copy_d2d(st, res->pool, flipped ? c->sv1 : c->sv0, (size_t)total * sizeof(u32));
+    return VCB_OK;
+}
+
+// Stage 2 (builder.rs:379-539) on the records / labels produced by stage 1.  See stage2.cuh.
+inline int run_stage2(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg, bool has_key, BatchResult *res) {
+    rt::Stream &st = c->st;
+    const u32 total = res->total_slots;
+    if (total > c->cap_s2_slots) {
+        const size_t cap = (size_t)total + 64;
+        bool ok = grow(c->s2_fw, cap) & grow(c->s2_mnext, cap) & grow(c->s2_mtail, cap) & grow(c->s2_mark, cap) &
+                  grow(c->s2_adj_off, cap + 1) & grow(c->s2_cursor, cap) & grow(c->s2_over, cap);
+        if (!ok) { c->cap_s2_slots = 0; return VCB_ERR_NOMEM; }
+        c->cap_s2_slots = total;
+    }
+    if ((size_t)d.N * 4 > c->cap_s2_adj) {
+        if (!grow(c->s2_adj, (size_t)d.N * 4 + 64)) { c->cap_s2_adj = 0; return VCB_ERR_NOMEM; }
+        c->cap_s2_adj = (size_t)d.N * 4;
+    }
+    if (d.nimg > c->cap_s2_img) {
+        if (!grow(c->s2_ist, (size_t)d.nimg + 1)) { c->cap_s2_img = 0; return VCB_ERR_NOMEM; }
+        c->cap_s2_img = d.nimg;
+    }
+    res->mpar = (u32 *)rt::dev_malloc((size_t)total * 4 + 4);
+    res->outpos = (u32 *)rt::dev_malloc((size_t)total * 4 + 4);
+    res->labels1 = res->labels;
+    res->labels = (u32 *)rt::dev_malloc((size_t)d.N * 4);
+    if (!res->mpar || !res->outpos || !res->labels) return VCB_ERR_NOMEM;
+    res->hier = true;
+
+    u32 max_slots = 1;
+    for (u32 i = 0; i < d.nimg; ++i) max_slots = std::max(max_slots, res->slot_base[i + 1] - res->slot_base[i]);
+    S2 a{};
+    a.d = d;
+    a.cfg.hierarchical = cfg->hierarchical; a.cfg.good_min = cfg->good_min_area; a.cfg.good_max = cfg->good_max_area;
+    a.cfg.deepen_diff = cfg->deepen_diff; a.cfg.hollow_neighbours = cfg->hollow_neighbours;
+    a.cfg.can_discard = (cfg->keying_action == VCB_KEYING_DISCARD && has_key) ? 1 : 0;
+    a.cfg.hier_max = cfg->hierarchical == VCB_HIERARCHICAL_MAX;
+    a.l1 = res->labels1; a.rec = res->rec; a.slot_base = res->d_slot_base; a.slot_img = res->d_slot_img; a.total_slots = total;
+    a.fw = c->s2_fw; a.mpar = res->mpar; a.mnext = c->s2_mnext; a.mtail = c->s2_mtail; a.mark = c->s2_mark; a.outpos = res->outpos;
+    a.adj_off = c->s2_adj_off; a.adj = c->s2_adj; a.cursor = c->s2_cursor; a.outputs = res->outputs; a.over = c->s2_over;
+    a.ist = c->s2_ist; a.keys = c->sk0; a.vals = c->sv0;
+    u32 *d_count = c->d_small + 3 * (d.nimg + 2) + 3;
+    a.count = d_count;
+    a.idx_bits = 1; while ((1u << a.idx_bits) < max_slots) ++a.idx_bits;
+    a.area_bits = 1; while ((1ull << a.area_bits) <= (u64)d.n) ++a.area_bits;
+    int img_bits = 1; while ((1u << img_bits) < d.nimg) ++img_bits;
+    const int nbits = a.idx_bits + a.area_bits + (d.nimg > 1 ? img_bits : 0);
+
+    const int gs = grid_for(c, total, 256, 16), gp = grid_for(c, d.N, 256, 16);
+    rt::launch(st, "k_s2_init_img", rt::SEQ, k_s2_init_img, dim3((d.nimg + 127) / 128), dim3(128), 0, a);
+    rt::launch(st, "k_s2_init", rt::SEQ, k_s2_init, dim3(gs), dim3(256), 0, a);
+    rt::launch(st, "k_rag_count", rt::SEQ, k_rag<false>, dim3(gp), dim3(256), 0, a);
+    prims::scan(st, "scan_deg", DegScan{a}, c->chunksum, total, c->sms * 8);
+    rt::launch(st, "k_rag_fill", rt::SEQ, k_rag<true>, dim3(gp), dim3(256), 0, a);
+    int max_epoch = 0;
+    while ((2ull << max_epoch) <= (u64)d.n) ++max_epoch;
+    for (int ep = 0; ep <= max_epoch; ++ep) {
+        rt::fill(st, d_count, 0, sizeof(u32));
+        rt::launch(st, "k_s2_collect", rt::THR, k_s2_collect, dim3(gs), dim3(256), 0, a, ep);
+        const bool flipped = prims::radix_sort(st, c->sk0, c->sv0, c->sk1, c->sv1, d_count, total, nbits, c->rs_table, c->chunksum, c->sms * 8);
+        rt::launch(st, "k_s2_epoch", rt::THR, k_s2_epoch, dim3(d.nimg), dim3(S2_THREADS), sizeof(S2Shared) + 16, a,
+                   (const u64 *)(flipped ? c->sk1 : c->sk0), ep);
+    }
+    rt::launch(st, "k_s2_labels", rt::SEQ, k_s2_labels, dim3(gp), dim3(256), 0, a, res->labels);
+    // offsets of the per-slot lists after the merges
+    prims::scan(st, "scan_off", OffScan{res->rec, res->d_slot_base, res->d_slot_img, total, nullptr}, c->chunksum, total, c->sms * 8);
+    rt::launch(st, "k_off_rebase", rt::SEQ, k_off_rebase, dim3(gs), dim3(REC_THREADS), 0, res->rec, res->d_slot_base, res->d_slot_img, total);
+    rt::launch(st, "k_off_rebase0", rt::SEQ, k_off_rebase0, dim3((d.nimg + 127) / 128), dim3(128), 0, res->rec, res->d_slot_base, d.nimg);
+    u32 *d_first = c->d_small;
+    prims::scan(st, "scan_holes", HolesScan{res->rec, total}, c->chunksum, total, c->sms * 8);
+    rt::launch(st, "k_holes_first", rt::SEQ, k_holes_first, dim3((d.nimg + 127) / 128), dim3(128), 0, (const vcb_cluster_rec *)res->rec, (const u32 *)res->d_slot_base, d.nimg, d_first);
+    rt::launch(st, "k_holes_rebase", rt::SEQ, k_holes_rebase, dim3(gs), dim3(256), 0, res->rec, (const u32 *)res->d_slot_base, (const u32 *)res->d_slot_img, total, d_first);
+    S2ImgState *h = (S2ImgState *)c->h_pinned;
+    rt::copy_d2h(st, h, c->s2_ist, d.nimg * sizeof(S2ImgState));
+    if (rt::stream_sync(st) != 0 || st.last_error) { c->err = st.last_error_text; st.last_error = 0; return VCB_ERR_CUDA; }
+    for (u32 i = 0; i < d.nimg; ++i) res->nout[i] = h[i].nout;
     return VCB_OK;
 }
 

@@ -69,7 +69,6 @@ int run_color(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w,
     if (n64 == 0 || n64 * nimg >= 0x7fffff00ull) return fail(c, VCB_ERR_INVALID_ARG, "width*height*n must be in 1..2^31");
     if (!d_rgba) return fail(c, VCB_ERR_INVALID_ARG, "null image");
     if (cfg->diagonal) return fail(c, VCB_ERR_UNSUPPORTED, "diagonal=true colour clustering (stale-upleft quirk) is fenced, see DESIGN.md");
-    if (cfg->hierarchical != 0) return fail(c, VCB_ERR_UNSUPPORTED, "hierarchical stage not built yet");
     rt::set_device(c->device);
     Dims d{w, h, (u32)n64, (u32)nimg, (u32)(n64 * nimg)};
     e = ensure_workspace(c, d.N, d.nimg);
@@ -103,6 +102,10 @@ int run_color(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w,
     if (want_pool) {
         e = materialize_pool(c, d, br.get(), keep);
         if (e) return fail(c, e, "materialising the indices pool failed");
+    }
+    if (cfg->hierarchical != 0) {
+        e = run_stage2(c, d, cfg, pol.has_key != 0, br.get());
+        if (e) return fail(c, e, c->err.empty() ? "hierarchical stage failed" : c->err);
     }
     out_br = br;
     return VCB_OK;
@@ -198,6 +201,8 @@ void vcb_ctx_destroy(vcb_ctx *c) {
     rt::dev_free(b.cand); rt::dev_free(b.newlist); rt::dev_free(b.attr); rt::dev_free(b.meta); rt::dev_free(b.ctr);
     rt::dev_free(c->chunksum); rt::dev_free(c->rs_table); rt::dev_free(c->sk0); rt::dev_free(c->sk1);
     rt::dev_free(c->sv0); rt::dev_free(c->sv1); rt::dev_free(c->d_small); rt::dev_free(c->d_stage);
+    rt::dev_free(c->s2_fw); rt::dev_free(c->s2_mnext); rt::dev_free(c->s2_mtail); rt::dev_free(c->s2_mark); rt::dev_free(c->s2_adj_off);
+    rt::dev_free(c->s2_cursor); rt::dev_free(c->s2_adj); rt::dev_free(c->s2_over); rt::dev_free(c->s2_ist);
     rt::host_free(c->h_pinned);
     rt::stream_destroy(c->st);
     delete c;
@@ -301,6 +306,7 @@ int vcb_clusters_records(const vcb_clusters *hc, vcb_cluster_rec *out) {
 int vcb_clusters_indices_pool(const vcb_clusters *h, uint32_t *out) {
     if (!h) return VCB_ERR_INVALID_ARG;
     BatchResult *br = h->br.get();
+    if (br->hier) return fail(br->ctx, VCB_ERR_UNSUPPORTED, "ordered indices after the hierarchical stage are not built yet");
     int e = ensure_pool(br);
     if (e) return e;
     const u32 n = br->pool_base[h->img + 1] - br->pool_base[h->img];
@@ -338,6 +344,14 @@ int vcb_clusters_to_color_image(const vcb_clusters *h, uint8_t *rgba_out) {
     const u32 n = br->d.n;
     u8 *d = stage_input(c, (size_t)n * 4);
     if (!d) return fail(c, VCB_ERR_NOMEM, "device out of memory");
+    if (br->hier) {
+        S2 a{};
+        a.d = br->d; a.l1 = br->labels1; a.rec = br->rec; a.slot_base = br->d_slot_base; a.slot_img = br->d_slot_img;
+        a.total_slots = br->total_slots; a.mpar = br->mpar; a.outpos = br->outpos;
+        u32 *slot_color = c->s2_cursor;      // scratch, total_slots entries
+        rt::launch(c->st, "k_s2_slot_color", rt::SEQ, k_s2_slot_color, dim3(grid_for(c, br->total_slots, 256, 16)), dim3(256), 0, a, slot_color);
+        rt::launch(c->st, "k_s2_paint", rt::SEQ, k_s2_paint, dim3(grid_for(c, n, 256, 16)), dim3(256), 0, a, (const u32 *)slot_color, h->img, (u32 *)d);
+    } else
     rt::launch(c->st, "k_color_image_flat", rt::SEQ, k_color_image_flat, dim3(grid_for(c, n, REC_THREADS, 16)), dim3(REC_THREADS), 0,
                n, (const u32 *)(br->labels + (size_t)h->img * n), (const vcb_cluster_rec *)(br->rec + br->slot_base[h->img]), (u32 *)d);
     rt::copy_d2h(c->st, rgba_out, d, (size_t)n * 4);

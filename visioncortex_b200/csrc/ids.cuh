@@ -80,9 +80,11 @@ struct ColorPolicy {
         const bool kc = has_key && c == key;
         u32 f = 0;
         if (has_key && !kc && same(c, key)) *err |= 1u;          // unclean key: order-dependent in the reference
-        const bool s_cu = vu && same(c, up), s_cl = vl && same(c, left), s_cul = vul && same(c, ul);
+        // keyed neighbours are never joined: with a clean key they are never color_same to a non-key pixel anyway, and an
+        // unclean key is rejected (VCB_ERR_UNSUPPORTED) -- this only keeps the J forest well formed until it is
+        const bool ku = has_key && up == key, kl = has_key && left == key, kul = has_key && ul == key;
+        const bool s_cu = vu && !ku && same(c, up), s_cl = vl && !kl && same(c, left), s_cul = vul && !kul && same(c, ul);
         if (vul) {
-            const bool ku = has_key && up == key, kl = has_key && left == key;
             if (!ku && !kl && same(left, up) && (diagonal || (s_cl && s_cu))) f |= F_M;
         }
         if (kc) return f | J_NONE | F_KEYED;

@@ -97,7 +97,11 @@ inline void *host_malloc(size_t n) { void *p = nullptr; if (cudaMallocHost(&p, n
 inline void host_free(void *p) { if (p) cudaFreeHost(p); }
 inline int stream_create(Stream &st) { return (int)cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking); }
 inline void stream_destroy(Stream &st) { if (st.s) cudaStreamDestroy(st.s); st.s = nullptr; }
-inline int stream_sync(Stream &st) { return (int)cudaStreamSynchronize(st.s); }
+inline int stream_sync(Stream &st) {
+    cudaError_t e = cudaStreamSynchronize(st.s);
+    if (e != cudaSuccess && !st.last_error) { st.last_error = (int)e; st.last_error_text = std::string("stream synchronize: ") + cudaGetErrorString(e); }
+    return (int)e;
+}
 inline int copy_h2d(Stream &st, void *d, const void *h, size_t n) { return (int)cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, st.s); }
 inline int copy_d2h(Stream &st, void *h, const void *d, size_t n) { return (int)cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, st.s); }
 inline int copy_d2d(Stream &st, void *d, const void *s, size_t n) { return (int)cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st.s); }

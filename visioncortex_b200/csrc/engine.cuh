@@ -58,11 +58,16 @@ struct BatchResult {
     std::vector<u64> indices_total, holes_total;
     u32 total_slots = 0;
     bool keep_key = false;
-    ~BatchResult() {
-        rt::dev_free(labels); rt::dev_free(rec); rt::dev_free(outputs); rt::dev_free(d_slot_base); rt::dev_free(d_slot_img);
-        rt::dev_free(pool); rt::dev_free(pixels); rt::dev_free(labels1); rt::dev_free(mpar); rt::dev_free(outpos);
-    }
+    ~BatchResult();
 };
+
+inline BatchResult::~BatchResult() {
+    if (!ctx) return;
+    rt::set_device(ctx->device);
+    for (void *p : {(void *)labels, (void *)rec, (void *)outputs, (void *)d_slot_base, (void *)d_slot_img, (void *)pool,
+                    (void *)pixels, (void *)labels1, (void *)mpar, (void *)outpos})
+        rt::dev_free_async(ctx->st, p);
+}
 
 inline int grid_for(const vcb_ctx *c, u64 items, int threads, int per_sm = 8) {
     u64 g = (items + threads - 1) / threads;
@@ -84,7 +89,7 @@ inline int ensure_workspace(vcb_ctx *c, size_t N, size_t nimg) {
         bool ok = true;
         ok &= grow(c->b.flags, cap); ok &= grow(c->b.pc, cap); ok &= grow(c->b.la, cap); ok &= grow(c->b.ls, cap);
         ok &= grow(c->b.lr, cap); ok &= grow(c->b.ev, cap); ok &= grow(c->b.cand, cap); ok &= grow(c->b.newlist, cap);
-        ok &= grow(c->b.attr, cap);
+        ok &= grow(c->b.attr, cap); ok &= grow(c->b.labex, cap);
         const size_t chunks = cap / 2048 + 4;
         ok &= grow(c->chunksum, 256 * chunks / 2048 + chunks + 1024);
         ok &= grow(c->rs_table, 256 * chunks + 16);
@@ -190,10 +195,10 @@ inline int build_records(vcb_ctx *c, const Dims &d, const std::vector<ImgMeta> &
     for (u32 i = 0; i < d.nimg; ++i) res->slot_base[i + 1] = res->slot_base[i] + meta[i].slots;
     const u32 total = res->slot_base[d.nimg];
     res->total_slots = total;
-    res->rec = (vcb_cluster_rec *)rt::dev_malloc((size_t)total * sizeof(vcb_cluster_rec));
-    res->d_slot_base = (u32 *)rt::dev_malloc((d.nimg + 1) * sizeof(u32));
-    res->d_slot_img = (u32 *)rt::dev_malloc((size_t)total * sizeof(u32));
-    res->outputs = (u32 *)rt::dev_malloc((size_t)total * sizeof(u32));
+    res->rec = (vcb_cluster_rec *)rt::dev_malloc_async(st, (size_t)total * sizeof(vcb_cluster_rec) + 16);
+    res->d_slot_base = (u32 *)rt::dev_malloc_async(st, (d.nimg + 1) * sizeof(u32));
+    res->d_slot_img = (u32 *)rt::dev_malloc_async(st, (size_t)total * sizeof(u32) + 16);
+    res->outputs = (u32 *)rt::dev_malloc_async(st, (size_t)total * sizeof(u32) + 16);
     if (!res->rec || !res->d_slot_base || !res->d_slot_img || !res->outputs) return VCB_ERR_NOMEM;
     rt::copy_h2d(st, res->d_slot_base, res->slot_base.data(), (d.nimg + 1) * sizeof(u32));
     const int g = grid_for(c, total, REC_THREADS, 16);
@@ -219,7 +224,7 @@ inline int build_records(vcb_ctx *c, const Dims &d, const std::vector<ImgMeta> &
         while ((1u << img_bits) < d.nimg) ++img_bits;
         rt::fill(st, d_live, 0, (d.nimg + 2) * sizeof(u32));
         rt::copy_h2d(st, d_total, &res->total_slots, sizeof(u32));
-        rt::launch(st, "k_out_keys", rt::SEQ, k_out_keys, dim3(g), dim3(REC_THREADS), 0, res->rec, res->d_slot_base,
+        rt::launch(st, "k_out_keys", rt::THR, k_out_keys, dim3(g), dim3(REC_THREADS), 0, res->rec, res->d_slot_base,
                    res->d_slot_img, total, key_bits, c->sk0, c->sv0, d_live);
         const bool flipped = prims::radix_sort(st, c->sk0, c->sv0, c->sk1, c->sv1, d_total, total, key_bits + (d.nimg > 1 ? img_bits : 0),
                                                c->rs_table, c->chunksum, c->sms * 8);
@@ -252,7 +257,7 @@ inline int materialize_pool(vcb_ctx *c, const Dims &d, BatchResult *res, bool ke
     if (rt::stream_sync(st) != 0 || st.last_error) { c->err = st.last_error_text; st.last_error = 0; return VCB_ERR_CUDA; }
     res->pool_base.assign((u32 *)c->h_pinned, (u32 *)c->h_pinned + d.nimg + 1);
     const u32 total = res->pool_base[d.nimg];
-    res->pool = (u32 *)rt::dev_malloc((size_t)total * sizeof(u32) + 4);
+    res->pool = (u32 *)rt::dev_malloc_async(st, (size_t)total * sizeof(u32) + 4);
     if (!res->pool) return VCB_ERR_NOMEM;
     rt::copy_d2d(st, res->pool, flipped ? c->sv1 : c->sv0, (size_t)total * sizeof(u32));
     return VCB_OK;
@@ -277,10 +282,10 @@ inline int run_stage2(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg, b
         if (!grow(c->s2_ist, (size_t)d.nimg + 1)) { c->cap_s2_img = 0; return VCB_ERR_NOMEM; }
         c->cap_s2_img = d.nimg;
     }
-    res->mpar = (u32 *)rt::dev_malloc((size_t)total * 4 + 4);
-    res->outpos = (u32 *)rt::dev_malloc((size_t)total * 4 + 4);
+    res->mpar = (u32 *)rt::dev_malloc_async(st, (size_t)total * 4 + 4);
+    res->outpos = (u32 *)rt::dev_malloc_async(st, (size_t)total * 4 + 4);
     res->labels1 = res->labels;
-    res->labels = (u32 *)rt::dev_malloc((size_t)d.N * 4);
+    res->labels = (u32 *)rt::dev_malloc_async(st, (size_t)d.N * 4);
     if (!res->mpar || !res->outpos || !res->labels) return VCB_ERR_NOMEM;
     res->hier = true;
 

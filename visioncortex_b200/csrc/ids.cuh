@@ -20,7 +20,7 @@ namespace vcb {
 constexpr u32 NONE = 0xFFFFFFFFu;
 constexpr u32 TAG = 0x80000000u;   // node ids: leaf = TAG | pixel, event = pixel; also "dead" mark in the candidate list
 
-enum : u32 { J_NEW = 0, J_UP = 1, J_LEFT = 2, J_UPLEFT = 3, J_NONE = 4, J_MASK = 7,
+enum : u32 { J_NEW = 0, J_UP = 1, J_LEFT = 2, J_UPLEFT = 3, J_NONE = 4, J_RUP = 5, J_MASK = 7,
              F_M = 8, F_CAND = 16, F_MSF = 32, F_KEYED = 64, F_LWIN = 128 };
 
 struct Dims { u32 w, h, n, nimg, N; };
@@ -38,7 +38,7 @@ struct ImgMeta {
     u32 slots;             // clusters.len()
     u32 live;              // slots with area > 0
     u32 key_sum[4]; u32 key_cnt; i32 key_rect[4];   // clusters[0] under KeyingAction::Keep (builder.rs:330-334)
-    u32 maxlabel;          // label of the image's last leaf = the largest label ever handed out (clusters.rs:320-324)
+    u32 maxlabel;          // label of the image's last NEW event = the largest label ever handed out (clusters.rs:320-324)
     u32 pad[2];
 };
 
@@ -53,7 +53,7 @@ struct Counters {
 
 struct Bufs {
     u8 *flags; u32 *pc; LeafA *la; LeafS *ls; LeafR *lr; EvRec *ev;
-    u32 *cand; u32 *newlist; u32 *attr; ImgMeta *meta; Counters *ctr;
+    u32 *cand; u32 *newlist; u32 *attr; u32 *labex; ImgMeta *meta; Counters *ctr;
 };
 
 // --------------------------------------------------------------------------------------------------------------
@@ -122,12 +122,20 @@ struct BinaryPolicy {
 
 // --------------------------------------------------------------------------------------------------------------
 // K1: one CTA per TW x TH tile.
+//
+// Contraction of trivial leaves: a NEW pixel p whose right neighbour carries a merge flag starts a cluster that is merged
+// away by the very next scan step -- as the LEFT side with area 1, so it always loses (builder.rs:313: 1 <= area(up)),
+// and its slot is handed to the next new cluster (builder.rs:315-317).  Nothing can happen between the two steps, so
+// p is re-parented to the pixel above its right neighbour (J_RUP): it joins that cluster one step early, which changes
+// no area seen by any comparison, no label and no list order, and removes one leaf and one event from the global graph
+// (half of all leaves on noisy inputs).
 constexpr int TW = 64, TH = 32, K1_THREADS = 256, K1_PPT = TW * TH / K1_THREADS;
-constexpr size_t K1_SMEM = (size_t)(TH + 1) * (TW + 1) * 4 + (size_t)TW * TH * 2 + (size_t)TW * TH;
+constexpr int PW = TW + 2, FW = TW + 1;
+constexpr size_t K1_SMEM = (size_t)(TH + 1) * PW * 4 + (size_t)TW * TH * 2 + (size_t)FW * TH;
 
 template <class P> __global__ void __launch_bounds__(K1_THREADS) k_edges_tile(Dims d, P pol, Bufs b) {
     VCB_SMEM(u32, pix);
-    u16 *lp = (u16 *)(pix + (TH + 1) * (TW + 1));
+    u16 *lp = (u16 *)(pix + (TH + 1) * PW);
     u8 *fl = (u8 *)(lp + TW * TH);
     const u32 tiles_x = (d.w + TW - 1) / TW, tiles_y = (d.h + TH - 1) / TH;
     const u32 tile = blockIdx.x;
@@ -135,8 +143,8 @@ template <class P> __global__ void __launch_bounds__(K1_THREADS) k_edges_tile(Di
     const u32 x0 = (tr % tiles_x) * TW, y0 = (tr / tiles_x) * TH;
     const u32 base = img * d.n;
 
-    for (int idx = threadIdx.x; idx < (TH + 1) * (TW + 1); idx += K1_THREADS) {
-        const int ly = idx / (TW + 1), lx = idx % (TW + 1);
+    for (int idx = threadIdx.x; idx < (TH + 1) * PW; idx += K1_THREADS) {
+        const int ly = idx / PW, lx = idx % PW;
         const i64 gy = (i64)y0 - 1 + ly, gx = (i64)x0 - 1 + lx;
         u32 v = 0;
         if (gy >= 0 && gx >= 0 && gy < d.h && gx < d.w) v = pol.load(base + (u32)gy * d.w + (u32)gx);
@@ -145,23 +153,36 @@ template <class P> __global__ void __launch_bounds__(K1_THREADS) k_edges_tile(Di
     __syncthreads();
 
     u32 err = 0;
+    for (int i = threadIdx.x; i < FW * TH; i += K1_THREADS) {      // tile pixels + one halo column to the right (M flag only)
+        const int ly = i / FW, lx = i % FW;
+        const u32 gx = x0 + lx, gy = y0 + ly;
+        u32 f = J_NONE;
+        if (gx < d.w && gy < d.h) {
+            const u32 c = pix[(ly + 1) * PW + lx + 1], up = pix[ly * PW + lx + 1];
+            const u32 left = pix[(ly + 1) * PW + lx], ul = pix[ly * PW + lx];
+            f = pol.classify(c, up, left, ul, gy > 0, gx > 0, &err);
+        }
+        fl[i] = (u8)f;
+    }
+    __syncthreads();
 #pragma unroll
     for (int k = 0; k < K1_PPT; ++k) {
         const int i = threadIdx.x + k * K1_THREADS;
         const int ly = i / TW, lx = i % TW;
         const u32 gx = x0 + lx, gy = y0 + ly;
-        u32 f = J_NONE;
+        u32 f = fl[ly * FW + lx];
         u16 l = (u16)i;
         if (gx < d.w && gy < d.h) {
-            const u32 c = pix[(ly + 1) * (TW + 1) + lx + 1], up = pix[ly * (TW + 1) + lx + 1];
-            const u32 left = pix[(ly + 1) * (TW + 1) + lx], ul = pix[ly * (TW + 1) + lx];
-            f = pol.classify(c, up, left, ul, gy > 0, gx > 0, &err);
+            if ((f & J_MASK) == J_NEW && gx + 1 < d.w && (fl[ly * FW + lx + 1] & F_M)) {
+                f = (f & ~J_MASK) | J_RUP;
+                fl[ly * FW + lx] = (u8)f;                            // only the J bits of the own entry change
+            }
             const u32 j = f & J_MASK;
             if (j == J_UP && ly > 0) l = (u16)(i - TW);
             else if (j == J_LEFT && lx > 0) l = (u16)(i - 1);
             else if (j == J_UPLEFT && ly > 0 && lx > 0) l = (u16)(i - TW - 1);
+            else if (j == J_RUP && ly > 0 && lx + 1 < TW) l = (u16)(i - TW + 1);
         }
-        fl[i] = (u8)f;
         lp[i] = l;
     }
     __syncthreads();
@@ -186,20 +207,20 @@ template <class P> __global__ void __launch_bounds__(K1_THREADS) k_edges_tile(Di
         const u32 gx = x0 + lx, gy = y0 + ly;
         if (gx >= d.w || gy >= d.h) continue;
         const u32 g = base + gy * d.w + gx;
-        const u32 f = fl[i], j = f & J_MASK;
+        const u32 f = fl[ly * FW + lx], j = f & J_MASK;
         b.flags[g] = (u8)f;
         u32 root = NONE;
         if (j != J_NONE) {
             const int r = lp[i];
-            const u32 jr = fl[r] & J_MASK;
+            const u32 jr = fl[(r / TW) * FW + r % TW] & J_MASK;
             const u32 gr = base + (y0 + r / TW) * d.w + x0 + r % TW;
-            root = jr == J_NEW ? gr : jr == J_UP ? gr - d.w : jr == J_LEFT ? gr - 1 : gr - d.w - 1;
+            root = jr == J_NEW ? gr : jr == J_UP ? gr - d.w : jr == J_LEFT ? gr - 1 : jr == J_UPLEFT ? gr - d.w - 1 : gr - d.w + 1;
         }
         b.pc[g] = root;
         if (j == J_NEW) {
             LeafA a; a.ufp = g; a.best0 = NONE; a.best1 = NONE; a.parL = NONE; a.cnt = 1; a.death = NONE; a.label = 0; a.flabel = 0;
             b.la[g] = a;
-            LeafS s; pol.stats(pix[(ly + 1) * (TW + 1) + lx + 1], s.sum); s.npx = 1; s.pad[0] = s.pad[1] = s.pad[2] = 0;
+            LeafS s; pol.stats(pix[(ly + 1) * PW + lx + 1], s.sum); s.npx = 1; s.pad[0] = s.pad[1] = s.pad[2] = 0;
             b.ls[g] = s;
             LeafR r; r.minx = r.maxx = (i32)gx; r.miny = r.maxy = (i32)gy;
             b.lr[g] = r;
@@ -423,11 +444,13 @@ __global__ void __launch_bounds__(K5_THREADS) k_attribute(Dims d, P pol, Bufs b,
                 stcg(&b.ev[p].childU, upnode);
             }
             const u32 gprev_left = __shfl_up_sync(0xffffffffu, gprev, 1);   // node of pixel (x-1, y-1), for UPLEFT
+            const u32 gprev_right = __shfl_down_sync(0xffffffffu, gprev, 1); // node of pixel (x+1, y-1), for RUP
             bool resolved = true;
             if (valid && j != J_NONE) {
                 if (j == J_NEW) g = p | TAG;
                 else if (j == J_UP) g = climb(b, upnode != NONE ? upnode : (b.pc[p] | TAG), p);
                 else if (j == J_UPLEFT) g = climb(b, (lane > 0 && gprev_left != NONE) ? gprev_left : (b.pc[p] | TAG), p);
+                else if (j == J_RUP) g = climb(b, (lane < 31 && gprev_right != NONE) ? gprev_right : (b.pc[p] | TAG), p);
                 else if (lane == 0) g = climb(b, b.pc[p] | TAG, p);         // J_LEFT across the warp edge
                 else resolved = false;                                       // J_LEFT: wait for the lane to the left
             }
@@ -480,9 +503,11 @@ __global__ void __launch_bounds__(K5_THREADS) k_attribute(Dims d, P pol, Bufs b,
 struct NewScan {
     Dims d; Bufs b;
     __device__ u32 count() const { return d.N; }
-    __device__ u32 value(u32 i) const { return (b.flags[i] & J_MASK) == J_NEW ? 1u : 0u; }
+    __device__ u32 value(u32 i) const { const u32 j = b.flags[i] & J_MASK; return (j == J_NEW || j == J_RUP) ? 1u : 0u; }
     __device__ void emit(u32 i, u32 ex, u32 v) const {
-        if (v) b.newlist[ex] = i;
+        // contracted (trivial) NEW events stay in the list, tagged: they own no leaf record but they are NEW events of the
+        // reference, so they bound the "next NEW" window of the numbering and they are always in D
+        if (v) b.newlist[ex] = i | (((b.flags[i] & J_MASK) == J_RUP) ? TAG : 0u);
         if (i % d.n == 0) b.meta[i / d.n].leaf_begin = ex;
         if (i == d.N - 1) b.ctr->kt = ex + v;
     }
@@ -498,6 +523,7 @@ __global__ void __launch_bounds__(K6_THREADS) k_tournament(Dims d, Bufs b) {
     const u32 stride = gridDim.x * K6_THREADS;
     for (u32 k = blockIdx.x * K6_THREADS + threadIdx.x; k < kt; k += stride) {
         const u32 leaf = b.newlist[k];
+        if (leaf & TAG) continue;
         u32 child = leaf | TAG, W = ldcg(&b.la[leaf].cnt), car = leaf;
         u32 v = ldcg(&b.la[leaf].parL);
         while (v != NONE) {
@@ -538,20 +564,22 @@ struct LabelScan {
     Dims d; Bufs b;
     __device__ u32 count() const { return ldcg(&b.ctr->kt); }
     __device__ u32 value(u32 k) const {
-        const u32 p = b.newlist[k];
-        const u32 death = b.la[p].death;
+        const u32 e = b.newlist[k];
+        if (e & TAG) return 0u;                           // contracted NEW event: in D by construction
+        const u32 death = b.la[e].death;
         if (death == NONE || !(death & TAG)) return 1u;
         const u32 kt = ldcg(&b.ctr->kt);
-        const u32 img = p / d.n;
-        const bool has_next = k + 1 < kt && b.newlist[k + 1] / d.n == img;
-        if (!has_next) return 0u;
-        return (death & ~TAG) <= b.newlist[k + 1] ? 0u : 1u;
+        const u32 img = e / d.n;
+        if (k + 1 >= kt) return 0u;
+        const u32 nxt = b.newlist[k + 1] & ~TAG;
+        if (nxt / d.n != img) return 0u;
+        return (death & ~TAG) <= nxt ? 0u : 1u;
     }
     __device__ void emit(u32 k, u32 ex, u32 v) const {
-        const u32 p = b.newlist[k];
-        b.la[p].label = ex;
-        b.la[p].flabel = v;                               // not-in-D flag, consumed by k_image_meta
-        const u32 img = p / d.n;
+        const u32 e = b.newlist[k];
+        b.labex[k] = ex;
+        if (!(e & TAG)) b.la[e].flabel = v;               // not-in-D flag, consumed by k_image_meta
+        const u32 img = (e & ~TAG) / d.n;
         if (k == b.meta[img].leaf_begin) b.meta[img].notd_base = ex;
     }
 };
@@ -566,7 +594,7 @@ __global__ void k_image_meta(Dims d, Bufs b, u32 base) {
     u32 slots = base, maxlabel = 0;
     if (le > lb) {
         const u32 last = b.newlist[le - 1];
-        const u32 last_ex = b.la[last].label, last_notd = b.la[last].flabel;
+        const u32 last_ex = b.labex[le - 1], last_notd = (last & TAG) ? 0u : b.la[last].flabel;
         slots = base + (last_ex + last_notd - b.meta[img].notd_base) + (last_notd ? 0u : 1u);
         maxlabel = base + last_ex - b.meta[img].notd_base;
     }
@@ -581,7 +609,8 @@ __global__ void __launch_bounds__(K8_THREADS) k_leaf_labels(Dims d, Bufs b, u32 
     const u32 stride = gridDim.x * K8_THREADS;
     for (u32 k = blockIdx.x * K8_THREADS + threadIdx.x; k < kt; k += stride) {
         const u32 p = b.newlist[k];
-        b.la[p].label = base + b.la[p].label - b.meta[p / d.n].notd_base;
+        if (p & TAG) continue;
+        b.la[p].label = base + b.labex[k] - b.meta[p / d.n].notd_base;
     }
 }
 // per leaf: label of the carrier of its final cluster
@@ -590,6 +619,7 @@ __global__ void __launch_bounds__(K8_THREADS) k_leaf_final(Dims d, Bufs b) {
     const u32 stride = gridDim.x * K8_THREADS;
     for (u32 k = blockIdx.x * K8_THREADS + threadIdx.x; k < kt; k += stride) {
         const u32 p = b.newlist[k];
+        if (p & TAG) continue;
         const u32 root = uf_find(b.la, p);
         const u32 car = ldcg(&b.la[root].best0);
         b.la[p].flabel = ldcg(&b.la[car].label);

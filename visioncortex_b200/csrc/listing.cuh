@@ -46,7 +46,7 @@ __device__ static __forceinline__ void list_init_node(const Bufs &b, u32 node) {
 constexpr int LST_THREADS = 256;
 // work items: [0, kt) = leaves (newlist), [kt, kt + ncand) = candidate events (effective ones only)
 __device__ static __forceinline__ u32 list_node(const Bufs &b, u32 t, u32 kt) {
-    if (t < kt) return b.newlist[t] | TAG;
+    if (t < kt) { const u32 e = b.newlist[t]; return (e & TAG) ? NONE : (e | TAG); }
     const u32 p = b.cand[t - kt] & ~TAG;
     return (b.flags[p] & F_MSF) ? p : NONE;
 }

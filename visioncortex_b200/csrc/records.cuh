@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(REC_THREADS) k_rec_accum(Dims d, Bufs b, vcb_c
     const u32 stride = gridDim.x * REC_THREADS;
     for (u32 k = blockIdx.x * REC_THREADS + threadIdx.x; k < kt; k += stride) {
         const u32 p = b.newlist[k];
+        if (p & TAG) continue;
         vcb_cluster_rec *r = rec + slot_base[p / d.n] + b.la[p].flabel;
         const LeafS s = b.ls[p];
         const LeafR q = b.lr[p];
@@ -95,13 +96,27 @@ __global__ void __launch_bounds__(REC_THREADS) k_slot_img(u32 *slot_img, const u
 __global__ void __launch_bounds__(REC_THREADS) k_out_keys(const vcb_cluster_rec *rec, const u32 *slot_base, const u32 *slot_img,
                                                           u32 total, int key_bits, u64 *keys, u32 *vals, u32 *live) {
     const u32 stride = gridDim.x * REC_THREADS;
-    for (u32 s = blockIdx.x * REC_THREADS + threadIdx.x; s < total; s += stride) {
-        const u32 img = slot_img[s], idx = s - slot_base[img];
-        const u64 area = rec[s].indices_len;
-        u64 key = area ? area * 65535ull + idx : ((1ull << key_bits) - 1ull);
-        keys[s] = ((u64)img << key_bits) | key;
-        vals[s] = idx;
-        if (area) atomicAdd(&live[img], 1u);
+    const int lane = threadIdx.x & 31;
+    const u32 nloop = (total + stride - 1) / stride;
+    for (u32 it = 0; it < nloop; ++it) {
+        const u32 s = it * stride + blockIdx.x * REC_THREADS + threadIdx.x;
+        u32 img = 0xffffffffu;
+        bool alive = false;
+        if (s < total) {
+            img = slot_img[s];
+            const u32 idx = s - slot_base[img];
+            const u64 area = rec[s].indices_len;
+            u64 key = area ? area * 65535ull + idx : ((1ull << key_bits) - 1ull);
+            keys[s] = ((u64)img << key_bits) | key;
+            vals[s] = idx;
+            alive = area != 0;
+        }
+        // slots of one image are contiguous: aggregate the live count per warp when the whole warp is in one image
+        const u32 img0 = __shfl_sync(0xffffffffu, img, 0);
+        const bool uniform = __all_sync(0xffffffffu, img == img0 || s >= total);
+        const u32 m = __ballot_sync(0xffffffffu, alive);
+        if (uniform) { if (lane == 0 && m && img0 != 0xffffffffu) atomicAdd(&live[img0], (u32)__popc(m)); }
+        else if (alive) atomicAdd(&live[img], 1u);
     }
 }
 

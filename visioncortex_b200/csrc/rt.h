@@ -67,6 +67,8 @@ inline void *dev_malloc(size_t n) { return std::malloc(n ? n : 1); }
 inline void dev_free(void *p) { std::free(p); }
 inline void *host_malloc(size_t n) { return std::malloc(n ? n : 1); }
 inline void host_free(void *p) { std::free(p); }
+inline void *dev_malloc_async(Stream &, size_t n) { return std::malloc(n ? n : 1); }
+inline void dev_free_async(Stream &, void *p) { std::free(p); }
 inline int stream_create(Stream &) { return 0; }
 inline void stream_destroy(Stream &) {}
 inline int stream_sync(Stream &) { return 0; }
@@ -95,7 +97,24 @@ inline void *dev_malloc(size_t n) { void *p = nullptr; if (cudaMalloc(&p, n ? n 
 inline void dev_free(void *p) { if (p) cudaFree(p); }
 inline void *host_malloc(size_t n) { void *p = nullptr; if (cudaMallocHost(&p, n ? n : 1) != cudaSuccess) return nullptr; return p; }
 inline void host_free(void *p) { if (p) cudaFreeHost(p); }
-inline int stream_create(Stream &st) { return (int)cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking); }
+// stream-ordered allocations from the device's default memory pool (kept resident: release threshold = max), so that
+// per-call result buffers cost no cudaMalloc / cudaFree synchronisation after warm-up
+inline void *dev_malloc_async(Stream &st, size_t n) {
+    void *p = nullptr;
+    if (cudaMallocAsync(&p, n ? n : 1, st.s) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+inline void dev_free_async(Stream &st, void *p) { if (p) cudaFreeAsync(p, st.s); }
+inline int stream_create(Stream &st) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    return (int)cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking);
+}
 inline void stream_destroy(Stream &st) { if (st.s) cudaStreamDestroy(st.s); st.s = nullptr; }
 inline int stream_sync(Stream &st) {
     cudaError_t e = cudaStreamSynchronize(st.s);

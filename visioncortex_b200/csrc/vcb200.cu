@@ -76,10 +76,10 @@ int run_color(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w,
 
     auto br = std::make_shared<BatchResult>();
     br->ctx = c; br->d = d; br->cfg = *cfg;
-    br->labels = (u32 *)rt::dev_malloc((size_t)d.N * sizeof(u32));
+    br->labels = (u32 *)rt::dev_malloc_async(c->st, (size_t)d.N * sizeof(u32));
     if (!br->labels) return fail(c, VCB_ERR_NOMEM, "device out of memory (labels)");
     if (retain) {
-        br->pixels = (u8 *)rt::dev_malloc((size_t)d.N * 4);
+        br->pixels = (u8 *)rt::dev_malloc_async(c->st, (size_t)d.N * 4);
         if (!br->pixels) return fail(c, VCB_ERR_NOMEM, "device out of memory (image copy)");
         rt::copy_d2d(c->st, br->pixels, d_rgba, (size_t)d.N * 4);
     }
@@ -198,7 +198,7 @@ void vcb_ctx_destroy(vcb_ctx *c) {
     rt::stream_sync(c->st);
     Bufs &b = c->b;
     rt::dev_free(b.flags); rt::dev_free(b.pc); rt::dev_free(b.la); rt::dev_free(b.ls); rt::dev_free(b.lr); rt::dev_free(b.ev);
-    rt::dev_free(b.cand); rt::dev_free(b.newlist); rt::dev_free(b.attr); rt::dev_free(b.meta); rt::dev_free(b.ctr);
+    rt::dev_free(b.cand); rt::dev_free(b.newlist); rt::dev_free(b.attr); rt::dev_free(b.labex); rt::dev_free(b.meta); rt::dev_free(b.ctr);
     rt::dev_free(c->chunksum); rt::dev_free(c->rs_table); rt::dev_free(c->sk0); rt::dev_free(c->sk1);
     rt::dev_free(c->sv0); rt::dev_free(c->sv1); rt::dev_free(c->d_small); rt::dev_free(c->d_stage);
     rt::dev_free(c->s2_fw); rt::dev_free(c->s2_mnext); rt::dev_free(c->s2_mtail); rt::dev_free(c->s2_mark); rt::dev_free(c->s2_adj_off);

@@ -177,3 +177,4 @@ SIM_ATOMIC_OPS(unsigned long long)
 #undef SIM_ATOMIC_OPS
 
 template <class T> static inline T __ldg(const T *p) { return *p; }
+template <class T> static inline T __ldcg(const T *p) { return *p; }

@@ -352,19 +352,13 @@ __global__ void __launch_bounds__(K3_THREADS) k_boruvka(Bufs b) {
 __device__ static __forceinline__ void chain_insert(Bufs b, u32 leaf, u32 g) {
     u32 *slot = &b.la[leaf].parL;
     while (true) {
-        const u32 cur = ldcg(slot);
-        if (cur == g) return;
-        if (cur > g) {                                   // includes NONE
-            const u32 old = atomicMin(slot, g);
-            if (old == g) return;
-            if (old > g) {                               // installed g below `old`
-                if (old == NONE) return;
-                slot = &b.ev[g].parE; g = old;           // now insert `old` above g
-            } else {
-                slot = &b.ev[old].parE;                  // somebody installed a lighter ancestor first: walk up
-            }
+        const u32 old = atomicMin(slot, g);               // one round trip per step
+        if (old == g) return;
+        if (old > g) {                                    // installed g below `old` (NONE included)
+            if (old == NONE) return;
+            slot = &b.ev[g].parE; g = old;                // now insert the displaced ancestor above g
         } else {
-            slot = &b.ev[cur].parE;
+            slot = &b.ev[old].parE;                       // a lighter ancestor is already there: g is also its ancestor
         }
     }
 }
@@ -528,14 +522,16 @@ __global__ void __launch_bounds__(K6_THREADS) k_tournament(Dims d, Bufs b) {
         u32 v = ldcg(&b.la[leaf].parL);
         while (v != NONE) {
             EvRec *e = b.ev + v;
-            const bool up = ldcg(&e->childU) == child;
-            if (up) { stcg(&e->b_wu, W); stcg(&e->carU, car); } else { stcg(&e->a_wl, W); stcg(&e->carL, car); }
-            __threadfence();
-            const u32 old = atomicAdd(&e->arrive, 1u);
-            if (old == 0) break;
-            __threadfence();
-            const u32 WL = up ? ldcg(&e->a_wl) : W, WU = up ? W : ldcg(&e->b_wu);
-            const u32 cL = up ? ldcg(&e->carL) : car, cU = up ? car : ldcg(&e->carU);
+            // one round trip per level: the head of the record (parE, cnt, childU) is loaded while the exchange that
+            // parks / collects the sibling's (area, carrier) is in flight.  (carL, carU) is the 64-bit mailbox, NONE/NONE = empty.
+            const uint4 head = __ldcg(reinterpret_cast<const uint4 *>(e));
+            const unsigned long long mine = ((unsigned long long)car << 32) | W;
+            const unsigned long long other = atomicExch(reinterpret_cast<unsigned long long *>(&e->carL), mine);
+            if (other == ~0ull) break;                    // first to arrive: the sibling will pick this up
+            const bool up = head.z == child;              // childU
+            const u32 Wo = (u32)other, co = (u32)(other >> 32);
+            const u32 WL = up ? Wo : W, WU = up ? W : Wo;
+            const u32 cL = up ? co : car, cU = up ? car : co;
             if (WL <= WU) {                               // left loses: its label dies as the left side
                 stcg(&b.la[cL].death, v | TAG);
                 car = cU;
@@ -544,10 +540,10 @@ __global__ void __launch_bounds__(K6_THREADS) k_tournament(Dims d, Bufs b) {
                 car = cL;
                 b.flags[v] = (u8)(b.flags[v] | F_LWIN);
             }
-            // (a_wl, b_wu now hold both child areas; the listing pass reads them)
-            W = WL + WU + ldcg(&e->cnt);
+            stcg(&e->a_wl, WL); stcg(&e->b_wu, WU);       // both child areas, for the listing pass
+            W = WL + WU + head.y;                         // + cnt(v)
             child = v;
-            v = ldcg(&e->parE);
+            v = head.x;                                   // parE
         }
         if (v == NONE) {                                  // reached the root of a final cluster
             const u32 root = uf_find(b.la, leaf);

@@ -32,7 +32,7 @@ struct S2 {
     const u32 *slot_base;          // nimg + 1
     const u32 *slot_img;           // total_slots
     u32 total_slots;
-    u32 *fw;                       // total_slots: forwarding (parent | hollow << 31), NONE = root
+    u32 *fw;                       // total_slots: current cluster of the slot | hollow << 31 (roots: own index)
     u32 *mpar;                     // total_slots: merge parent (to | deepen << 31), NONE = never merged; never compressed
     u32 *mnext, *mtail;            // member lists (stage-1 slots of a cluster)
     u32 *mark;                     // distinct-neighbour stamps
@@ -50,18 +50,13 @@ struct S2 {
 
 constexpr u32 FLAGBIT = 0x80000000u;
 
-__device__ static __forceinline__ u32 s2_find(u32 *fw, u32 base, u32 s, u32 *flag) {
-    u32 x = s, f = 0;
-    while (true) {
-        const u32 p = ldcg(&fw[base + x]);
-        if (p == NONE) { *flag = f; return x; }
-        const u32 px = p & ~FLAGBIT;
-        const u32 gp = ldcg(&fw[base + px]);
-        if (gp == NONE) { *flag = p >> 31; return px; }
-        stcg(&fw[base + x], gp);              // halving: the pair of the parent (last-hop flag is preserved by design)
-        f = gp >> 31;
-        x = gp & ~FLAGBIT;
-    }
+// Every slot points DIRECTLY at its current cluster (roots point at themselves): a merge rewrites the pointers of all
+// members of the absorbed cluster (the counterpart of the reference's relabel loop, builder.rs:527-529), so resolving a
+// stage-1 label is one load.  Bit 31 = "the hop into the root was a hollow deepen merge" (the pixel is in root.holes).
+__device__ static __forceinline__ u32 s2_find(const u32 *fw, u32 base, u32 s, u32 *flag) {
+    const u32 v = ldcg(&fw[base + s]);
+    *flag = v >> 31;
+    return v & ~FLAGBIT;
 }
 
 // ------------------------------------------------------------------------------------------------- RAG
@@ -109,7 +104,7 @@ struct DegScan {
 __global__ void __launch_bounds__(256) k_s2_init(S2 a) {
     const u32 stride = gridDim.x * 256;
     for (u32 s = blockIdx.x * 256 + threadIdx.x; s < a.total_slots; s += stride) {
-        a.fw[s] = NONE; a.mpar[s] = NONE; a.mnext[s] = NONE; a.mtail[s] = s - a.slot_base[a.slot_img[s]];
+        a.fw[s] = s - a.slot_base[a.slot_img[s]]; a.mpar[s] = NONE; a.mnext[s] = NONE; a.mtail[s] = s - a.slot_base[a.slot_img[s]];
         a.mark[s] = 0; a.outpos[s] = NONE; a.cursor[s] = 0;
         const u32 area = a.rec[s].indices_len;
         if (area) atomicMax(&a.ist[a.slot_img[s]].maxarea, area);
@@ -131,7 +126,7 @@ __global__ void __launch_bounds__(256) k_s2_collect(S2 a, int epoch) {
         const u32 s = it * stride + blockIdx.x * 256 + threadIdx.x;
         bool take = false;
         u64 key = 0; u32 idx = 0;
-        if (s < a.total_slots && a.fw[s] == NONE) {
+        if (s < a.total_slots && a.fw[s] == s - a.slot_base[a.slot_img[s]]) {
             const u32 area = a.rec[s].indices_len;
             if (area && (31 - __clz((int)area)) == epoch) {
                 const u32 img = a.slot_img[s];
@@ -173,7 +168,8 @@ struct S2Shared {
     unsigned long long best;
     unsigned long long urgent[S2_URGENT];
     u32 mem[S2_MEMCHUNK];
-    u32 cur, area, ndist, perim, nmem, more, mycolor, nurg, lo, hi, stamp;
+    u32 cur, area, ndist, perim, nmem, more, mycolor, nurg, lo, hi, stamp, nchunks, newfw, target, want_perim, deepen;
+    i32 rect[4];
 };
 
 __global__ void __launch_bounds__(S2_THREADS) k_s2_epoch(S2 a, const u64 *keys, int epoch) {
@@ -214,14 +210,14 @@ __global__ void __launch_bounds__(S2_THREADS) k_s2_epoch(S2 a, const u64 *keys, 
                 else if (src == 1) { sh->urgent[which] = sh->urgent[--sh->nurg]; }
                 else { over[which] = over[--ist->nover]; }
                 const u32 idx = (u32)(kb & idx_mask), ar = (u32)((kb >> a.idx_bits) & area_mask);
-                if (a.fw[base + idx] == NONE && a.rec[base + idx].indices_len == ar) { c = idx; carea = ar; break; }
+                if (a.fw[base + idx] == idx && a.rec[base + idx].indices_len == ar) { c = idx; carea = ar; break; }
             }
             sh->cur = c; sh->area = carea;
             if (c != NONE) {
                 sh->best = ~0ull; sh->ndist = 0; sh->perim = 0;
                 sh->stamp = ++ist->stamp;
                 sh->mycolor = avg_color(a.rec[base + c].sum);
-                sh->more = c;
+                sh->more = c; sh->nchunks = 0;
             }
         }
         __syncthreads();
@@ -243,7 +239,7 @@ __global__ void __launch_bounds__(S2_THREADS) k_s2_epoch(S2 a, const u64 *keys, 
             if (tid == 0) {
                 u32 n = 0, m = sh->more;
                 while (m != NONE && n < S2_MEMCHUNK) { sh->mem[n++] = m; m = a.mnext[base + m]; }
-                sh->nmem = n; sh->more = m;
+                sh->nmem = n; sh->more = m; sh->nchunks++;
             }
             __syncthreads();
             const u32 nm = sh->nmem;
@@ -275,38 +271,46 @@ __global__ void __launch_bounds__(S2_THREADS) k_s2_epoch(S2 a, const u64 *keys, 
             __syncthreads();
             continue;
         }
-        const u32 target = (u32)sh->best;
-        const i32 mindiff = color_diff(mycolor, avg_color(a.rec[base + target].sum));
-        bool deepen = false;
-        if (a.cfg.hier_max && a.cfg.good_min < (u64)area && (u64)area < a.cfg.good_max && mindiff > a.cfg.deepen_diff) {
-            if (a.cfg.good_min == 0) deepen = true;
-            else {
-                // perimeter (shape/geometry.rs:52-75 on Cluster::to_image_with_hole): pixels of c (holes removed) with a
-                // 4-neighbour outside c
-                const vcb_cluster_rec *rc = a.rec + base + c;
-                const i32 L = rc->rect[0], T = rc->rect[1], R = rc->rect[2], B = rc->rect[3];
-                const u32 rw = (u32)(R - L), rh = (u32)(B - T);
-                const u32 *l1 = a.l1 + (size_t)img * d.n;
-                u32 cntp = 0;
-                for (u64 q = tid; q < (u64)rw * rh; q += S2_THREADS) {
-                    const u32 x = (u32)L + (u32)(q % rw), y = (u32)T + (u32)(q / rw);
-                    u32 fl;
-                    if (s2_find(a.fw, base, l1[y * d.w + x], &fl) != c || fl) continue;
-                    bool edge = (x == 0) || (y == 0) || (x + 1 == d.w) || (y + 1 == d.h);
-                    if (!edge) {
-                        const i32 off[4] = {-1, 1, -(i32)d.w, (i32)d.w};
-#pragma unroll
-                        for (int k2 = 0; k2 < 4; ++k2) {
-                            u32 f2;
-                            if (s2_find(a.fw, base, l1[(i32)(y * d.w + x) + off[k2]], &f2) != c || f2) { edge = true; break; }
-                        }
-                    }
-                    if (edge) cntp++;
-                }
-                if (cntp) atomicAdd(&sh->perim, cntp);
-                __syncthreads();
-                deepen = (u64)sh->perim < (u64)area;
+        // thread 0 alone reads the target's record here: it goes on to modify it while the others may still be behind
+        if (tid == 0) {
+            const u32 tg = (u32)sh->best;
+            const i32 md = color_diff(mycolor, avg_color(a.rec[base + tg].sum));
+            sh->target = tg;
+            sh->want_perim = 0; sh->deepen = 0;
+            if (a.cfg.hier_max && a.cfg.good_min < (u64)area && (u64)area < a.cfg.good_max && md > a.cfg.deepen_diff) {
+                if (a.cfg.good_min == 0) sh->deepen = 1; else sh->want_perim = 1;
             }
+            const vcb_cluster_rec *rc = a.rec + base + c;
+            sh->rect[0] = rc->rect[0]; sh->rect[1] = rc->rect[1]; sh->rect[2] = rc->rect[2]; sh->rect[3] = rc->rect[3];
+        }
+        __syncthreads();
+        const u32 target = sh->target;
+        bool deepen = sh->deepen != 0;
+        if (sh->want_perim) {
+            // perimeter (shape/geometry.rs:52-75 on Cluster::to_image_with_hole): pixels of c (holes removed) with a
+            // 4-neighbour outside c
+            const i32 L = sh->rect[0], T = sh->rect[1], R = sh->rect[2], B = sh->rect[3];
+            const u32 rw = (u32)(R - L), rh = (u32)(B - T);
+            const u32 *l1 = a.l1 + (size_t)img * d.n;
+            u32 cntp = 0;
+            for (u64 q = tid; q < (u64)rw * rh; q += S2_THREADS) {
+                const u32 x = (u32)L + (u32)(q % rw), y = (u32)T + (u32)(q / rw);
+                u32 fl;
+                if (s2_find(a.fw, base, l1[y * d.w + x], &fl) != c || fl) continue;
+                bool edge = (x == 0) || (y == 0) || (x + 1 == d.w) || (y + 1 == d.h);
+                if (!edge) {
+                    const i32 off[4] = {-1, 1, -(i32)d.w, (i32)d.w};
+#pragma unroll
+                    for (int k2 = 0; k2 < 4; ++k2) {
+                        u32 f2;
+                        if (s2_find(a.fw, base, l1[(i32)(y * d.w + x) + off[k2]], &f2) != c || f2) { edge = true; break; }
+                    }
+                }
+                if (edge) cntp++;
+            }
+            if (cntp) atomicAdd(&sh->perim, cntp);
+            __syncthreads();
+            deepen = (u64)sh->perim < (u64)area;
         }
         const bool hollow = (u64)ndist <= a.cfg.hollow_neighbours;
         if (tid == 0) {
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(S2_THREADS) k_s2_epoch(S2 a, const u64 *keys, 
                 rf->merged_into = target;
                 rt_->depth += 1;
             }
-            a.fw[base + c] = target | ((deepen && hollow) ? FLAGBIT : 0u);
+            sh->newfw = target | ((deepen && hollow) ? FLAGBIT : 0u);
             a.mpar[base + c] = target | (deepen ? FLAGBIT : 0u);
             a.mnext[base + a.mtail[base + target]] = c;
             a.mtail[base + target] = a.mtail[base + c];
@@ -349,6 +353,34 @@ __global__ void __launch_bounds__(S2_THREADS) k_s2_epoch(S2 a, const u64 *keys, 
             if ((31 - __clz((int)na)) == epoch) {                     // same epoch: must still be popped in order
                 const u64 k = ((u64)na << a.idx_bits) | target;
                 if (sh->nurg < S2_URGENT) sh->urgent[sh->nurg++] = k; else over[ist->nover++] = k;
+            }
+            if (sh->nchunks > 1) sh->more = c;                        // the member list no longer fits sh->mem: walk it again
+        }
+        __syncthreads();
+        // relabel: every member slot of c now resolves to the target (builder.rs:527-529)
+        {
+            const u32 nf = sh->newfw;
+            if (sh->nchunks <= 1) {
+                const u32 nm = sh->nmem;
+                for (u32 i = tid; i < nm; i += S2_THREADS) stcg(&a.fw[base + sh->mem[i]], nf);
+            } else {
+                // c's list is c -> ... -> old tail; it was appended to the target's list, so stop at the old tail of c
+                const u32 stop = a.mtail[base + target];              // == old tail of c
+                while (true) {
+                    __syncthreads();
+                    if (tid == 0) {
+                        u32 n = 0, m = sh->more;
+                        while (m != NONE && n < S2_MEMCHUNK) { sh->mem[n++] = m; m = (m == stop) ? NONE : a.mnext[base + m]; }
+                        sh->nmem = n; sh->more = m;
+                    }
+                    __syncthreads();
+                    const u32 nm = sh->nmem;
+                    for (u32 i = tid; i < nm; i += S2_THREADS) stcg(&a.fw[base + sh->mem[i]], nf);
+                    __syncthreads();
+                    const bool last = sh->more == NONE;
+                    __syncthreads();
+                    if (last) break;
+                }
             }
         }
         __syncthreads();
@@ -362,9 +394,7 @@ __global__ void __launch_bounds__(256) k_s2_labels(S2 a, u32 *labels) {
     const u32 stride = gridDim.x * 256;
     for (u32 g = blockIdx.x * 256 + threadIdx.x; g < d.N; g += stride) {
         const u32 base = a.slot_base[g / d.n];
-        u32 x = a.l1[g];
-        while (true) { const u32 p = a.fw[base + x]; if (p == NONE) break; x = p & ~FLAGBIT; }
-        labels[g] = x;
+        labels[g] = a.fw[base + a.l1[g]] & ~FLAGBIT;
     }
 }
 

@@ -163,13 +163,17 @@ __device__ static __forceinline__ i32 color_diff(u32 a, u32 b) {     // runner.r
 constexpr int S2_THREADS = 128;
 constexpr int S2_MEMCHUNK = 256;
 constexpr int S2_URGENT = 64;
+constexpr u32 S2_MAPBYTES = 24576;
 
 struct S2Shared {
     unsigned long long best;
     unsigned long long urgent[S2_URGENT];
     u32 mem[S2_MEMCHUNK];
+    u32 eoff[S2_MEMCHUNK];
+    u32 deg[S2_MEMCHUNK + 1];
     u32 cur, area, ndist, perim, nmem, more, mycolor, nurg, lo, hi, stamp, nchunks, newfw, target, want_perim, deepen;
     i32 rect[4];
+    u8 map[S2_MAPBYTES];
 };
 
 __global__ void __launch_bounds__(S2_THREADS) k_s2_epoch(S2 a, const u64 *keys, int epoch) {
@@ -243,18 +247,27 @@ __global__ void __launch_bounds__(S2_THREADS) k_s2_epoch(S2 a, const u64 *keys, 
             }
             __syncthreads();
             const u32 nm = sh->nmem;
+            // edge-parallel: prefix of the member degrees in shared memory, then one (member, edge) item per thread step
             for (u32 i = tid; i < nm; i += S2_THREADS) {
                 const u32 s = sh->mem[i];
-                const u32 e0 = a.adj_off[base + s], e1 = a.adj_off[base + s + 1];
-                for (u32 e = e0; e < e1; ++e) {
-                    u32 fl;
-                    const u32 o = s2_find(a.fw, base, a.adj[e], &fl);
-                    if (o == c || o == 0) continue;                 // label 0 and self are not neighbours (cluster.rs:150)
-                    if (atomicExch(&a.mark[base + o], stamp) != stamp) atomicAdd(&sh->ndist, 1u);
-                    const i32 df = color_diff(mycolor, avg_color(a.rec[base + o].sum));
-                    const unsigned long long k = ((unsigned long long)((u32)df * 65535u + o) << 32) | o;
-                    atomicMin(&sh->best, k);
-                }
+                sh->eoff[i] = a.adj_off[base + s];
+                sh->deg[i] = a.adj_off[base + s + 1] - sh->eoff[i];
+            }
+            __syncthreads();
+            if (tid == 0) { u32 acc = 0; for (u32 i = 0; i < nm; ++i) { const u32 dg = sh->deg[i]; sh->deg[i] = acc; acc += dg; } sh->deg[nm] = acc; }
+            __syncthreads();
+            const u32 nitems = sh->deg[nm];
+            for (u32 it = tid; it < nitems; it += S2_THREADS) {
+                u32 lo = 0, hi = nm;                                  // last member with prefix <= it
+                while (hi - lo > 1) { const u32 mid = (lo + hi) / 2; if (sh->deg[mid] <= it) lo = mid; else hi = mid; }
+                const u32 e = sh->eoff[lo] + (it - sh->deg[lo]);
+                u32 fl;
+                const u32 o = s2_find(a.fw, base, a.adj[e], &fl);
+                if (o == c || o == 0) continue;                     // label 0 and self are not neighbours (cluster.rs:150)
+                if (atomicExch(&a.mark[base + o], stamp) != stamp) atomicAdd(&sh->ndist, 1u);
+                const i32 df = color_diff(mycolor, avg_color(a.rec[base + o].sum));
+                const unsigned long long k = ((unsigned long long)((u32)df * 65535u + o) << 32) | o;
+                atomicMin(&sh->best, k);
             }
             __syncthreads();
             const bool last = sh->more == NONE;
@@ -293,20 +306,50 @@ __global__ void __launch_bounds__(S2_THREADS) k_s2_epoch(S2 a, const u64 *keys, 
             const u32 rw = (u32)(R - L), rh = (u32)(B - T);
             const u32 *l1 = a.l1 + (size_t)img * d.n;
             u32 cntp = 0;
-            for (u64 q = tid; q < (u64)rw * rh; q += S2_THREADS) {
-                const u32 x = (u32)L + (u32)(q % rw), y = (u32)T + (u32)(q / rw);
-                u32 fl;
-                if (s2_find(a.fw, base, l1[y * d.w + x], &fl) != c || fl) continue;
-                bool edge = (x == 0) || (y == 0) || (x + 1 == d.w) || (y + 1 == d.h);
-                if (!edge) {
-                    const i32 off[4] = {-1, 1, -(i32)d.w, (i32)d.w};
+            // membership of the rect (+1 halo) is staged band by band into a shared byte map; pixels outside the rect
+            // are outside the cluster by definition (the rect bounds it), pixels outside the image likewise
+            const u32 pw = rw + 2;
+            u32 band = S2_MAPBYTES / pw;
+            if (band < 3) band = 3;
+            const u32 inner = band - 2;                               // rows counted per band
+            for (u32 r0 = 0; r0 < rh; r0 += inner) {
+                const u32 rows = (rh - r0 < inner) ? rh - r0 : inner;
+                const u32 cells = (rows + 2) * pw;
+                if (cells > S2_MAPBYTES) {                            // rect wider than the map: direct (slow) evaluation
+                    for (u64 q = tid; q < (u64)rw * rows; q += S2_THREADS) {
+                        const u32 x = (u32)L + (u32)(q % rw), y = (u32)T + r0 + (u32)(q / rw);
+                        u32 fl;
+                        if (s2_find(a.fw, base, l1[y * d.w + x], &fl) != c || fl) continue;
+                        bool edge = (x == 0) || (y == 0) || (x + 1 == d.w) || (y + 1 == d.h);
+                        if (!edge) {
+                            const i32 off[4] = {-1, 1, -(i32)d.w, (i32)d.w};
 #pragma unroll
-                    for (int k2 = 0; k2 < 4; ++k2) {
-                        u32 f2;
-                        if (s2_find(a.fw, base, l1[(i32)(y * d.w + x) + off[k2]], &f2) != c || f2) { edge = true; break; }
+                            for (int k2 = 0; k2 < 4; ++k2) {
+                                u32 f2;
+                                if (s2_find(a.fw, base, l1[(i32)(y * d.w + x) + off[k2]], &f2) != c || f2) { edge = true; break; }
+                            }
+                        }
+                        if (edge) cntp++;
                     }
+                    continue;
                 }
-                if (edge) cntp++;
+                __syncthreads();
+                for (u32 q = tid; q < cells; q += S2_THREADS) {
+                    const i32 mx = (i32)(q % pw) - 1, my = (i32)(q / pw) - 1;        // rect-relative
+                    const i32 x = L + mx, y = T + (i32)r0 + my;
+                    u8 in = 0;
+                    if (mx >= 0 && mx < (i32)rw && y >= T && y < B) {
+                        u32 fl;
+                        in = (s2_find(a.fw, base, l1[(u32)y * d.w + (u32)x], &fl) == c && !fl) ? 1 : 0;
+                    }
+                    sh->map[q] = in;
+                }
+                __syncthreads();
+                for (u32 q = tid; q < rw * rows; q += S2_THREADS) {
+                    const u32 mx = q % rw + 1, my = q / rw + 1;
+                    const u32 idx = my * pw + mx;
+                    if (sh->map[idx] && !(sh->map[idx - 1] && sh->map[idx + 1] && sh->map[idx - pw] && sh->map[idx + pw])) cntp++;
+                }
             }
             if (cntp) atomicAdd(&sh->perim, cntp);
             __syncthreads();

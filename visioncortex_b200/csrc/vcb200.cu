@@ -395,11 +395,11 @@ int vcb_binary_to_clusters_device(vcb_ctx *c, const uint32_t *d_bits, uint32_t w
     if (!e) e = materialize_pool(c, d, &br, false);
     if (e) { delete hb; return e; }
     const u32 total = br.total_slots, npts = br.pool_base[1];
-    vcb_bin_cluster_rec *d_out = (vcb_bin_cluster_rec *)rt::dev_malloc((size_t)(total + 1) * sizeof(vcb_bin_cluster_rec));
-    i32 *d_xy = (i32 *)rt::dev_malloc((size_t)npts * 8 + 8);
+    vcb_bin_cluster_rec *d_out = (vcb_bin_cluster_rec *)rt::dev_malloc_async(c->st, (size_t)(total + 1) * sizeof(vcb_bin_cluster_rec));
+    i32 *d_xy = (i32 *)rt::dev_malloc_async(c->st, (size_t)npts * 8 + 8);
     i32 *d_overall = (i32 *)c->d_small;
     u32 *d_count = c->d_small + 4;
-    if (!d_out || !d_xy) { rt::dev_free(d_out); rt::dev_free(d_xy); delete hb; return fail(c, VCB_ERR_NOMEM, "device out of memory"); }
+    if (!d_out || !d_xy) { rt::dev_free_async(c->st, d_out); rt::dev_free_async(c->st, d_xy); delete hb; return fail(c, VCB_ERR_NOMEM, "device out of memory"); }
     const i32 init[5] = {0x7fffffff, 0x7fffffff, -1, -1, 0};
     rt::copy_h2d(c->st, d_overall, init, sizeof(init));
     if (total)
@@ -419,7 +419,7 @@ int vcb_binary_to_clusters_device(vcb_ctx *c, const uint32_t *d_bits, uint32_t w
         hb->info.num_clusters = ncl; hb->info.points_total = npts;
         if (ncl) { for (int k = 0; k < 4; ++k) hb->info.rect[k] = h_small[k]; }
     }
-    rt::dev_free(d_out); rt::dev_free(d_xy);
+    rt::dev_free_async(c->st, d_out); rt::dev_free_async(c->st, d_xy);
     if (e) { delete hb; return e; }
     *out = hb;
     return VCB_OK;

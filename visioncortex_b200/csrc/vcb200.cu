@@ -47,15 +47,19 @@ int validate_cfg(vcb_ctx *c, const vcb_runner_config *cfg) {
     return VCB_OK;
 }
 
-int fetch_records(vcb_clusters *h) {
+// the last record of the image gives the pool totals (indices_off + indices_len, holes_off + holes_len)
+int fetch_last_record(vcb_clusters *h) {
     if (h->have_rec) return VCB_OK;
     BatchResult *br = h->br.get();
     vcb_ctx *c = br->ctx;
     const u32 s0 = br->slot_base[h->img], s1 = br->slot_base[h->img + 1];
-    h->h_rec.resize(s1 - s0);
-    rt::copy_d2h(c->st, h->h_rec.data(), br->rec + s0, (size_t)(s1 - s0) * sizeof(vcb_cluster_rec));
-    const int e = check_stream(c);
-    if (e) return e;
+    h->h_rec.resize(1);
+    std::memset(&h->h_rec[0], 0, sizeof(vcb_cluster_rec));
+    if (s1 > s0) {
+        rt::copy_d2h(c->st, h->h_rec.data(), br->rec + s1 - 1, sizeof(vcb_cluster_rec));
+        const int e = check_stream(c);
+        if (e) return e;
+    }
     h->have_rec = true;
     return VCB_OK;
 }
@@ -262,11 +266,11 @@ int vcb_runner_run_batch(vcb_ctx *c, const vcb_runner_config *cfg, const uint8_t
 int vcb_clusters_info_get(const vcb_clusters *hc, vcb_clusters_info *info) {
     if (!hc || !info) return VCB_ERR_INVALID_ARG;
     vcb_clusters *h = const_cast<vcb_clusters *>(hc);
-    int e = fetch_records(h);
+    int e = fetch_last_record(h);
     if (e) return e;
     const BatchResult *br = h->br.get();
     info->width = br->d.w; info->height = br->d.h;
-    info->num_slots = (u32)h->h_rec.size();
+    info->num_slots = br->slot_base[h->img + 1] - br->slot_base[h->img];
     info->num_outputs = br->nout[h->img];
     u64 it = 0, ht = 0;
     if (!h->h_rec.empty()) {
@@ -296,11 +300,10 @@ int vcb_clusters_outputs(const vcb_clusters *h, uint32_t *out) {
 
 int vcb_clusters_records(const vcb_clusters *hc, vcb_cluster_rec *out) {
     if (!hc || !out) return VCB_ERR_INVALID_ARG;
-    vcb_clusters *h = const_cast<vcb_clusters *>(hc);
-    int e = fetch_records(h);
-    if (e) return e;
-    std::copy(h->h_rec.begin(), h->h_rec.end(), out);
-    return VCB_OK;
+    const BatchResult *br = hc->br.get();
+    const u32 s0 = br->slot_base[hc->img], s1 = br->slot_base[hc->img + 1];
+    rt::copy_d2h(br->ctx->st, out, br->rec + s0, (size_t)(s1 - s0) * sizeof(vcb_cluster_rec));   // straight into the caller's buffer
+    return check_stream(br->ctx);
 }
 
 int vcb_clusters_indices_pool(const vcb_clusters *h, uint32_t *out) {

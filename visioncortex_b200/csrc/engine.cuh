@@ -124,6 +124,44 @@ __global__ void k_meta_init(Dims d, Bufs b) {
     b.meta[img] = m;
 }
 
+// K1 with TMA staging: colour images whose row pitch is a multiple of 16 bytes (TMA global-stride rule).  Returns false
+// when the plain-load kernel has to be used instead (binary images, odd widths, host simulator).
+template <class P> inline bool launch_edges_tma(vcb_ctx *, const Dims &, const P &, const Bufs &, u32) { return false; }
+#ifndef VCB_HOSTSIM
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+template <> inline bool launch_edges_tma<ColorPolicy>(vcb_ctx *c, const Dims &d, const ColorPolicy &pol, const Bufs &b, u32 tiles) {
+    if (d.w % 4 != 0 || ((uintptr_t)pol.rgba & 15) != 0) return false;
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return false;
+    CUtensorMap tmap;
+    const cuuint64_t gdim[3] = {d.w, d.h, d.nimg};
+    const cuuint64_t gstride[2] = {(cuuint64_t)d.w * 4, (cuuint64_t)d.n * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)PW, (cuuint32_t)(TH + 1), 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)pol.rgba, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    rt::launch(c->st, "k_edges_tile", rt::THR, k_edges_tile_tma<ColorPolicy>, dim3(tiles), dim3(K1_THREADS), K1_SMEM, d, pol, b, tmap);
+    return true;
+}
+#endif
+
 // Runs K1..K8 for `nimg` equally sized images resident on the device and builds the per-slot records.
 // base = 1 for the colour path (slot 0 = ZERO, builder.rs:44-45,189), 0 for the binary path.
 template <class P>
@@ -135,7 +173,8 @@ inline int run_stage1(vcb_ctx *c, const Dims &d, const P &pol, u32 base, bool wa
     rt::launch(st, "k_meta_init", rt::SEQ, k_meta_init, dim3(g_img), dim3(128), 0, d, b);
 
     const u32 tiles = ((d.w + TW - 1) / TW) * ((d.h + TH - 1) / TH) * d.nimg;
-    rt::launch(st, "k_edges_tile", rt::THR, k_edges_tile<P>, dim3(tiles), dim3(K1_THREADS), K1_SMEM, d, pol, b);
+    if (!launch_edges_tma(c, d, pol, b, tiles))
+        rt::launch(st, "k_edges_tile", rt::THR, k_edges_tile<P>, dim3(tiles), dim3(K1_THREADS), K1_SMEM, d, pol, b);
     rt::launch(st, "k_flatten_events", rt::THR, k_flatten_events, dim3(grid_for(c, d.N, K2_THREADS, 16)), dim3(K2_THREADS), 0, d, b);
     {
         static int coop_blocks = 0;

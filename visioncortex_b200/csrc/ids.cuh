@@ -130,27 +130,78 @@ struct BinaryPolicy {
 // no area seen by any comparison, no label and no list order, and removes one leaf and one event from the global graph
 // (half of all leaves on noisy inputs).
 constexpr int TW = 64, TH = 32, K1_THREADS = 256, K1_PPT = TW * TH / K1_THREADS;
-constexpr int PW = TW + 2, FW = TW + 1;
-constexpr size_t K1_SMEM = (size_t)(TH + 1) * PW * 4 + (size_t)TW * TH * 2 + (size_t)FW * TH;
+constexpr int PW = TW + 8, FW = TW + 1, XO = 4;   // box = 72 x 33 pixels starting at (x0 - 4, y0 - 1): TMA needs the inner
+                                                    // start coordinate and the box row to be multiples of 16 bytes (probed on B200)
+constexpr size_t K1_PIX_BYTES = (size_t)(TH + 1) * PW * 4;
+constexpr size_t K1_SMEM = K1_PIX_BYTES + (size_t)TW * TH * 2 + (((size_t)FW * TH + 15) & ~(size_t)15) + 16;
 
+template <class P> __device__ __forceinline__ void edges_tile_body(const Dims &d, const P &pol, const Bufs &b, u32 *pix, u32 img,
+                                                                    u32 x0, u32 y0);
+
+// staging by plain loads (any width, binary images, and the host simulator)
 template <class P> __global__ void __launch_bounds__(K1_THREADS) k_edges_tile(Dims d, P pol, Bufs b) {
     VCB_SMEM(u32, pix);
-    u16 *lp = (u16 *)(pix + (TH + 1) * PW);
-    u8 *fl = (u8 *)(lp + TW * TH);
     const u32 tiles_x = (d.w + TW - 1) / TW, tiles_y = (d.h + TH - 1) / TH;
     const u32 tile = blockIdx.x;
     const u32 img = tile / (tiles_x * tiles_y), tr = tile % (tiles_x * tiles_y);
     const u32 x0 = (tr % tiles_x) * TW, y0 = (tr / tiles_x) * TH;
     const u32 base = img * d.n;
-
     for (int idx = threadIdx.x; idx < (TH + 1) * PW; idx += K1_THREADS) {
         const int ly = idx / PW, lx = idx % PW;
-        const i64 gy = (i64)y0 - 1 + ly, gx = (i64)x0 - 1 + lx;
+        const i64 gy = (i64)y0 - 1 + ly, gx = (i64)x0 - XO + lx;
         u32 v = 0;
         if (gy >= 0 && gx >= 0 && gy < d.h && gx < d.w) v = pol.load(base + (u32)gy * d.w + (u32)gx);
         pix[idx] = v;
     }
     __syncthreads();
+    edges_tile_body(d, pol, b, pix, img, x0, y0);
+}
+
+#ifndef VCB_HOSTSIM
+// staging by TMA: one elected thread issues a 3-D bulk tensor copy (x, y, image) of the 68 x 33 pixel box -- halo included,
+// out-of-image coordinates zero-filled by the hardware -- into shared memory and the CTA waits on an mbarrier.
+__device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+template <class P> __global__ void __launch_bounds__(K1_THREADS)
+k_edges_tile_tma(Dims d, P pol, Bufs b, const __grid_constant__ CUtensorMap tmap) {
+    VCB_SMEM(u32, pix);
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(pix) + K1_SMEM - 16);
+    const u32 tiles_x = (d.w + TW - 1) / TW, tiles_y = (d.h + TH - 1) / TH;
+    const u32 tile = blockIdx.x;
+    const u32 img = tile / (tiles_x * tiles_y), tr = tile % (tiles_x * tiles_y);
+    const u32 x0 = (tr % tiles_x) * TW, y0 = (tr / tiles_x) * TH;
+    const u32 bar = smem_addr(mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((u32)K1_PIX_BYTES) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(smem_addr(pix)), "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"((int)x0 - XO), "r"((int)y0 - 1),
+            "r"((int)img), "r"(bar)
+            : "memory");
+    }
+    {
+        u32 done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                : "=r"(done)
+                : "r"(bar)
+                : "memory");
+        }
+    }
+    edges_tile_body(d, pol, b, pix, img, x0, y0);
+}
+#endif
+
+template <class P> __device__ __forceinline__ void edges_tile_body(const Dims &d, const P &pol, const Bufs &b, u32 *pix, u32 img,
+                                                                    u32 x0, u32 y0) {
+    u16 *lp = (u16 *)(pix + (TH + 1) * PW);
+    u8 *fl = (u8 *)(lp + TW * TH);
+    const u32 base = img * d.n;
 
     u32 err = 0;
     for (int i = threadIdx.x; i < FW * TH; i += K1_THREADS) {      // tile pixels + one halo column to the right (M flag only)
@@ -158,8 +209,8 @@ template <class P> __global__ void __launch_bounds__(K1_THREADS) k_edges_tile(Di
         const u32 gx = x0 + lx, gy = y0 + ly;
         u32 f = J_NONE;
         if (gx < d.w && gy < d.h) {
-            const u32 c = pix[(ly + 1) * PW + lx + 1], up = pix[ly * PW + lx + 1];
-            const u32 left = pix[(ly + 1) * PW + lx], ul = pix[ly * PW + lx];
+            const u32 c = pix[(ly + 1) * PW + lx + XO], up = pix[ly * PW + lx + XO];
+            const u32 left = pix[(ly + 1) * PW + lx + XO - 1], ul = pix[ly * PW + lx + XO - 1];
             f = pol.classify(c, up, left, ul, gy > 0, gx > 0, &err);
         }
         fl[i] = (u8)f;
@@ -220,7 +271,7 @@ template <class P> __global__ void __launch_bounds__(K1_THREADS) k_edges_tile(Di
         if (j == J_NEW) {
             LeafA a; a.ufp = g; a.best0 = NONE; a.best1 = NONE; a.parL = NONE; a.cnt = 1; a.death = NONE; a.label = 0; a.flabel = 0;
             b.la[g] = a;
-            LeafS s; pol.stats(pix[(ly + 1) * PW + lx + 1], s.sum); s.npx = 1; s.pad[0] = s.pad[1] = s.pad[2] = 0;
+            LeafS s; pol.stats(pix[(ly + 1) * PW + lx + XO], s.sum); s.npx = 1; s.pad[0] = s.pad[1] = s.pad[2] = 0;
             b.ls[g] = s;
             LeafR r; r.minx = r.maxx = (i32)gx; r.miny = r.maxy = (i32)gy;
             b.lr[g] = r;

@@ -29,9 +29,10 @@ template <class T> __device__ static inline void stcg(T *p, T v) { __atomic_stor
 __device__ static inline u8 ldcg8(const u8 *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
 #else
 #include <cooperative_groups.h>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #define VCB_SMEM(T, name)                                      \
-    extern __shared__ __align__(16) unsigned char _vcb_smem[]; \
+    extern __shared__ __align__(128) unsigned char _vcb_smem[]; \
     T *name = reinterpret_cast<T *>(_vcb_smem)
 #define VCB_GRID_SYNC() cooperative_groups::this_grid().sync()
 template <class T> __device__ static __forceinline__ T ldcg(const T *p) { return __ldcg(p); }

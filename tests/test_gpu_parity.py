@@ -21,7 +21,7 @@ def run_gpu(gpu, img, cfg, **kw):
     try:
         return gpu.runner_run(img, cfg, **kw)
     except VcbError as e:
-        if e.status == 3 and "not clean" in str(e):
+        if e.status == 3 and ("not clean" in str(e) or "stale cluster_upleft" in str(e)):
             raise Fenced()
         raise
 
@@ -190,12 +190,12 @@ def test_hierarchical_random_small(gpu, oracle):
         cfg.good_max_area = int(rng.choice([50, 65536]))
         cfg.deepen_diff = int(rng.choice([0, 16, 64]))
         cfg.hollow_neighbours = int(rng.choice([0, 1, 2]))
-        ref = oracle.runner_run(img, cfg, pools=False, color_image=True)
+        ref = oracle.runner_run(img, cfg, pools=True, color_image=True)
         try:
-            got = run_gpu(gpu, img, cfg, pools=False, color_image=True)
+            got = run_gpu(gpu, img, cfg, pools=True, color_image=True)
         except Fenced:
             continue
-        assert_same_clusters(got, ref, pools=False, ctx=f"hier case {k} {img.shape} hier={hier}")
+        assert_same_clusters(got, ref, pools=True, ctx=f"hier case {k} {img.shape} hier={hier}")
 
 
 def test_hierarchical_medium(gpu, oracle):
@@ -238,3 +238,38 @@ def test_c3_cutout_two_pass_4k(gpu, oracle):
     except Exception as e:        # the rendered image may make the key unclean: then the oracle result is order-dependent
         pytest.skip(f"pass 2 fenced: {e}")
     assert_same_clusters(got2, ref2, pools=False, ctx="C3 pass 2")
+
+
+def test_c4_default_with_pools(gpu, oracle):
+    """Cluster.indices / Cluster.holes in exact order after the hierarchical stage (default config, 960x540)."""
+    img = synth.g2_scene(960, 540, seed=101)
+    cfg = make_config()
+    ref = oracle.runner_run(img, cfg, pools=True, color_image=True)
+    got = gpu.runner_run(img, cfg, pools=True, color_image=True)
+    assert_same_clusters(got, ref, pools=True, ctx="C4-style with pools")
+
+
+def test_diagonal_colour(gpu, oracle):
+    """diagonal = true (BuilderConfig default, builder.rs:22-32).  Inputs on which the reference resurrects a dead slot through
+    the stale cluster_upleft read are detected on the device and fenced, never silently different."""
+    rng = np.random.default_rng(71)
+    ok = fenced = 0
+    for k in range(150):
+        img, cfg = random_case(rng, max_side=40, keyed=(k % 4 == 3), hierarchical=[0, HM, 0][k % 3], diagonal=True)
+        ref = oracle.runner_run(img, cfg, pools=True, color_image=True)
+        try:
+            got = run_gpu(gpu, img, cfg, pools=True, color_image=True)
+        except Fenced:
+            fenced += 1
+            continue
+        assert_same_clusters(got, ref, pools=True, ctx=f"diag case {k} {img.shape}")
+        ok += 1
+    assert ok > 100, (ok, fenced)
+    img = synth.g2_scene(1280, 720, seed=9)
+    cfg = c2_config(1280, 720, diagonal=1)
+    ref = oracle.runner_run(img, cfg, pools=False)
+    try:
+        got = run_gpu(gpu, img, cfg, pools=False)
+        assert_same_clusters(got, ref, pools=False, ctx="diag 720p")
+    except Fenced:
+        pass

@@ -51,6 +51,8 @@ struct BatchResult {
     u32 *d_slot_img = nullptr;        // total_slots
     u32 *labels1 = nullptr;           // stage-1 labels when a hierarchical stage ran (labels then holds the final ones)
     u32 *mpar = nullptr, *outpos = nullptr;   // stage-2 merge forest / first output position per slot
+    u32 *childoff = nullptr, *holeoff = nullptr, *off1 = nullptr, *hpool = nullptr, *pool1 = nullptr;
+    std::vector<u32> hpool_base, pool1_base;
     bool hier = false;
     u32 *pool = nullptr;              // concatenated Cluster.indices of all images (exact order), when materialised
     u8 *pixels = nullptr;             // retained copy of the input (Clusters.pixels, container.rs:8; take_image :34-40)
@@ -65,7 +67,8 @@ inline BatchResult::~BatchResult() {
     if (!ctx) return;
     rt::set_device(ctx->device);
     for (void *p : {(void *)labels, (void *)rec, (void *)outputs, (void *)d_slot_base, (void *)d_slot_img, (void *)pool,
-                    (void *)pixels, (void *)labels1, (void *)mpar, (void *)outpos})
+                    (void *)pixels, (void *)labels1, (void *)mpar, (void *)outpos, (void *)childoff, (void *)holeoff, (void *)off1,
+                    (void *)hpool, (void *)pool1})
         rt::dev_free_async(ctx->st, p);
 }
 
@@ -89,7 +92,7 @@ inline int ensure_workspace(vcb_ctx *c, size_t N, size_t nimg) {
         bool ok = true;
         ok &= grow(c->b.flags, cap); ok &= grow(c->b.pc, cap); ok &= grow(c->b.la, cap); ok &= grow(c->b.ls, cap);
         ok &= grow(c->b.lr, cap); ok &= grow(c->b.ev, cap); ok &= grow(c->b.cand, cap); ok &= grow(c->b.newlist, cap);
-        ok &= grow(c->b.attr, cap); ok &= grow(c->b.labex, cap);
+        ok &= grow(c->b.attr, cap); ok &= grow(c->b.labex, cap); ok &= grow(c->b.leaflist, cap);
         const size_t chunks = cap / 2048 + 4;
         ok &= grow(c->chunksum, 256 * chunks / 2048 + chunks + 1024);
         ok &= grow(c->rs_table, 256 * chunks + 16);
@@ -186,6 +189,7 @@ inline int run_stage1(vcb_ctx *c, const Dims &d, const P &pol, u32 base, bool wa
     }
     rt::launch(st, "k_chain_insert", rt::SEQ, k_chain_insert, dim3(grid_for(c, d.N / 2, K4_THREADS, 16)), dim3(K4_THREADS), 0, d, b);
     prims::scan(st, "scan_new", NewScan{d, b}, c->chunksum, d.N, c->sms * 8);
+    prims::scan(st, "scan_new", LeafScan{d, b}, c->chunksum, d.N, c->sms * 8);
     {
         // rows per segment: enough threads to fill the machine, as few restarts as possible
         const u64 wpad = (d.w + 31) & ~31u;
@@ -323,9 +327,11 @@ inline int run_stage2(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg, b
     }
     res->mpar = (u32 *)rt::dev_malloc_async(st, (size_t)total * 4 + 4);
     res->outpos = (u32 *)rt::dev_malloc_async(st, (size_t)total * 4 + 4);
+    res->childoff = (u32 *)rt::dev_malloc_async(st, (size_t)total * 4 + 4);
+    res->holeoff = (u32 *)rt::dev_malloc_async(st, (size_t)total * 4 + 4);
     res->labels1 = res->labels;
     res->labels = (u32 *)rt::dev_malloc_async(st, (size_t)d.N * 4);
-    if (!res->mpar || !res->outpos || !res->labels) return VCB_ERR_NOMEM;
+    if (!res->mpar || !res->outpos || !res->labels || !res->childoff || !res->holeoff) return VCB_ERR_NOMEM;
     res->hier = true;
 
     u32 max_slots = 1;
@@ -337,6 +343,7 @@ inline int run_stage2(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg, b
     a.cfg.can_discard = (cfg->keying_action == VCB_KEYING_DISCARD && has_key) ? 1 : 0;
     a.cfg.hier_max = cfg->hierarchical == VCB_HIERARCHICAL_MAX;
     a.l1 = res->labels1; a.rec = res->rec; a.slot_base = res->d_slot_base; a.slot_img = res->d_slot_img; a.total_slots = total;
+    a.childoff = res->childoff; a.holeoff = res->holeoff;
     a.fw = c->s2_fw; a.mpar = res->mpar; a.mnext = c->s2_mnext; a.mtail = c->s2_mtail; a.mark = c->s2_mark; a.outpos = res->outpos;
     a.adj_off = c->s2_adj_off; a.adj = c->s2_adj; a.cursor = c->s2_cursor; a.outputs = res->outputs; a.over = c->s2_over;
     a.ist = c->s2_ist; a.keys = c->sk0; a.vals = c->sv0;
@@ -375,6 +382,24 @@ inline int run_stage2(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg, b
     rt::copy_d2h(st, h, c->s2_ist, d.nimg * sizeof(S2ImgState));
     if (rt::stream_sync(st) != 0 || st.last_error) { c->err = st.last_error_text; st.last_error = 0; return VCB_ERR_CUDA; }
     for (u32 i = 0; i < d.nimg; ++i) res->nout[i] = h[i].nout;
+    if (res->pool1) {
+        // ordered indices / holes pools from the stage-1 pool and the merge forest
+        u32 *d_ib = c->d_small, *d_hb = c->d_small + (d.nimg + 2), *d_p1b = c->d_small + 2 * (d.nimg + 2);
+        rt::launch(st, "k_pool_base", rt::SEQ, k_pool_base, dim3(1), dim3(32), 0, (const vcb_cluster_rec *)res->rec, (const u32 *)res->d_slot_base, d.nimg, d_ib);
+        rt::launch(st, "k_hpool_base", rt::SEQ, k_hpool_base, dim3(1), dim3(32), 0, (const vcb_cluster_rec *)res->rec, (const u32 *)res->d_slot_base, d.nimg, d_hb);
+        rt::copy_h2d(st, d_p1b, res->pool1_base.data(), (d.nimg + 1) * sizeof(u32));
+        u32 *hb = (u32 *)c->h_pinned;
+        rt::copy_d2h(st, hb, d_ib, (d.nimg + 1) * sizeof(u32));
+        rt::copy_d2h(st, hb + d.nimg + 1, d_hb, (d.nimg + 1) * sizeof(u32));
+        if (rt::stream_sync(st) != 0 || st.last_error) { c->err = st.last_error_text; st.last_error = 0; return VCB_ERR_CUDA; }
+        res->pool_base.assign(hb, hb + d.nimg + 1);
+        res->hpool_base.assign(hb + d.nimg + 1, hb + 2 * (d.nimg + 1));
+        res->pool = (u32 *)rt::dev_malloc_async(st, (size_t)res->pool_base[d.nimg] * 4 + 4);
+        res->hpool = (u32 *)rt::dev_malloc_async(st, (size_t)res->hpool_base[d.nimg] * 4 + 4);
+        if (!res->pool || !res->hpool) return VCB_ERR_NOMEM;
+        rt::launch(st, "k_s2_pool_scatter", rt::SEQ, k_s2_pool_scatter, dim3(grid_for(c, res->pool1_base[d.nimg], 256, 16)), dim3(256), 0, a,
+                   (const u32 *)res->pool1, (const u32 *)d_p1b, (const u32 *)res->off1, (const u32 *)d_ib, (const u32 *)d_hb, res->pool, res->hpool);
+    }
     return VCB_OK;
 }
 

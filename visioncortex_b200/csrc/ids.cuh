@@ -48,12 +48,13 @@ struct Counters {
     u32 err;               // bit 0: unclean key colour, bit 1: stale-upleft resurrection
     u32 kt;                // total leaves (all images)
     u32 rounds;            // boruvka rounds executed
-    u32 pad[2];
+    u32 lt;                // total real leaves (NEW events that were not contracted)
+    u32 pad[1];
 };
 
 struct Bufs {
     u8 *flags; u32 *pc; LeafA *la; LeafS *ls; LeafR *lr; EvRec *ev;
-    u32 *cand; u32 *newlist; u32 *attr; u32 *labex; ImgMeta *meta; Counters *ctr;
+    u32 *cand; u32 *newlist; u32 *leaflist; u32 *attr; u32 *labex; ImgMeta *meta; Counters *ctr;
 };
 
 // --------------------------------------------------------------------------------------------------------------
@@ -490,6 +491,16 @@ __global__ void __launch_bounds__(K5_THREADS) k_attribute(Dims d, P pol, Bufs b,
             }
             const u32 gprev_left = __shfl_up_sync(0xffffffffu, gprev, 1);   // node of pixel (x-1, y-1), for UPLEFT
             const u32 gprev_right = __shfl_down_sync(0xffffffffu, gprev, 1); // node of pixel (x+1, y-1), for RUP
+            if (valid && (f & F_MSF) && j == J_UPLEFT) {
+                // builder.rs:301-305 reads cluster_upleft BEFORE the merge step: if the up-left pixel's cluster is one of the
+                // two merging sides and loses, the reference labels this pixel with the dead slot.
+                // Record which side it is on; k_tournament rejects the input if that side loses.
+                u32 ul = (lane > 0 && gprev_left != NONE) ? gprev_left : (b.pc[p - d.w - 1] | TAG);
+                ul = climb(b, ul, p - 1);
+                u32 side = 0;
+                if (node_par(b, ul) == p) side = (ul == upnode) ? 2u : 1u;
+                stcg(&b.ev[p].arrive, side);
+            }
             bool resolved = true;
             if (valid && j != J_NONE) {
                 if (j == J_NEW) g = p | TAG;
@@ -558,17 +569,27 @@ struct NewScan {
     }
 };
 
+// ordered compaction of the real leaves only (the per-leaf kernels run over this list)
+struct LeafScan {
+    Dims d; Bufs b;
+    __device__ u32 count() const { return d.N; }
+    __device__ u32 value(u32 i) const { return (b.flags[i] & J_MASK) == J_NEW ? 1u : 0u; }
+    __device__ void emit(u32 i, u32 ex, u32 v) const {
+        if (v) b.leaflist[ex] = i;
+        if (i == d.N - 1) b.ctr->lt = ex + v;
+    }
+};
+
 // --------------------------------------------------------------------------------------------------------------
 // K6: tournament, bottom-up over the reconstruction tree (one thread per leaf; at every event the first arriving
 // child parks its (area, carrier) and leaves, the second one decides the winner and carries on).
 // builder.rs:313-325: `if area(left) <= area(up) { combine(left -> up) } else { combine(up -> left) }`.
 constexpr int K6_THREADS = 256;
 __global__ void __launch_bounds__(K6_THREADS) k_tournament(Dims d, Bufs b) {
-    const u32 kt = ldcg(&b.ctr->kt);
+    const u32 lt = ldcg(&b.ctr->lt);
     const u32 stride = gridDim.x * K6_THREADS;
-    for (u32 k = blockIdx.x * K6_THREADS + threadIdx.x; k < kt; k += stride) {
-        const u32 leaf = b.newlist[k];
-        if (leaf & TAG) continue;
+    for (u32 k = blockIdx.x * K6_THREADS + threadIdx.x; k < lt; k += stride) {
+        const u32 leaf = b.leaflist[k];
         u32 child = leaf | TAG, W = ldcg(&b.la[leaf].cnt), car = leaf;
         u32 v = ldcg(&b.la[leaf].parL);
         while (v != NONE) {
@@ -580,16 +601,19 @@ __global__ void __launch_bounds__(K6_THREADS) k_tournament(Dims d, Bufs b) {
             const unsigned long long other = atomicExch(reinterpret_cast<unsigned long long *>(&e->carL), mine);
             if (other == ~0ull) break;                    // first to arrive: the sibling will pick this up
             const bool up = head.z == child;              // childU
+            const u32 stale = head.w;                     // side of the up-left pixel's cluster (UPLEFT join at an event), 0 = none
             const u32 Wo = (u32)other, co = (u32)(other >> 32);
             const u32 WL = up ? Wo : W, WU = up ? W : Wo;
             const u32 cL = up ? co : car, cU = up ? car : co;
             if (WL <= WU) {                               // left loses: its label dies as the left side
                 stcg(&b.la[cL].death, v | TAG);
                 car = cU;
+                if (stale == 1) atomicOr(&b.ctr->err, 2u);
             } else {
                 stcg(&b.la[cU].death, v);
                 car = cL;
                 b.flags[v] = (u8)(b.flags[v] | F_LWIN);
+                if (stale == 2) atomicOr(&b.ctr->err, 2u);
             }
             stcg(&e->a_wl, WL); stcg(&e->b_wu, WU);       // both child areas, for the listing pass
             W = WL + WU + head.y;                         // + cnt(v)
@@ -625,7 +649,7 @@ struct LabelScan {
     __device__ void emit(u32 k, u32 ex, u32 v) const {
         const u32 e = b.newlist[k];
         b.labex[k] = ex;
-        if (!(e & TAG)) b.la[e].flabel = v;               // not-in-D flag, consumed by k_image_meta
+        if (!(e & TAG)) { b.la[e].label = ex; b.la[e].flabel = v; }   // raw scan value + not-in-D flag
         const u32 img = (e & ~TAG) / d.n;
         if (k == b.meta[img].leaf_begin) b.meta[img].notd_base = ex;
     }
@@ -652,21 +676,19 @@ __global__ void k_image_meta(Dims d, Bufs b, u32 base) {
 // per leaf: image-relative label
 constexpr int K8_THREADS = 256;
 __global__ void __launch_bounds__(K8_THREADS) k_leaf_labels(Dims d, Bufs b, u32 base) {
-    const u32 kt = ldcg(&b.ctr->kt);
+    const u32 lt = ldcg(&b.ctr->lt);
     const u32 stride = gridDim.x * K8_THREADS;
-    for (u32 k = blockIdx.x * K8_THREADS + threadIdx.x; k < kt; k += stride) {
-        const u32 p = b.newlist[k];
-        if (p & TAG) continue;
-        b.la[p].label = base + b.labex[k] - b.meta[p / d.n].notd_base;
+    for (u32 k = blockIdx.x * K8_THREADS + threadIdx.x; k < lt; k += stride) {
+        const u32 p = b.leaflist[k];
+        b.la[p].label = base + b.la[p].label - b.meta[p / d.n].notd_base;
     }
 }
 // per leaf: label of the carrier of its final cluster
 __global__ void __launch_bounds__(K8_THREADS) k_leaf_final(Dims d, Bufs b) {
-    const u32 kt = ldcg(&b.ctr->kt);
+    const u32 lt = ldcg(&b.ctr->lt);
     const u32 stride = gridDim.x * K8_THREADS;
-    for (u32 k = blockIdx.x * K8_THREADS + threadIdx.x; k < kt; k += stride) {
-        const u32 p = b.newlist[k];
-        if (p & TAG) continue;
+    for (u32 k = blockIdx.x * K8_THREADS + threadIdx.x; k < lt; k += stride) {
+        const u32 p = b.leaflist[k];
         const u32 root = uf_find(b.la, p);
         const u32 car = ldcg(&b.la[root].best0);
         b.la[p].flabel = ldcg(&b.la[car].label);

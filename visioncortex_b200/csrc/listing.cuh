@@ -46,13 +46,13 @@ __device__ static __forceinline__ void list_init_node(const Bufs &b, u32 node) {
 constexpr int LST_THREADS = 256;
 // work items: [0, kt) = leaves (newlist), [kt, kt + ncand) = candidate events (effective ones only)
 __device__ static __forceinline__ u32 list_node(const Bufs &b, u32 t, u32 kt) {
-    if (t < kt) { const u32 e = b.newlist[t]; return (e & TAG) ? NONE : (e | TAG); }
+    if (t < kt) return b.leaflist[t] | TAG;
     const u32 p = b.cand[t - kt] & ~TAG;
     return (b.flags[p] & F_MSF) ? p : NONE;
 }
 
 __global__ void __launch_bounds__(LST_THREADS) k_list_init(Bufs b) {
-    const u32 kt = ldcg(&b.ctr->kt), total = kt + ldcg(&b.ctr->ncand);
+    const u32 kt = ldcg(&b.ctr->lt), total = kt + ldcg(&b.ctr->ncand);
     const u32 stride = gridDim.x * LST_THREADS;
     for (u32 t = blockIdx.x * LST_THREADS + threadIdx.x; t < total; t += stride) {
         const u32 node = list_node(b, t, kt);
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(LST_THREADS) k_list_init(Bufs b) {
 }
 
 __global__ void __launch_bounds__(LST_THREADS) k_list_jump(Bufs b) {
-    const u32 kt = ldcg(&b.ctr->kt), total = kt + ldcg(&b.ctr->ncand);
+    const u32 kt = ldcg(&b.ctr->lt), total = kt + ldcg(&b.ctr->ncand);
     const u32 stride = gridDim.x * LST_THREADS;
     for (u32 t = blockIdx.x * LST_THREADS + threadIdx.x; t < total; t += stride) {
         const u32 node = list_node(b, t, kt);

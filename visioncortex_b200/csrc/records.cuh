@@ -24,11 +24,10 @@ __global__ void __launch_bounds__(REC_THREADS) k_rec_init(vcb_cluster_rec *rec, 
 // per leaf: fold the provisional cluster's sums / rect into the slot of its final cluster (ColorSum::merge color.rs:278-284,
 // BoundingRect::merge bound.rs:204-219; both order-independent)
 __global__ void __launch_bounds__(REC_THREADS) k_rec_accum(Dims d, Bufs b, vcb_cluster_rec *rec, const u32 *slot_base) {
-    const u32 kt = ldcg(&b.ctr->kt);
+    const u32 lt = ldcg(&b.ctr->lt);
     const u32 stride = gridDim.x * REC_THREADS;
-    for (u32 k = blockIdx.x * REC_THREADS + threadIdx.x; k < kt; k += stride) {
-        const u32 p = b.newlist[k];
-        if (p & TAG) continue;
+    for (u32 k = blockIdx.x * REC_THREADS + threadIdx.x; k < lt; k += stride) {
+        const u32 p = b.leaflist[k];
         vcb_cluster_rec *r = rec + slot_base[p / d.n] + b.la[p].flabel;
         const LeafS s = b.ls[p];
         const LeafR q = b.lr[p];

@@ -33,7 +33,8 @@ struct S2 {
     const u32 *slot_img;           // total_slots
     u32 total_slots;
     u32 *fw;                       // total_slots: current cluster of the slot | hollow << 31 (roots: own index)
-    u32 *mpar;                     // total_slots: merge parent (to | deepen << 31), NONE = never merged; never compressed
+    u32 *mpar;                     // total_slots: merge parent (to | deepen << 31 | hollow-deepen << 30), NONE = never merged
+    u32 *childoff, *holeoff;       // offset of the absorbed list inside to.indices / to.holes at merge time
     u32 *mnext, *mtail;            // member lists (stage-1 slots of a cluster)
     u32 *mark;                     // distinct-neighbour stamps
     u32 *outpos;                   // first position in clusters_output, NONE if absent
@@ -49,6 +50,8 @@ struct S2 {
 };
 
 constexpr u32 FLAGBIT = 0x80000000u;
+constexpr u32 HOLLOWBIT = 0x40000000u;
+constexpr u32 MPAR_MASK = 0x3fffffffu;
 
 // Every slot points DIRECTLY at its current cluster (roots point at themselves): a merge rewrites the pointers of all
 // members of the absorbed cluster (the counterpart of the reference's relabel loop, builder.rs:527-529), so resolving a
@@ -376,6 +379,8 @@ __global__ void __launch_bounds__(S2_THREADS) k_s2_epoch(S2 a, const u64 *keys, 
                     rt_->rect[3] = rt_->rect[3] > rf->rect[3] ? rt_->rect[3] : rf->rect[3];
                 }
             }
+            a.childoff[base + c] = rt_->indices_len;                 // builder.rs:529: to.indices.append(from.indices)
+            a.holeoff[base + c] = rt_->holes_len;
             rt_->indices_len += area;
             if (!deepen) {
                 for (int k2 = 0; k2 < 5; ++k2) rf->sum[k2] = 0;
@@ -387,7 +392,7 @@ __global__ void __launch_bounds__(S2_THREADS) k_s2_epoch(S2 a, const u64 *keys, 
                 rt_->depth += 1;
             }
             sh->newfw = target | ((deepen && hollow) ? FLAGBIT : 0u);
-            a.mpar[base + c] = target | (deepen ? FLAGBIT : 0u);
+            a.mpar[base + c] = target | (deepen ? FLAGBIT : 0u) | ((deepen && hollow) ? HOLLOWBIT : 0u);
             a.mnext[base + a.mtail[base + target]] = c;
             a.mtail[base + target] = a.mtail[base + c];
             ist->nmerge++;
@@ -470,7 +475,7 @@ __global__ void __launch_bounds__(256) k_s2_slot_color(S2 a, u32 *slot_color) {
             const bool owns = (mp == NONE) || (mp & FLAGBIT);
             if (owns) { const u32 op = a.outpos[base + x]; if (op < best) { best = op; bestx = x; } }
             if (mp == NONE) break;
-            x = mp & ~FLAGBIT;
+            x = mp & MPAR_MASK;
         }
         u32 col = 0;
         if (bestx != NONE) {
@@ -484,6 +489,52 @@ __global__ void __launch_bounds__(256) k_s2_paint(S2 a, const u32 *slot_color, u
     const u32 stride = gridDim.x * 256;
     const u32 base = a.slot_base[img];
     for (u32 p = blockIdx.x * 256 + threadIdx.x; p < a.d.n; p += stride) out[p] = slot_color[base + a.l1[(size_t)img * a.d.n + p]];
+}
+
+// Ordered `Cluster.indices` / `Cluster.holes` after the hierarchical stage.  A merge appends the absorbed cluster's whole
+// list to the target's (builder.rs:526-533), a deepened cluster also keeps its own copy (builder.rs:514-524) and a hollow
+// deepen merge appends the same list to target.holes (builder.rs:503-507).  So every list is a contiguous run of the
+// merge forest's preorder, and a stage-1 pixel with rank r in its stage-1 list lands at offset r + sum(childoff) in every
+// owning ancestor.  One thread per entry of the stage-1 pool walks its merge chain.
+__global__ void __launch_bounds__(256) k_s2_pool_scatter(S2 a, const u32 *pool1, const u32 *pool1_base, const u32 *off1,
+                                                         const u32 *ipool_base, const u32 *hpool_base, u32 *out_i, u32 *out_h) {
+    const Dims d = a.d;
+    const u32 total = pool1_base[d.nimg];
+    const u32 stride = gridDim.x * 256;
+    for (u32 i = blockIdx.x * 256 + threadIdx.x; i < total; i += stride) {
+        u32 lo = 0, hi = d.nimg;                                      // image owning pool entry i
+        while (hi - lo > 1) { const u32 mid = (lo + hi) / 2; if (pool1_base[mid] <= i) lo = mid; else hi = mid; }
+        const u32 img = lo, base = a.slot_base[img];
+        const u32 p = pool1[i];
+        u32 x = a.l1[(size_t)img * d.n + p];
+        u32 rel = (i - pool1_base[img]) - off1[base + x];
+        while (true) {
+            const u32 mp = a.mpar[base + x];
+            if (mp == NONE || (mp & FLAGBIT)) out_i[ipool_base[img] + (u32)a.rec[base + x].indices_off + rel] = p;
+            if (mp == NONE) break;
+            const u32 z = mp & MPAR_MASK;
+            if (mp & HOLLOWBIT) out_h[hpool_base[img] + (u32)a.rec[base + z].holes_off + a.holeoff[base + x] + rel] = p;
+            rel += a.childoff[base + x];
+            x = z;
+        }
+    }
+}
+__global__ void k_save_off1(const vcb_cluster_rec *rec, u32 total, u32 *off1) {
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < total; s += stride) off1[s] = (u32)rec[s].indices_off;
+}
+__global__ void k_hpool_base(const vcb_cluster_rec *rec, const u32 *slot_base, u32 nimg, u32 *hpool_base) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        u32 acc = 0;
+        for (u32 i = 0; i < nimg; ++i) {
+            hpool_base[i] = acc;
+            if (slot_base[i + 1] > slot_base[i]) {
+                const vcb_cluster_rec *l = rec + slot_base[i + 1] - 1;
+                acc += (u32)l->holes_off + l->holes_len;
+            }
+        }
+        hpool_base[nimg] = acc;
+    }
 }
 
 }  // namespace vcb

@@ -72,7 +72,6 @@ int run_color(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w,
     const u64 n64 = (u64)w * h;
     if (n64 == 0 || n64 * nimg >= 0x7fffff00ull) return fail(c, VCB_ERR_INVALID_ARG, "width*height*n must be in 1..2^31");
     if (!d_rgba) return fail(c, VCB_ERR_INVALID_ARG, "null image");
-    if (cfg->diagonal) return fail(c, VCB_ERR_UNSUPPORTED, "diagonal=true colour clustering (stale-upleft quirk) is fenced, see DESIGN.md");
     rt::set_device(c->device);
     Dims d{w, h, (u32)n64, (u32)nimg, (u32)(n64 * nimg)};
     e = ensure_workspace(c, d.N, d.nimg);
@@ -101,6 +100,7 @@ int run_color(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w,
     e = run_stage1(c, d, pol, 1u, want_pool, keep ? 1 : 0, br.get(), meta, ctr);
     if (e) return e;
     if (ctr.err & 1u) return fail(c, VCB_ERR_UNSUPPORTED, "key colour is not clean: a non-key pixel is color_same to the key (order-dependent in the reference)");
+    if (ctr.err & 2u) return fail(c, VCB_ERR_UNSUPPORTED, "diagonal=true: a stale cluster_upleft label resurrects a dead slot in the reference (builder.rs:301-305,341-343); this input is fenced");
     e = build_records(c, d, meta, br.get(), cfg->hierarchical == 0, keep);
     if (e) return e;
     if (want_pool) {
@@ -108,6 +108,15 @@ int run_color(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w,
         if (e) return fail(c, e, "materialising the indices pool failed");
     }
     if (cfg->hierarchical != 0) {
+        if (want_pool) {
+            // the stage-1 pool and its per-slot offsets feed the stage-2 pools
+            br->pool1 = br->pool; br->pool = nullptr;
+            br->pool1_base = br->pool_base;
+            br->off1 = (u32 *)rt::dev_malloc_async(c->st, (size_t)br->total_slots * 4 + 4);
+            if (!br->off1) return fail(c, VCB_ERR_NOMEM, "device out of memory");
+            rt::launch(c->st, "k_save_off1", rt::SEQ, k_save_off1, dim3(grid_for(c, br->total_slots, 256, 16)), dim3(256), 0,
+                       (const vcb_cluster_rec *)br->rec, br->total_slots, br->off1);
+        }
         e = run_stage2(c, d, cfg, pol.has_key != 0, br.get());
         if (e) return fail(c, e, c->err.empty() ? "hierarchical stage failed" : c->err);
     }
@@ -141,6 +150,8 @@ int ensure_pool(BatchResult *br) {
     if (e) return e;
     std::swap(br->pool, tmp->pool);
     br->pool_base = tmp->pool_base;
+    std::swap(br->hpool, tmp->hpool);
+    br->hpool_base = tmp->hpool_base;
     return check_stream(c);
 }
 
@@ -202,7 +213,7 @@ void vcb_ctx_destroy(vcb_ctx *c) {
     rt::stream_sync(c->st);
     Bufs &b = c->b;
     rt::dev_free(b.flags); rt::dev_free(b.pc); rt::dev_free(b.la); rt::dev_free(b.ls); rt::dev_free(b.lr); rt::dev_free(b.ev);
-    rt::dev_free(b.cand); rt::dev_free(b.newlist); rt::dev_free(b.attr); rt::dev_free(b.labex); rt::dev_free(b.meta); rt::dev_free(b.ctr);
+    rt::dev_free(b.cand); rt::dev_free(b.newlist); rt::dev_free(b.attr); rt::dev_free(b.labex); rt::dev_free(b.leaflist); rt::dev_free(b.meta); rt::dev_free(b.ctr);
     rt::dev_free(c->chunksum); rt::dev_free(c->rs_table); rt::dev_free(c->sk0); rt::dev_free(c->sk1);
     rt::dev_free(c->sv0); rt::dev_free(c->sv1); rt::dev_free(c->d_small); rt::dev_free(c->d_stage);
     rt::dev_free(c->s2_fw); rt::dev_free(c->s2_mnext); rt::dev_free(c->s2_mtail); rt::dev_free(c->s2_mark); rt::dev_free(c->s2_adj_off);
@@ -309,7 +320,6 @@ int vcb_clusters_records(const vcb_clusters *hc, vcb_cluster_rec *out) {
 int vcb_clusters_indices_pool(const vcb_clusters *h, uint32_t *out) {
     if (!h) return VCB_ERR_INVALID_ARG;
     BatchResult *br = h->br.get();
-    if (br->hier) return fail(br->ctx, VCB_ERR_UNSUPPORTED, "ordered indices after the hierarchical stage are not built yet");
     int e = ensure_pool(br);
     if (e) return e;
     const u32 n = br->pool_base[h->img + 1] - br->pool_base[h->img];
@@ -335,8 +345,15 @@ int vcb_ctx_set_option(vcb_ctx *c, int option, int64_t value) {
 
 int vcb_clusters_holes_pool(const vcb_clusters *h, uint32_t *out) {
     if (!h) return VCB_ERR_INVALID_ARG;
-    (void)out;
-    return VCB_OK;   // hierarchical == 0: no holes
+    BatchResult *br = h->br.get();
+    if (!br->hier) return VCB_OK;                        // hierarchical == 0: no holes
+    int e = ensure_pool(br);
+    if (e) return e;
+    const u32 n = br->hpool_base[h->img + 1] - br->hpool_base[h->img];
+    if (n == 0) return VCB_OK;
+    if (!out) return VCB_ERR_INVALID_ARG;
+    rt::copy_d2h(br->ctx->st, out, br->hpool + br->hpool_base[h->img], (size_t)n * 4);
+    return check_stream(br->ctx);
 }
 
 int vcb_clusters_to_color_image(const vcb_clusters *h, uint8_t *rgba_out) {

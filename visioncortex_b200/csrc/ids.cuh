@@ -21,7 +21,8 @@ constexpr u32 NONE = 0xFFFFFFFFu;
 constexpr u32 TAG = 0x80000000u;   // node ids: leaf = TAG | pixel, event = pixel; also "dead" mark in the candidate list
 
 enum : u32 { J_NEW = 0, J_UP = 1, J_LEFT = 2, J_UPLEFT = 3, J_NONE = 4, J_RUP = 5, J_MASK = 7,
-             F_M = 8, F_CAND = 16, F_MSF = 32, F_KEYED = 64, F_LWIN = 128 };
+             F_M = 8, F_CAND = 16, F_MSF = 32, F_FINAL = 64, F_LWIN = 128 };
+// F_FINAL: pc[] already holds the leaf after the tile kernel (its tile-local root is a NEW pixel); J_NONE on the colour path = keyed pixel
 
 struct Dims { u32 w, h, n, nimg, N; };
 
@@ -88,7 +89,7 @@ struct ColorPolicy {
         if (vul) {
             if (!ku && !kl && same(left, up) && (diagonal || (s_cl && s_cu))) f |= F_M;
         }
-        if (kc) return f | J_NONE | F_KEYED;
+        if (kc) return f | J_NONE;
         if (s_cu && s_cul) return f | J_UP;
         if (s_cl && s_cul) return f | J_LEFT;
         if (diagonal && s_cul) return f | J_UPLEFT;
@@ -260,14 +261,15 @@ template <class P> __device__ __forceinline__ void edges_tile_body(const Dims &d
         if (gx >= d.w || gy >= d.h) continue;
         const u32 g = base + gy * d.w + gx;
         const u32 f = fl[ly * FW + lx], j = f & J_MASK;
-        b.flags[g] = (u8)f;
-        u32 root = NONE;
+        u32 root = NONE, fin = 0;
         if (j != J_NONE) {
             const int r = lp[i];
             const u32 jr = fl[(r / TW) * FW + r % TW] & J_MASK;
             const u32 gr = base + (y0 + r / TW) * d.w + x0 + r % TW;
             root = jr == J_NEW ? gr : jr == J_UP ? gr - d.w : jr == J_LEFT ? gr - 1 : jr == J_UPLEFT ? gr - d.w - 1 : gr - d.w + 1;
+            if (jr == J_NEW) fin = F_FINAL;
         }
+        b.flags[g] = (u8)(f | fin);
         b.pc[g] = root;
         if (j == J_NEW) {
             LeafA a; a.ufp = g; a.best0 = NONE; a.best1 = NONE; a.parL = NONE; a.cnt = 1; a.death = NONE; a.label = 0; a.flabel = 0;
@@ -291,6 +293,10 @@ __device__ static __forceinline__ u32 pc_root(const u32 *pc, u32 q) {
         r = t;
     }
 }
+// leaf of pixel q during K2: one load when the tile kernel already resolved it
+__device__ static __forceinline__ u32 pc_root_f(const u32 *pc, const u8 *flags, u32 q) {
+    return (flags[q] & F_FINAL) ? ldcg(pc + q) : pc_root(pc, q);
+}
 
 constexpr int K2_THREADS = 256;
 __global__ void __launch_bounds__(K2_THREADS) k_flatten_events(Dims d, Bufs b) {
@@ -303,7 +309,7 @@ __global__ void __launch_bounds__(K2_THREADS) k_flatten_events(Dims d, Bufs b) {
         u32 ea = 0, eb = 0;
         if (g < d.N) {
             const u32 f = b.flags[g];
-            if ((f & J_MASK) != J_NONE) {
+            if ((f & J_MASK) != J_NONE && !(f & F_FINAL)) {
                 const u32 r = pc_root(b.pc, g);
                 stcg(b.pc + g, r);
             }
@@ -312,8 +318,8 @@ __global__ void __launch_bounds__(K2_THREADS) k_flatten_events(Dims d, Bufs b) {
                 const u32 fl = b.flags[g - 1], fu = b.flags[g - d.w];
                 const bool dup = (fl & J_MASK) == J_UP && (fu & J_MASK) == J_UP && (fu & F_M);
                 if (!dup) {
-                    ea = pc_root(b.pc, g - 1);
-                    eb = pc_root(b.pc, g - d.w);
+                    ea = pc_root_f(b.pc, b.flags, g - 1);
+                    eb = pc_root_f(b.pc, b.flags, g - d.w);
                     is_cand = ea != eb;
                 }
             }
@@ -434,12 +440,20 @@ __global__ void __launch_bounds__(K4_THREADS) k_chain_insert(Dims d, Bufs b) {
 __device__ static __forceinline__ u32 node_par(const Bufs &b, u32 node) {
     return (node & TAG) ? ldcg(&b.la[node & ~TAG].parL) : ldcg(&b.ev[node].parE);
 }
+// the tree is final and read-only from K5 on: parents through the read-only path
+__device__ static __forceinline__ u32 node_par_ro(const Bufs &b, u32 node) {
+    return (node & TAG) ? __ldg(&b.la[node & ~TAG].parL) : __ldg(&b.ev[node].parE);
+}
 __device__ static __forceinline__ u32 climb(const Bufs &b, u32 node, u32 bound) {   // parents born <= bound
     while (true) {
         const u32 q = node_par(b, node);
         if (q > bound) return node;                      // NONE > anything
         node = q;
     }
+}
+// (node, par) pair kept in registers: no load at all while the pixel column stays on the same node
+__device__ static __forceinline__ void climb2(const Bufs &b, u32 &node, u32 &par, u32 bound) {
+    while (par <= bound) { node = par; par = __ldg(&b.ev[node].parE); }
 }
 
 struct LeafRun {
@@ -473,7 +487,7 @@ __global__ void __launch_bounds__(K5_THREADS) k_attribute(Dims d, P pol, Bufs b,
         const u32 seg = (u32)((t / wpad) % nseg), img = (u32)(t / ((u64)wpad * nseg));
         const bool valid = x < d.w;
         const u32 y0 = seg * rows_per_seg, y1 = (y0 + rows_per_seg < d.h) ? y0 + rows_per_seg : d.h;
-        u32 gprev = NONE;                                // node of the pixel above (NONE: unknown / keyed)
+        u32 gprev = NONE, gprev_par = NONE;              // node of the pixel above and its parent (NONE: unknown / keyed)
         u32 run_node = NONE, run_cnt = 0;
         LeafRun lr; lr.leaf = NONE; lr.n = 0; lr.s[0] = lr.s[1] = lr.s[2] = lr.s[3] = 0; lr.miny = 0; lr.maxy = 0;
         u32 ks[4] = {0, 0, 0, 0}, kn = 0; i32 kminy = 0x7fffffff, kmaxy = -1;
@@ -481,44 +495,48 @@ __global__ void __launch_bounds__(K5_THREADS) k_attribute(Dims d, P pol, Bufs b,
             const u32 p = img * d.n + y * d.w + (valid ? x : 0);
             const u32 f = valid ? b.flags[p] : (u32)J_NONE;
             const u32 j = f & J_MASK;
-            u32 g = NONE;
+            u32 g = NONE, gpar = NONE;
+            const u32 gl_n = __shfl_up_sync(0xffffffffu, gprev, 1), gl_p = __shfl_up_sync(0xffffffffu, gprev_par, 1);     // (x-1, y-1)
+            const u32 gr_n = __shfl_down_sync(0xffffffffu, gprev, 1), gr_p = __shfl_down_sync(0xffffffffu, gprev_par, 1); // (x+1, y-1)
             // the up-side child of an effective event at p: climb the chain of pixel p-w to just below p
-            u32 upnode = gprev;
+            u32 upnode = gprev, uppar = gprev_par;
             if (valid && (f & F_MSF)) {
-                if (upnode == NONE) upnode = b.pc[p - d.w] | TAG;
-                upnode = climb(b, upnode, p - 1);
+                if (upnode == NONE) { upnode = b.pc[p - d.w] | TAG; uppar = node_par_ro(b, upnode); }
+                climb2(b, upnode, uppar, p - 1);
                 stcg(&b.ev[p].childU, upnode);
-            }
-            const u32 gprev_left = __shfl_up_sync(0xffffffffu, gprev, 1);   // node of pixel (x-1, y-1), for UPLEFT
-            const u32 gprev_right = __shfl_down_sync(0xffffffffu, gprev, 1); // node of pixel (x+1, y-1), for RUP
-            if (valid && (f & F_MSF) && j == J_UPLEFT) {
-                // builder.rs:301-305 reads cluster_upleft BEFORE the merge step: if the up-left pixel's cluster is one of the
-                // two merging sides and loses, the reference labels this pixel with the dead slot.
-                // Record which side it is on; k_tournament rejects the input if that side loses.
-                u32 ul = (lane > 0 && gprev_left != NONE) ? gprev_left : (b.pc[p - d.w - 1] | TAG);
-                ul = climb(b, ul, p - 1);
-                u32 side = 0;
-                if (node_par(b, ul) == p) side = (ul == upnode) ? 2u : 1u;
-                stcg(&b.ev[p].arrive, side);
+                if (j == J_UPLEFT) {
+                    // builder.rs:301-305 reads cluster_upleft BEFORE the merge step: if the up-left pixel's cluster is one of
+                    // the two merging sides and loses, the reference labels this pixel with the dead slot (SURVEY Appendix E
+                    // item 5).  Record which side it is on; k_tournament rejects the input if that side loses.
+                    u32 ul = gl_n, ulp = gl_p;
+                    if (lane == 0 || ul == NONE) { ul = b.pc[p - d.w - 1] | TAG; ulp = node_par_ro(b, ul); }
+                    climb2(b, ul, ulp, p - 1);
+                    u32 side = 0;
+                    if (ulp == p) side = (ul == upnode) ? 2u : 1u;
+                    stcg(&b.ev[p].arrive, side);
+                }
             }
             bool resolved = true;
             if (valid && j != J_NONE) {
-                if (j == J_NEW) g = p | TAG;
-                else if (j == J_UP) g = climb(b, upnode != NONE ? upnode : (b.pc[p] | TAG), p);
-                else if (j == J_UPLEFT) g = climb(b, (lane > 0 && gprev_left != NONE) ? gprev_left : (b.pc[p] | TAG), p);
-                else if (j == J_RUP) g = climb(b, (lane < 31 && gprev_right != NONE) ? gprev_right : (b.pc[p] | TAG), p);
-                else if (lane == 0) g = climb(b, b.pc[p] | TAG, p);         // J_LEFT across the warp edge
-                else resolved = false;                                       // J_LEFT: wait for the lane to the left
+                if (j == J_NEW) { g = p | TAG; gpar = __ldg(&b.la[p].parL); }
+                else if (j == J_LEFT && lane > 0) resolved = false;          // wait for the lane to the left
+                else {
+                    if (j == J_UP && upnode != NONE) { g = upnode; gpar = uppar; }
+                    else if (j == J_UPLEFT && lane > 0 && gl_n != NONE) { g = gl_n; gpar = gl_p; }
+                    else if (j == J_RUP && lane < 31 && gr_n != NONE) { g = gr_n; gpar = gr_p; }
+                    else { g = b.pc[p] | TAG; gpar = node_par_ro(b, g); }   // fresh start from the leaf
+                    climb2(b, g, gpar, p);
+                }
             }
             while (true) {
-                const u32 gl = __shfl_up_sync(0xffffffffu, g, 1);
+                const u32 gl = __shfl_up_sync(0xffffffffu, g, 1), glp = __shfl_up_sync(0xffffffffu, gpar, 1);
                 const int rl = __shfl_up_sync(0xffffffffu, (int)resolved, 1);
-                if (!resolved && rl) { g = climb(b, gl, p); resolved = true; }
+                if (!resolved && rl) { g = gl; gpar = glp; climb2(b, g, gpar, p); resolved = true; }
                 if (__all_sync(0xffffffffu, resolved)) break;
             }
             if (valid) {
                 if (j == J_NONE) {
-                    if ((f & F_KEYED) && keep_key) {
+                    if (keep_key) {                                  // colour path: J_NONE = keyed pixel (builder.rs:330-334)
                         u32 s[4]; pol.stats(pol.load(p), s);
                         ks[0] += s[0]; ks[1] += s[1]; ks[2] += s[2]; ks[3] += s[3]; kn++;
                         if ((i32)y < kminy) kminy = (i32)y;
@@ -539,7 +557,7 @@ __global__ void __launch_bounds__(K5_THREADS) k_attribute(Dims d, P pol, Bufs b,
                     }
                 }
             }
-            gprev = g;
+            gprev = g; gprev_par = gpar;
         }
         if (run_cnt) atomicAdd((run_node & TAG) ? &b.la[run_node & ~TAG].cnt : &b.ev[run_node].cnt, run_cnt);
         lr.flush(b, (i32)x);

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(LST_THREADS) k_list_keys(Dims d, Bufs b, const
         const u32 f = b.flags[g];
         u64 key = ~0ull;
         if ((f & J_MASK) == J_NONE) {
-            if ((f & F_KEYED) && keep_key) key = pool_base[img];            // clusters[0].indices: raster order
+            if (keep_key) key = pool_base[img];                              // keyed pixel -> clusters[0].indices: raster order
         } else {
             const u32 node = b.attr[g];
             u32 own = (u32)(ld_pair(pair_ptr(b, node)) >> 32);

@@ -293,7 +293,7 @@ def main():
                 "roofline": roof, "cpu_baseline": cpu,
                 "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": B * NPX * 4, "d2h_bytes_per_step": int(d2h),
                         "steps": e2e_steps},
-                "gpu_launches": int(launches), "clocks": clocks, "kernel_profile_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
+                "gpu_launches": int(launches), "clocks": clocks, "graph_counters_per_step": ctx.last_counters(), "kernel_profile_ms": {k: round(v["ms"], 4) for k, v in prof.items()},
                 "wall_s_timed": wall}
         print(json.dumps(line), flush=True)
     if world > 1:

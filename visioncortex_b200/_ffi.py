@@ -96,7 +96,7 @@ EXPORTED_SYMBOLS = [
     "vcb_binary_to_clusters", "vcb_binary_to_clusters_device", "vcb_bin_clusters_info_get",
     "vcb_bin_clusters_records", "vcb_bin_clusters_points", "vcb_bin_clusters_free",
     "vcb_ctx_synchronize", "vcb_ctx_kernel_launches", "vcb_ctx_profile_reset", "vcb_ctx_profile_read",
-    "vcb_ctx_event_record", "vcb_ctx_event_elapsed_ms",
+    "vcb_ctx_event_record", "vcb_ctx_event_elapsed_ms", "vcb_ctx_last_counters",
 ]
 
 
@@ -170,6 +170,7 @@ class Library:
             f("ctx_kernel_launches").restype = C.c_uint64
             f("ctx_profile_reset").argtypes = [p, C.c_int]
             f("ctx_profile_read").argtypes = [p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+            f("ctx_last_counters").argtypes = [p, C.POINTER(C.c_uint32 * 8)]
             f("ctx_event_record").argtypes = [p, C.c_int]
             f("ctx_event_elapsed_ms").argtypes = [p, C.c_int, C.c_int, C.POINTER(C.c_double)]
 

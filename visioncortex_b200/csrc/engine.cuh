@@ -25,6 +25,7 @@ struct vcb_ctx {
     u8 *d_stage = nullptr;            // device staging of host inputs
     size_t d_stage_cap = 0;
     int opt_materialize = 0;          // VCB_OPT_MATERIALIZE_INDICES
+    u32 last_counters[8] = {};
     // stage-2 workspace
     size_t cap_s2_slots = 0, cap_s2_adj = 0;
     u32 *s2_fw = nullptr, *s2_mnext = nullptr, *s2_mtail = nullptr, *s2_mark = nullptr, *s2_adj_off = nullptr,
@@ -91,7 +92,7 @@ inline int ensure_workspace(vcb_ctx *c, size_t N, size_t nimg) {
         const size_t cap = N + 64;
         bool ok = true;
         ok &= grow(c->b.flags, cap); ok &= grow(c->b.pc, cap); ok &= grow(c->b.la, cap); ok &= grow(c->b.ls, cap);
-        ok &= grow(c->b.lr, cap); ok &= grow(c->b.ev, cap); ok &= grow(c->b.cand, cap); ok &= grow(c->b.newlist, cap);
+        ok &= grow(c->b.lr, cap); ok &= grow(c->b.ev, cap); ok &= grow(c->b.cand, cap); ok &= grow(c->b.ea, cap); ok &= grow(c->b.eb, cap); ok &= grow(c->b.newlist, cap);
         ok &= grow(c->b.attr, cap); ok &= grow(c->b.labex, cap); ok &= grow(c->b.leaflist, cap);
         const size_t chunks = cap / 2048 + 4;
         ok &= grow(c->chunksum, 256 * chunks / 2048 + chunks + 1024);
@@ -178,7 +179,12 @@ inline int run_stage1(vcb_ctx *c, const Dims &d, const P &pol, u32 base, bool wa
     const u32 tiles = ((d.w + TW - 1) / TW) * ((d.h + TH - 1) / TH) * d.nimg;
     if (!launch_edges_tma(c, d, pol, b, tiles))
         rt::launch(st, "k_edges_tile", rt::THR, k_edges_tile<P>, dim3(tiles), dim3(K1_THREADS), K1_SMEM, d, pol, b);
-    rt::launch(st, "k_flatten_events", rt::THR, k_flatten_events, dim3(grid_for(c, d.N, K2_THREADS, 16)), dim3(K2_THREADS), 0, d, b);
+    if (d.w % 4 == 0)
+        rt::launch(st, "k_flatten_events", rt::THR, k_flatten_events4, dim3(grid_for(c, d.N / 4, K2_THREADS, 16)), dim3(K2_THREADS), 0, d, b);
+    else
+        rt::launch(st, "k_flatten_events", rt::THR, k_flatten_events, dim3(grid_for(c, d.N, K2_THREADS, 16)), dim3(K2_THREADS), 0, d, b);
+    prims::scan(st, "scan_new", NewScan{d, b}, c->chunksum, d.N, c->sms * 8);
+    prims::scan(st, "scan_new", LeafScan{d, b}, c->chunksum, d.N, c->sms * 8);
     {
         static int coop_blocks = 0;
         if (!coop_blocks) coop_blocks = rt::max_coop_blocks((const void *)k_boruvka, K3_THREADS, 0, c->device);
@@ -187,9 +193,7 @@ inline int run_stage1(vcb_ctx *c, const Dims &d, const P &pol, u32 base, bool wa
         if (g > want) g = want < 1 ? 1 : want;
         rt::launch(st, "k_boruvka", rt::COOP, k_boruvka, dim3(g), dim3(K3_THREADS), 0, b);
     }
-    rt::launch(st, "k_chain_insert", rt::SEQ, k_chain_insert, dim3(grid_for(c, d.N / 2, K4_THREADS, 16)), dim3(K4_THREADS), 0, d, b);
-    prims::scan(st, "scan_new", NewScan{d, b}, c->chunksum, d.N, c->sms * 8);
-    prims::scan(st, "scan_new", LeafScan{d, b}, c->chunksum, d.N, c->sms * 8);
+    rt::launch(st, "k_chain_insert", rt::THR, k_chain_insert, dim3(grid_for(c, d.N / 2, K4_THREADS, 16)), dim3(K4_THREADS), 0, d, b);
     {
         // rows per segment: enough threads to fill the machine, as few restarts as possible
         const u64 wpad = (d.w + 31) & ~31u;
@@ -206,7 +210,7 @@ inline int run_stage1(vcb_ctx *c, const Dims &d, const P &pol, u32 base, bool wa
         else
             rt::launch(st, "k_attribute", rt::THR, k_attribute<P, false>, dim3(g), dim3(K5_THREADS), 0, d, pol, b, rows, keep_key);
     }
-    rt::launch(st, "k_tournament", rt::SEQ, k_tournament, dim3(grid_for(c, d.N / 4, K6_THREADS, 16)), dim3(K6_THREADS), 0, d, b);
+    rt::launch(st, "k_tournament", rt::THR, k_tournament, dim3(grid_for(c, d.N / 4, K6_THREADS, 16)), dim3(K6_THREADS), 0, d, b);
     prims::scan(st, "scan_label", LabelScan{d, b}, c->chunksum, d.N, c->sms * 8);
     rt::launch(st, "k_image_meta", rt::SEQ, k_image_meta, dim3(g_img), dim3(128), 0, d, b, base);
     rt::launch(st, "k_leaf_labels", rt::SEQ, k_leaf_labels, dim3(grid_for(c, d.N / 4, K8_THREADS, 16)), dim3(K8_THREADS), 0, d, b, base);
@@ -226,6 +230,8 @@ inline int run_stage1(vcb_ctx *c, const Dims &d, const P &pol, u32 base, bool wa
     }
     meta_out.assign(hm, hm + d.nimg);
     ctr_out = *hc;
+    c->last_counters[0] = hc->ncand; c->last_counters[1] = hc->kt; c->last_counters[2] = hc->lt; c->last_counters[3] = hc->rounds;
+    c->last_counters[4] = hc->err;
     return VCB_OK;
 }
 

@@ -21,7 +21,8 @@ constexpr u32 NONE = 0xFFFFFFFFu;
 constexpr u32 TAG = 0x80000000u;   // node ids: leaf = TAG | pixel, event = pixel; also "dead" mark in the candidate list
 
 enum : u32 { J_NEW = 0, J_UP = 1, J_LEFT = 2, J_UPLEFT = 3, J_NONE = 4, J_RUP = 5, J_MASK = 7,
-             F_M = 8, F_CAND = 16, F_MSF = 32, F_FINAL = 64, F_LWIN = 128 };
+             F_M = 8, F_CAND = 16, F_MSF = 32, F_FINAL = 64 };
+constexpr u32 EV_LWIN = 0x100u;   // EvRec.arrive: bits 0-1 = side of the up-left cluster (stale check), bit 8 = left child won
 // F_FINAL: pc[] already holds the leaf after the tile kernel (its tile-local root is a NEW pixel); J_NONE on the colour path = keyed pixel
 
 struct Dims { u32 w, h, n, nimg, N; };
@@ -50,12 +51,13 @@ struct Counters {
     u32 kt;                // total leaves (all images)
     u32 rounds;            // boruvka rounds executed
     u32 lt;                // total real leaves (NEW events that were not contracted)
-    u32 pad[1];
+    u32 twork;             // k_tournament work counter
+    u32 cwork;             // k_chain_insert work counter
 };
 
 struct Bufs {
     u8 *flags; u32 *pc; LeafA *la; LeafS *ls; LeafR *lr; EvRec *ev;
-    u32 *cand; u32 *newlist; u32 *leaflist; u32 *attr; u32 *labex; ImgMeta *meta; Counters *ctr;
+    u32 *cand; u32 *ea; u32 *eb; u32 *newlist; u32 *leaflist; u32 *attr; u32 *labex; ImgMeta *meta; Counters *ctr;
 };
 
 // --------------------------------------------------------------------------------------------------------------
@@ -330,8 +332,64 @@ __global__ void __launch_bounds__(K2_THREADS) k_flatten_events(Dims d, Bufs b) {
             if (lane == __ffs((int)m) - 1) pos = atomicAdd(&b.ctr->ncand, (u32)__popc(m));
             pos = __shfl_sync(0xffffffffu, pos, __ffs((int)m) - 1);
             if (is_cand) {
-                b.cand[pos + __popc(m & ((1u << lane) - 1u))] = g;
-                EvRec e; e.parE = NONE; e.cnt = 0; e.childU = NONE; e.arrive = 0; e.a_wl = ea; e.b_wu = eb; e.carL = NONE; e.carU = NONE;
+                const u32 slot = pos + __popc(m & ((1u << lane) - 1u));
+                b.cand[slot] = g; b.ea[slot] = ea; b.eb[slot] = eb;     // dense endpoint arrays for the spanning-forest rounds
+                EvRec e; e.parE = NONE; e.cnt = 0; e.childU = NONE; e.arrive = 0; e.a_wl = 0; e.b_wu = 0; e.carL = NONE; e.carU = NONE;
+                b.ev[g] = e;
+                b.flags[g] = (u8)(b.flags[g] | F_CAND);
+            }
+        }
+    }
+}
+
+// K2 for widths that are a multiple of 4: one thread per 4 consecutive pixels of a row, flags read as one 32-bit word
+// (own row and the row above), candidates compacted with one atomic per warp.
+__global__ void __launch_bounds__(K2_THREADS) k_flatten_events4(Dims d, Bufs b) {
+    const u32 groups = d.N / 4;
+    const u32 stride = gridDim.x * K2_THREADS;
+    const int lane = threadIdx.x & 31;
+    const u32 nloop = (groups + stride - 1) / stride;
+    for (u32 it = 0; it < nloop; ++it) {
+        const u32 grp = it * stride + blockIdx.x * K2_THREADS + threadIdx.x;
+        u32 ncand = 0, cg[4], ca[4], cb[4];
+        if (grp < groups) {
+            const u32 g4 = grp * 4;
+            const u32 f4 = *reinterpret_cast<const u32 *>(b.flags + g4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const u32 f = (f4 >> (8 * k)) & 255u;
+                if ((f & J_MASK) != J_NONE && !(f & F_FINAL)) stcg(b.pc + g4 + k, pc_root(b.pc, g4 + k));
+            }
+            if (f4 & 0x08080808u) {                       // some pixel carries a merge flag (implies a row above)
+                const u32 fu4 = *reinterpret_cast<const u32 *>(b.flags + g4 - d.w);
+                u32 fleft = 0;
+                if (f4 & F_M) fleft = b.flags[g4 - 1];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const u32 f = (f4 >> (8 * k)) & 255u;
+                    if (!(f & F_M)) continue;
+                    const u32 fl = k ? (f4 >> (8 * (k - 1))) & 255u : fleft;
+                    const u32 fu = (fu4 >> (8 * k)) & 255u;
+                    if ((fl & J_MASK) == J_UP && (fu & J_MASK) == J_UP && (fu & F_M)) continue;   // duplicate of the event one row up
+                    const u32 g = g4 + k;
+                    const u32 ea = pc_root_f(b.pc, b.flags, g - 1), eb = pc_root_f(b.pc, b.flags, g - d.w);
+                    if (ea != eb) { cg[ncand] = g; ca[ncand] = ea; cb[ncand] = eb; ++ncand; }
+                }
+            }
+        }
+        // warp-aggregated append
+        u32 inc = ncand;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, inc, dlt); if (lane >= dlt) inc += t; }
+        const u32 total = __shfl_sync(0xffffffffu, inc, 31);
+        if (total) {
+            u32 pos = 0;
+            if (lane == 31) pos = atomicAdd(&b.ctr->ncand, total);
+            pos = __shfl_sync(0xffffffffu, pos, 31) + inc - ncand;
+            for (u32 k = 0; k < ncand; ++k) {
+                const u32 g = cg[k];
+                b.cand[pos + k] = g; b.ea[pos + k] = ca[k]; b.eb[pos + k] = cb[k];
+                EvRec e; e.parE = NONE; e.cnt = 0; e.childU = NONE; e.arrive = 0; e.a_wl = 0; e.b_wu = 0; e.carL = NONE; e.carU = NONE;
                 b.ev[g] = e;
                 b.flags[g] = (u8)(b.flags[g] | F_CAND);
             }
@@ -366,10 +424,9 @@ __global__ void __launch_bounds__(K3_THREADS) k_boruvka(Bufs b) {
         for (u32 e = tid; e < ncand; e += stride) {
             const u32 p = ldcg(b.cand + e);
             if (p & TAG) continue;
-            EvRec *ev = b.ev + p;
-            const u32 ra = uf_find(b.la, ev->a_wl), rb = uf_find(b.la, ev->b_wu);
+            const u32 ra = uf_find(b.la, b.ea[e]), rb = uf_find(b.la, b.eb[e]);
             if (ra == rb) { b.cand[e] = p | TAG; continue; }
-            ev->a_wl = ra; ev->b_wu = rb;
+            b.ea[e] = ra; b.eb[e] = rb;
             u32 *ba = par ? &b.la[ra].best1 : &b.la[ra].best0, *bb = par ? &b.la[rb].best1 : &b.la[rb].best0;
             atomicMin(ba, p); atomicMin(bb, p);
             stcg(par ? &b.la[ra].best0 : &b.la[ra].best1, NONE);
@@ -383,8 +440,7 @@ __global__ void __launch_bounds__(K3_THREADS) k_boruvka(Bufs b) {
         for (u32 e = tid; e < ncand; e += stride) {
             const u32 p = ldcg(b.cand + e);
             if (p & TAG) continue;
-            EvRec *ev = b.ev + p;
-            const u32 ra = ev->a_wl, rb = ev->b_wu;
+            const u32 ra = b.ea[e], rb = b.eb[e];
             const bool sa = ldcg(par ? &b.la[ra].best1 : &b.la[ra].best0) == p;
             const bool sb = ldcg(par ? &b.la[rb].best1 : &b.la[rb].best0) == p;
             if (sa || sb) {
@@ -400,6 +456,13 @@ __global__ void __launch_bounds__(K3_THREADS) k_boruvka(Bufs b) {
         ++round;
     }
     if (tid == 0) b.ctr->rounds = round;
+    // epilogue: every leaf points directly at the root of its final cluster (later finds are one load)
+    const u32 lt = ldcg(&b.ctr->lt);
+    for (u32 k = tid; k < lt; k += stride) {
+        const u32 leaf = b.leaflist[k];
+        const u32 r = uf_find(b.la, leaf);
+        if (r != leaf) stcg(&b.la[leaf].ufp, r);
+    }
 }
 
 // --------------------------------------------------------------------------------------------------------------
@@ -421,15 +484,65 @@ __device__ static __forceinline__ void chain_insert(Bufs b, u32 leaf, u32 g) {
     }
 }
 
+// Warp-level dynamic work claiming: the warp takes WORK_CHUNK consecutive items from a global counter with one atomic and
+// hands them to its lanes as they become free.  Returns the item index for this lane or NONE.
+constexpr u32 WORK_CHUNK = 2048;
+struct WarpWork {
+    u32 pos = 0, end = 0;      // warp-uniform
+    bool exhausted = false;
+    __device__ __forceinline__ u32 claim(u32 *counter, u32 total, bool want, int lane) {
+        const u32 need = __ballot_sync(0xffffffffu, want);
+        if (!need) return NONE;
+        if (pos >= end && !exhausted) {
+            u32 base = 0;
+            if (lane == 0) base = atomicAdd(counter, WORK_CHUNK);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= total) exhausted = true;
+            else { pos = base; end = base + WORK_CHUNK < total ? base + WORK_CHUNK : total; }
+        }
+        u32 idx = NONE;
+        if (pos < end) {
+            const u32 mine = pos + __popc(need & ((1u << lane) - 1u));
+            if (want && mine < end) idx = mine;
+            pos += __popc(need);
+        }
+        return idx;
+    }
+};
+
 constexpr int K4_THREADS = 256;
+// One insertion step per lane per iteration; a lane whose insertion is complete claims the next (event, side) item from
+// a global counter, so the few long walks do not idle the rest of the warp.
 __global__ void __launch_bounds__(K4_THREADS) k_chain_insert(Dims d, Bufs b) {
-    const u32 ncand = ldcg(&b.ctr->ncand);
-    const u32 stride = gridDim.x * K4_THREADS;
-    for (u32 t = blockIdx.x * K4_THREADS + threadIdx.x; t < 2 * ncand; t += stride) {
-        const u32 p = b.cand[t >> 1] & ~TAG;
-        if (!(b.flags[p] & F_MSF)) continue;
-        const u32 leaf = (t & 1u) ? b.pc[p - d.w] : b.pc[p - 1];
-        chain_insert(b, leaf, p);
+    const u32 nitems = 2 * ldcg(&b.ctr->ncand);
+    const int lane = threadIdx.x & 31;
+    bool have = false;
+    u32 *slot = nullptr;
+    u32 g = 0;
+    WarpWork ww;
+    while (true) {
+        const u32 t = ww.claim(&b.ctr->cwork, nitems, !have, lane);
+        if (t != NONE) {
+            const u32 p = b.cand[t >> 1] & ~TAG;
+            if (b.flags[p] & F_MSF) {
+                const u32 leaf = (t & 1u) ? b.pc[p - d.w] : b.pc[p - 1];
+                slot = &b.la[leaf].parL; g = p; have = true;
+            }
+        }
+        if (__all_sync(0xffffffffu, !have)) {
+            // nobody holds a live item: either the list is exhausted or this batch held only non-effective candidates
+            if (ww.exhausted && ww.pos >= ww.end) break;
+            continue;
+        }
+        const bool drained = ww.exhausted && ww.pos >= ww.end;   // nothing left to claim: finish the own walk in a tight loop
+        while (have) {
+            const u32 old = atomicMin(slot, g);           // one round trip per step
+            if (old == g || old == NONE) { have = false; break; }
+            if (old > g) { slot = &b.ev[g].parE; g = old; }   // installed g below `old`: now insert the displaced ancestor above g
+            else slot = &b.ev[old].parE;                  // a lighter ancestor is already there: g is also its ancestor
+            if (!drained) break;
+        }
+        if (drained) break;
     }
 }
 
@@ -605,44 +718,66 @@ struct LeafScan {
 constexpr int K6_THREADS = 256;
 __global__ void __launch_bounds__(K6_THREADS) k_tournament(Dims d, Bufs b) {
     const u32 lt = ldcg(&b.ctr->lt);
-    const u32 stride = gridDim.x * K6_THREADS;
-    for (u32 k = blockIdx.x * K6_THREADS + threadIdx.x; k < lt; k += stride) {
-        const u32 leaf = b.leaflist[k];
-        u32 child = leaf | TAG, W = ldcg(&b.la[leaf].cnt), car = leaf;
-        u32 v = ldcg(&b.la[leaf].parL);
-        while (v != NONE) {
+    const int lane = threadIdx.x & 31;
+    // Every lane walks its own leaf-to-root path one level per iteration; a lane whose walk ends (first to arrive at an
+    // event, or root reached) immediately claims the next leaf from a global counter, so the warp stays full even though
+    // most walks are one level long and a few are thousands.
+    bool have = false;
+    u32 child = 0, W = 0, car = 0, v = NONE;
+    WarpWork ww;
+    while (true) {
+        const u32 k = ww.claim(&b.ctr->twork, lt, !have, lane);
+        if (k != NONE) {
+            const u32 leaf = b.leaflist[k];
+            const uint4 la4 = __ldcg(reinterpret_cast<const uint4 *>(&b.la[leaf].cnt));   // cnt, death, label, flabel
+            child = leaf | TAG; W = la4.x; car = leaf;
+            v = ldcg(&b.la[leaf].parL);
+            have = true;
+        }
+        if (!__any_sync(0xffffffffu, have)) {
+            if (ww.exhausted && ww.pos >= ww.end) break;
+            continue;
+        }
+        const bool drained = ww.exhausted && ww.pos >= ww.end;   // nothing left to claim: finish the own walk in a tight loop
+        while (have) {
+            if (v == NONE) {                              // reached the root of a final cluster
+                const u32 root = ldcg(&b.la[car].ufp);    // any leaf of the cluster: ufp is flat after k_boruvka
+                stcg(&b.la[root].best0, car);             // carrier of the component (best0 is free after K3)
+                stcg(&b.la[root].best1, W);               // final area
+                have = false;
+                break;
+            }
             EvRec *e = b.ev + v;
-            // one round trip per level: the head of the record (parE, cnt, childU) is loaded while the exchange that
-            // parks / collects the sibling's (area, carrier) is in flight.  (carL, carU) is the 64-bit mailbox, NONE/NONE = empty.
+            // one round trip per level: the head of the record (parE, cnt, childU, stale side) is loaded while the exchange
+            // that parks / collects the sibling's (area, carrier) is in flight.  (carL, carU) = 64-bit mailbox, NONE/NONE = empty.
             const uint4 head = __ldcg(reinterpret_cast<const uint4 *>(e));
             const unsigned long long mine = ((unsigned long long)car << 32) | W;
             const unsigned long long other = atomicExch(reinterpret_cast<unsigned long long *>(&e->carL), mine);
-            if (other == ~0ull) break;                    // first to arrive: the sibling will pick this up
+            if (other == ~0ull) { have = false; break; }  // first to arrive: the sibling will pick this up
             const bool up = head.z == child;              // childU
-            const u32 stale = head.w;                     // side of the up-left pixel's cluster (UPLEFT join at an event), 0 = none
+            const u32 stale = head.w & 3u;                // side of the up-left pixel's cluster (UPLEFT join at an event), 0 = none
             const u32 Wo = (u32)other, co = (u32)(other >> 32);
             const u32 WL = up ? Wo : W, WU = up ? W : Wo;
             const u32 cL = up ? co : car, cU = up ? car : co;
-            if (WL <= WU) {                               // left loses: its label dies as the left side
+            u32 lwin = 0;
+            if (WL <= WU) {                               // left loses: its label dies as the left side (builder.rs:313-318)
                 stcg(&b.la[cL].death, v | TAG);
                 car = cU;
                 if (stale == 1) atomicOr(&b.ctr->err, 2u);
             } else {
                 stcg(&b.la[cU].death, v);
                 car = cL;
-                b.flags[v] = (u8)(b.flags[v] | F_LWIN);
+                lwin = EV_LWIN;
                 if (stale == 2) atomicOr(&b.ctr->err, 2u);
             }
+            stcg(&e->arrive, stale | lwin);
             stcg(&e->a_wl, WL); stcg(&e->b_wu, WU);       // both child areas, for the listing pass
             W = WL + WU + head.y;                         // + cnt(v)
             child = v;
             v = head.x;                                   // parE
+            if (!drained) break;
         }
-        if (v == NONE) {                                  // reached the root of a final cluster
-            const u32 root = uf_find(b.la, leaf);
-            stcg(&b.la[root].best0, car);                 // carrier of the component (best0 is free after K3)
-            stcg(&b.la[root].best1, W);                   // final area
-        }
+        if (drained) break;
     }
 }
 

@@ -36,7 +36,7 @@ __device__ static __forceinline__ void list_init_node(const Bufs &b, u32 node) {
     if (v != NONE) {
         const EvRec *e = b.ev + v;
         const bool up = e->childU == node;
-        const bool lwin = (b.flags[v] & F_LWIN) != 0;
+        const bool lwin = (e->arrive & EV_LWIN) != 0;
         const bool winner = up ? !lwin : lwin;
         if (!winner) delta = up ? e->a_wl : e->b_wu;      // area of the winning sibling
     }

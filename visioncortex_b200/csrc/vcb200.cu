@@ -213,7 +213,7 @@ void vcb_ctx_destroy(vcb_ctx *c) {
     rt::stream_sync(c->st);
     Bufs &b = c->b;
     rt::dev_free(b.flags); rt::dev_free(b.pc); rt::dev_free(b.la); rt::dev_free(b.ls); rt::dev_free(b.lr); rt::dev_free(b.ev);
-    rt::dev_free(b.cand); rt::dev_free(b.newlist); rt::dev_free(b.attr); rt::dev_free(b.labex); rt::dev_free(b.leaflist); rt::dev_free(b.meta); rt::dev_free(b.ctr);
+    rt::dev_free(b.cand); rt::dev_free(b.ea); rt::dev_free(b.eb); rt::dev_free(b.newlist); rt::dev_free(b.attr); rt::dev_free(b.labex); rt::dev_free(b.leaflist); rt::dev_free(b.meta); rt::dev_free(b.ctr);
     rt::dev_free(c->chunksum); rt::dev_free(c->rs_table); rt::dev_free(c->sk0); rt::dev_free(c->sk1);
     rt::dev_free(c->sv0); rt::dev_free(c->sv1); rt::dev_free(c->d_small); rt::dev_free(c->d_stage);
     rt::dev_free(c->s2_fw); rt::dev_free(c->s2_mnext); rt::dev_free(c->s2_mtail); rt::dev_free(c->s2_mark); rt::dev_free(c->s2_adj_off);
@@ -508,6 +508,12 @@ int vcb_ctx_profile_read(vcb_ctx *c, const char *kernel_name, double *total_ms, 
     (void)kernel_name;
 #endif
     *total_ms = t; *launches = n;
+    return VCB_OK;
+}
+
+int vcb_ctx_last_counters(const vcb_ctx *c, uint32_t out[8]) {
+    if (!c || !out) return VCB_ERR_INVALID_ARG;
+    for (int k = 0; k < 8; ++k) out[k] = c->last_counters[k];
     return VCB_OK;
 }
 

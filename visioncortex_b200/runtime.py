@@ -135,3 +135,8 @@ class Context:
         ms = C.c_double()
         self.lib.check(self.lib.fn("ctx_event_elapsed_ms")(self.handle, a, b, C.byref(ms)), self.handle)
         return ms.value
+
+    def last_counters(self) -> dict:
+        arr = (C.c_uint32 * 8)()
+        self.lib.check(self.lib.fn("ctx_last_counters")(self.handle, C.byref(arr)), self.handle)
+        return {"candidate_events": arr[0], "new_events": arr[1], "leaves": arr[2], "msf_rounds": arr[3], "err": arr[4]}

@@ -273,3 +273,13 @@ def test_diagonal_colour(gpu, oracle):
         assert_same_clusters(got, ref, pools=False, ctx="diag 720p")
     except Fenced:
         pass
+
+
+def test_c5_giant_image_single_gpu(gpu, oracle):
+    """BASELINE config 5 geometry on one GPU: G3(cell=256) posterised, RunnerConfig::default().  8192x8192 keeps the CPU oracle
+    to a few seconds; the full 16384x16384 image (u32 colour sums wrap there) is run by tools/bench_configs.py --only C5."""
+    img = synth.g3_posterised(8192, 8192, seed=5, cell=256)
+    cfg = make_config()
+    ref = oracle.runner_run(img, cfg, pools=False)
+    got = gpu.runner_run(img, cfg, pools=False)
+    assert_same_clusters(got, ref, pools=False, ctx="C5 8192^2")

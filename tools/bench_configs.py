@@ -106,6 +106,11 @@ def main():
         run_colour("C3 pass 2 (hierarchical 64, Discard) 4K", [res["color_image"]], cfg2)
         run_colour("C3 stage 1 only (hierarchical 0) 4K", [img], make_config(hierarchical=0, is_same_color_a=2, good_max_area=3840 * 2160,
                                                                             key_color=key))
+    if only and "C5" in only:
+        # BASELINE config 5 on ONE GPU (the 8-GPU row-band mode is not built in round 1): 16384x16384 posterised, default config
+        img = synth.g3_posterised(16384, 16384, seed=5, cell=256)
+        run_colour("C5 single 16384x16384 image, Runner default (hierarchical MAX), one GPU", [img], make_config(),
+                   note="single GPU; release-profile wrapping u32 colour sums apply (cluster > 16.8 Mpx)")
     if not only or "C1" in only:
         from visioncortex_b200._ffi import pack_bits
 

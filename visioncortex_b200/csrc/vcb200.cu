@@ -124,18 +124,32 @@ int run_color(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w,
     return VCB_OK;
 }
 
+// Device batches are processed in chunks of at most MAX_CHUNK_PX pixels: the workspace is ~140 bytes per pixel and the
+// per-image stage-2 CTAs want >= 148 images in flight, so one chunk is sized to fill the SMs without exhausting HBM.
+constexpr u64 MAX_CHUNK_PX = 320ull << 20;
+
 int run_color_device(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w, u32 h, size_t nimg,
                      vcb_clusters **out) {
     if (!out) return fail(c, VCB_ERR_INVALID_ARG, "null output");
     if (nimg == 0) return VCB_OK;
-    std::shared_ptr<BatchResult> br;
-    int e = run_color(c, cfg, d_rgba, w, h, nimg, c->opt_materialize != 0, true, br);
-    if (e) return e;
-    for (size_t i = 0; i < nimg; ++i) {
-        vcb_clusters *hd = new (std::nothrow) vcb_clusters();
-        if (!hd) return fail(c, VCB_ERR_NOMEM, "host out of memory");
-        hd->br = br; hd->img = (u32)i;
-        out[i] = hd;
+    const u64 n64 = (u64)w * h;
+    if (n64 == 0) return fail(c, VCB_ERR_INVALID_ARG, "empty image");
+    size_t per_chunk = (size_t)(MAX_CHUNK_PX / n64);
+    if (per_chunk < 1) per_chunk = 1;
+    for (size_t i0 = 0; i0 < nimg; i0 += per_chunk) {
+        const size_t cnt = nimg - i0 < per_chunk ? nimg - i0 : per_chunk;
+        std::shared_ptr<BatchResult> br;
+        int e = run_color(c, cfg, d_rgba + i0 * n64 * 4, w, h, cnt, c->opt_materialize != 0, true, br);
+        if (e) {
+            for (size_t k = 0; k < i0; ++k) { delete out[k]; out[k] = nullptr; }
+            return e;
+        }
+        for (size_t i = 0; i < cnt; ++i) {
+            vcb_clusters *hd = new (std::nothrow) vcb_clusters();
+            if (!hd) return fail(c, VCB_ERR_NOMEM, "host out of memory");
+            hd->br = br; hd->img = (u32)i;
+            out[i0 + i] = hd;
+        }
     }
     return VCB_OK;
 }
@@ -259,7 +273,7 @@ int vcb_runner_run_batch(vcb_ctx *c, const vcb_runner_config *cfg, const uint8_t
     while (i < n) {
         size_t j = i + 1;
         const size_t bytes = (size_t)width[i] * height[i] * 4;
-        while (j < n && width[j] == width[i] && height[j] == height[i] && (j - i + 1) * (bytes / 4) < 0x30000000ull) ++j;
+        while (j < n && width[j] == width[i] && height[j] == height[i] && (j - i + 1) * (bytes / 4) <= MAX_CHUNK_PX) ++j;
         if (bytes == 0) return fail(c, VCB_ERR_INVALID_ARG, "empty image");
         u8 *d = stage_input(c, bytes * (j - i));
         if (!d) return fail(c, VCB_ERR_NOMEM, "device out of memory (input)");

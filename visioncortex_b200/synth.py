@@ -37,28 +37,41 @@ def g1_binary(width: int, height: int, p: float, seed: int) -> np.ndarray:
 
 
 def _voronoi_ids(width: int, height: int, seed: int, cell: int):
+    """Nearest jittered-grid site among the 3x3 neighbouring cells (squared distance, ties -> smaller id).
+    Evaluated in row bands with 32-bit arithmetic (distances < 2^31 for cell <= 10000) to stay cache resident."""
     gx = (width + cell - 1) // cell
     gy = (height + cell - 1) // cell
     ids = np.arange(gx * gy, dtype=np.uint64)
     cx = (ids % np.uint64(gx)).astype(np.int64)
     cy = (ids // np.uint64(gx)).astype(np.int64)
-    sx = cx * cell + (_h(seed, 2, ids) % np.uint64(cell)).astype(np.int64)
-    sy = cy * cell + (_h(seed, 3, ids) % np.uint64(cell)).astype(np.int64)
-    ys, xs = np.mgrid[0:height, 0:width].astype(np.int64)
-    pcx, pcy = xs // cell, ys // cell
-    best_d = np.full((height, width), np.iinfo(np.int64).max, dtype=np.int64)
-    best_id = np.zeros((height, width), dtype=np.int64)
-    for dy in (-1, 0, 1):
-        for dx in (-1, 0, 1):
-            qx, qy = pcx + dx, pcy + dy
-            ok = (qx >= 0) & (qx < gx) & (qy >= 0) & (qy < gy)
-            qid = np.where(ok, qy * gx + qx, 0)
-            d = (xs - sx[qid]) ** 2 + (ys - sy[qid]) ** 2
-            d = np.where(ok, d, np.iinfo(np.int64).max)
-            better = (d < best_d) | ((d == best_d) & (qid < best_id))
-            best_d = np.where(better, d, best_d)
-            best_id = np.where(better, qid, best_id)
-    return best_id, gx * gy
+    sx = (cx * cell + (_h(seed, 2, ids) % np.uint64(cell)).astype(np.int64)).astype(np.int32)
+    sy = (cy * cell + (_h(seed, 3, ids) % np.uint64(cell)).astype(np.int64)).astype(np.int32)
+    out = np.empty((height, width), dtype=np.int32)
+    xs = np.arange(width, dtype=np.int32)[None, :]
+    pcx = xs // cell
+    band = max(1, min(height, (1 << 21) // max(1, width)))
+    big = np.int32(np.iinfo(np.int32).max)
+    for y0 in range(0, height, band):
+        y1 = min(height, y0 + band)
+        ys = np.arange(y0, y1, dtype=np.int32)[:, None]
+        pcy = ys // cell
+        best_d = np.full((y1 - y0, width), big, dtype=np.int32)
+        best_id = np.zeros((y1 - y0, width), dtype=np.int32)
+        for dy in (-1, 0, 1):
+            qy = pcy + dy
+            oky = (qy >= 0) & (qy < gy)
+            for dx in (-1, 0, 1):
+                qx = pcx + dx
+                ok = oky & ((qx >= 0) & (qx < gx))
+                qid = np.where(ok, qy * gx + qx, 0).astype(np.int32)
+                ddx = xs - sx[qid]
+                ddy = ys - sy[qid]
+                dist = np.where(ok, ddx * ddx + ddy * ddy, big)
+                better = (dist < best_d) | ((dist == best_d) & (qid < best_id))
+                best_d = np.where(better, dist, best_d)
+                best_id = np.where(better, qid, best_id)
+        out[y0:y1] = best_id
+    return out, gx * gy
 
 
 def g2_scene(width: int, height: int, seed: int, cell: int = 48, amp: int = 3) -> np.ndarray:

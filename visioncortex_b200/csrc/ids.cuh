@@ -741,7 +741,7 @@ __global__ void __launch_bounds__(K6_THREADS) k_tournament(Dims d, Bufs b) {
         const bool drained = ww.exhausted && ww.pos >= ww.end;   // nothing left to claim: finish the own walk in a tight loop
         while (have) {
             if (v == NONE) {                              // reached the root of a final cluster
-                const u32 root = ldcg(&b.la[car].ufp);    // any leaf of the cluster: ufp is flat after k_boruvka
+                const u32 root = uf_find(b.la, car);      // any leaf of the cluster; ufp is (nearly) flat after k_boruvka's epilogue
                 stcg(&b.la[root].best0, car);             // carrier of the component (best0 is free after K3)
                 stcg(&b.la[root].best1, W);               // final area
                 have = false;

@@ -4,6 +4,7 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <tuple>
@@ -155,6 +156,14 @@ inline void launch(Stream &st, const char *name, LaunchMode mode, void (*k)(KArg
         if (e != cudaSuccess && !st.last_error) { st.last_error = (int)e; st.last_error_text = std::string(name) + ": " + cudaGetErrorString(e); }
     }
     if (st.profiling) { cudaEventRecord(pe.e1, st.s); st.prof.push_back(pe); }
+    static const bool sync_each = std::getenv("VCB_SYNC_EACH") != nullptr;   // debugging aid: name the faulting kernel
+    if (sync_each) {
+        cudaError_t e = cudaStreamSynchronize(st.s);
+        if (e != cudaSuccess && !st.last_error) {
+            st.last_error = (int)e; st.last_error_text = std::string(name) + ": " + cudaGetErrorString(e);
+            std::fprintf(stderr, "[vcb] kernel %s failed: %s\n", name, cudaGetErrorString(e));
+        }
+    }
 }
 #endif
 

@@ -166,6 +166,7 @@ def main():
     from visioncortex_b200.runtime import Context
 
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     ctx = Context(local)      # raises without the CUDA library / a GPU: there is no CPU fallback

@@ -372,7 +372,14 @@ inline int run_stage2(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg, b
         rt::fill(st, d_count, 0, sizeof(u32));
         rt::launch(st, "k_s2_collect", rt::THR, k_s2_collect, dim3(gs), dim3(256), 0, a, ep);
         const bool flipped = prims::radix_sort(st, c->sk0, c->sv0, c->sk1, c->sv1, d_count, total, nbits, c->rs_table, c->chunksum, c->sms * 8);
-        rt::launch(st, "k_s2_epoch", rt::THR, k_s2_epoch, dim3(d.nimg), dim3(S2_THREADS), sizeof(S2Shared) + 16, a,
+        // few images: one fat CTA each (perimeter / neighbour scans are block-parallel); many images: more CTAs per SM
+        const int s2_threads =
+#ifdef VCB_HOSTSIM
+            64;
+#else
+            d.nimg * 8 <= (u32)c->sms ? 1024 : d.nimg * 2 <= (u32)c->sms ? 512 : d.nimg <= (u32)c->sms ? 256 : 128;
+#endif
+        rt::launch(st, "k_s2_epoch", rt::THR, k_s2_epoch, dim3(d.nimg), dim3(s2_threads), sizeof(S2Shared) + 16, a,
                    (const u64 *)(flipped ? c->sk1 : c->sk0), ep);
     }
     rt::launch(st, "k_s2_labels", rt::SEQ, k_s2_labels, dim3(gp), dim3(256), 0, a, res->labels);

@@ -163,10 +163,10 @@ __device__ static __forceinline__ i32 color_diff(u32 a, u32 b) {     // runner.r
     return dsum;
 }
 
-constexpr int S2_THREADS = 128;
+constexpr int S2_MAX_THREADS = 1024;   // block size is chosen at launch: 1024 for a few large images, 128 for big batches
 constexpr int S2_MEMCHUNK = 256;
 constexpr int S2_URGENT = 64;
-constexpr u32 S2_MAPBYTES = 24576;
+constexpr u32 S2_MAPBYTES = 40960;
 
 struct S2Shared {
     unsigned long long best;
@@ -179,7 +179,8 @@ struct S2Shared {
     u8 map[S2_MAPBYTES];
 };
 
-__global__ void __launch_bounds__(S2_THREADS) k_s2_epoch(S2 a, const u64 *keys, int epoch) {
+__global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_epoch(S2 a, const u64 *keys, int epoch) {
+    const u32 S2_THREADS = blockDim.x;
     VCB_SMEM(S2Shared, sh);
     const Dims d = a.d;
     const u32 img = blockIdx.x, base = a.slot_base[img];
@@ -337,15 +338,25 @@ __global__ void __launch_bounds__(S2_THREADS) k_s2_epoch(S2 a, const u64 *keys, 
                     continue;
                 }
                 __syncthreads();
-                for (u32 q = tid; q < cells; q += S2_THREADS) {
-                    const i32 mx = (i32)(q % pw) - 1, my = (i32)(q / pw) - 1;        // rect-relative
-                    const i32 x = L + mx, y = T + (i32)r0 + my;
-                    u8 in = 0;
-                    if (mx >= 0 && mx < (i32)rw && y >= T && y < B) {
-                        u32 fl;
-                        in = (s2_find(a.fw, base, l1[(u32)y * d.w + (u32)x], &fl) == c && !fl) ? 1 : 0;
+                for (u32 q0 = tid; q0 < cells; q0 += 4 * S2_THREADS) {
+                    // four independent cells per step: the label loads, then the forwarding loads, are all in flight together
+                    u32 lab[4]; bool ok[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const u32 q = q0 + u * S2_THREADS;
+                        const i32 mx = (i32)(q % pw) - 1, my = (i32)(q / pw) - 1;    // rect-relative
+                        const i32 x = L + mx, y = T + (i32)r0 + my;
+                        ok[u] = q < cells && mx >= 0 && mx < (i32)rw && y >= T && y < B;
+                        lab[u] = ok[u] ? __ldg(&l1[(u32)y * d.w + (u32)x]) : 0u;
                     }
-                    sh->map[q] = in;
+                    u32 fwv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) fwv[u] = ok[u] ? ldcg(&a.fw[base + lab[u]]) : 0xffffffffu;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const u32 q = q0 + u * S2_THREADS;
+                        if (q < cells) sh->map[q] = (ok[u] && fwv[u] == c) ? 1 : 0;   // == c: root is c and the hollow flag is clear
+                    }
                 }
                 __syncthreads();
                 for (u32 q = tid; q < rw * rows; q += S2_THREADS) {

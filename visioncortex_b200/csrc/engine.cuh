@@ -358,7 +358,6 @@ inline int run_stage2(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg, b
     a.idx_bits = 1; while ((1u << a.idx_bits) < max_slots) ++a.idx_bits;
     a.area_bits = 1; while ((1ull << a.area_bits) <= (u64)d.n) ++a.area_bits;
     int img_bits = 1; while ((1u << img_bits) < d.nimg) ++img_bits;
-    const int nbits = a.idx_bits + a.area_bits + (d.nimg > 1 ? img_bits : 0);
 
     const int gs = grid_for(c, total, 256, 16), gp = grid_for(c, d.N, 256, 16);
     rt::launch(st, "k_s2_init_img", rt::SEQ, k_s2_init_img, dim3((d.nimg + 127) / 128), dim3(128), 0, a);
@@ -371,6 +370,7 @@ inline int run_stage2(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg, b
     for (int ep = 0; ep <= max_epoch; ++ep) {
         rt::fill(st, d_count, 0, sizeof(u32));
         rt::launch(st, "k_s2_collect", rt::THR, k_s2_collect, dim3(gs), dim3(256), 0, a, ep);
+        const int nbits = a.idx_bits + ep + (d.nimg > 1 ? img_bits : 0);      // within an epoch only `ep` bits of the area vary
         const bool flipped = prims::radix_sort(st, c->sk0, c->sv0, c->sk1, c->sv1, d_count, total, nbits, c->rs_table, c->chunksum, c->sms * 8);
         // few images: one fat CTA each (perimeter / neighbour scans are block-parallel); many images: more CTAs per SM
         const int s2_threads =

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) k_s2_collect(S2 a, int epoch) {
             if (area && (31 - __clz((int)area)) == epoch) {
                 const u32 img = a.slot_img[s];
                 idx = s - a.slot_base[img];
-                key = ((u64)img << (a.idx_bits + a.area_bits)) | ((u64)area << a.idx_bits) | idx;
+                key = ((u64)img << (a.idx_bits + epoch)) | ((u64)(area - (1u << epoch)) << a.idx_bits) | idx;   // area has `epoch` free bits
                 take = true;
             }
         }
@@ -174,7 +174,7 @@ struct S2Shared {
     u32 mem[S2_MEMCHUNK];
     u32 eoff[S2_MEMCHUNK];
     u32 deg[S2_MEMCHUNK + 1];
-    u32 cur, area, ndist, perim, nmem, more, mycolor, nurg, lo, hi, stamp, nchunks, newfw, target, want_perim, deepen;
+    u32 cur, area, ndist, perim, nmem, more, mycolor, nurg, lo, hi, stamp, nchunks, newfw, target, want_perim, deepen, single;
     i32 rect[4];
     u8 map[S2_MAPBYTES];
 };
@@ -187,8 +187,9 @@ __global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_epoch(S2 a, const u64 *ke
     const u32 nslots = a.slot_base[img + 1] - base;
     const u32 tid = threadIdx.x;
     S2ImgState *ist = a.ist + img;
-    const int kshift = a.idx_bits + a.area_bits;
-    const u64 idx_mask = (1ull << a.idx_bits) - 1ull, area_mask = (1ull << a.area_bits) - 1ull;
+    const int kshift = a.idx_bits + epoch;                      // sorted keys: image | (area - 2^epoch) | index
+    const u64 idx_mask = (1ull << a.idx_bits) - 1ull;
+    const u32 area_base = 1u << epoch;
     u64 *over = a.over + base;
 
     if (tid == 0) {
@@ -210,14 +211,14 @@ __global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_epoch(S2 a, const u64 *ke
             u32 c = NONE, carea = 0;
             while (true) {
                 u64 kb = ~0ull; int src = -1; u32 which = 0;
-                if (sh->lo < sh->hi) { kb = keys[sh->lo] & ((1ull << kshift) - 1ull); src = 0; }
+                if (sh->lo < sh->hi) { kb = (keys[sh->lo] & ((1ull << kshift) - 1ull)) + ((u64)area_base << a.idx_bits); src = 0; }
                 for (u32 i = 0; i < sh->nurg; ++i) if (sh->urgent[i] < kb) { kb = sh->urgent[i]; src = 1; which = i; }
                 for (u32 i = 0; i < ist->nover; ++i) if (over[i] < kb) { kb = over[i]; src = 2; which = i; }
                 if (src < 0) break;
                 if (src == 0) sh->lo++;
                 else if (src == 1) { sh->urgent[which] = sh->urgent[--sh->nurg]; }
                 else { over[which] = over[--ist->nover]; }
-                const u32 idx = (u32)(kb & idx_mask), ar = (u32)((kb >> a.idx_bits) & area_mask);
+                const u32 idx = (u32)(kb & idx_mask), ar = (u32)(kb >> a.idx_bits);   // kb = (area << idx_bits) | index
                 if (a.fw[base + idx] == idx && a.rec[base + idx].indices_len == ar) { c = idx; carea = ar; break; }
             }
             sh->cur = c; sh->area = carea;
@@ -226,6 +227,14 @@ __global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_epoch(S2 a, const u64 *ke
                 sh->stamp = ++ist->stamp;
                 sh->mycolor = avg_color(a.rec[base + c].sum);
                 sh->more = c; sh->nchunks = 0;
+                // fast path for a cluster that never absorbed anything (most pops): its member list is itself, so the
+                // adjacency range is loaded here and the gather / degree-prefix rounds are skipped
+                sh->single = 0;
+                if (a.mnext[base + c] == NONE) {
+                    const u32 e0 = a.adj_off[base + c], e1 = a.adj_off[base + c + 1];
+                    sh->mem[0] = c; sh->eoff[0] = e0; sh->deg[0] = 0; sh->deg[1] = e1 - e0;
+                    sh->nmem = 1; sh->more = NONE; sh->nchunks = 1; sh->single = 1;
+                }
             }
         }
         __syncthreads();
@@ -243,23 +252,26 @@ __global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_epoch(S2 a, const u64 *ke
         }
         // ---- neighbours of c (cluster.rs:132-171) over the member lists and the static adjacency
         const u32 stamp = sh->stamp, mycolor = sh->mycolor;
+        const bool single = sh->single != 0;                          // uniform (written before the barrier above)
         while (true) {
-            if (tid == 0) {
-                u32 n = 0, m = sh->more;
-                while (m != NONE && n < S2_MEMCHUNK) { sh->mem[n++] = m; m = a.mnext[base + m]; }
-                sh->nmem = n; sh->more = m; sh->nchunks++;
+            if (!single) {
+                if (tid == 0) {
+                    u32 n = 0, m = sh->more;
+                    while (m != NONE && n < S2_MEMCHUNK) { sh->mem[n++] = m; m = a.mnext[base + m]; }
+                    sh->nmem = n; sh->more = m; sh->nchunks++;
+                }
+                __syncthreads();
+                // edge-parallel: prefix of the member degrees in shared memory, then one (member, edge) item per thread step
+                for (u32 i = tid; i < sh->nmem; i += S2_THREADS) {
+                    const u32 s = sh->mem[i];
+                    sh->eoff[i] = a.adj_off[base + s];
+                    sh->deg[i] = a.adj_off[base + s + 1] - sh->eoff[i];
+                }
+                __syncthreads();
+                if (tid == 0) { const u32 nm0 = sh->nmem; u32 acc = 0; for (u32 i = 0; i < nm0; ++i) { const u32 dg = sh->deg[i]; sh->deg[i] = acc; acc += dg; } sh->deg[nm0] = acc; }
+                __syncthreads();
             }
-            __syncthreads();
             const u32 nm = sh->nmem;
-            // edge-parallel: prefix of the member degrees in shared memory, then one (member, edge) item per thread step
-            for (u32 i = tid; i < nm; i += S2_THREADS) {
-                const u32 s = sh->mem[i];
-                sh->eoff[i] = a.adj_off[base + s];
-                sh->deg[i] = a.adj_off[base + s + 1] - sh->eoff[i];
-            }
-            __syncthreads();
-            if (tid == 0) { u32 acc = 0; for (u32 i = 0; i < nm; ++i) { const u32 dg = sh->deg[i]; sh->deg[i] = acc; acc += dg; } sh->deg[nm] = acc; }
-            __syncthreads();
             const u32 nitems = sh->deg[nm];
             for (u32 it = tid; it < nitems; it += S2_THREADS) {
                 u32 lo = 0, hi = nm;                                  // last member with prefix <= it
@@ -291,7 +303,7 @@ __global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_epoch(S2 a, const u64 *ke
         // thread 0 alone reads the target's record here: it goes on to modify it while the others may still be behind
         if (tid == 0) {
             const u32 tg = (u32)sh->best;
-            const i32 md = color_diff(mycolor, avg_color(a.rec[base + tg].sum));
+            const i32 md = (i32)(((u32)(sh->best >> 32) - tg) / 65535u);   // key = diff * 65535 + index (builder.rs:452)
             sh->target = tg;
             sh->want_perim = 0; sh->deepen = 0;
             if (a.cfg.hier_max && a.cfg.good_min < (u64)area && (u64)area < a.cfg.good_max && md > a.cfg.deepen_diff) {

@@ -124,6 +124,14 @@ int vcb_runner_run(vcb_ctx *ctx, const vcb_runner_config *cfg, const uint8_t *rg
 int vcb_runner_run_batch(vcb_ctx *ctx, const vcb_runner_config *cfg, const uint8_t *const *rgba,
                          const uint32_t *width, const uint32_t *height, size_t n, vcb_clusters **out);
 
+/* One giant image split into row bands over the GPUs of one box (BASELINE config 5).  ctxs[0..nctx) are contexts on
+ * distinct devices with peer access; ctxs[0] owns the result.  The workspace arrays are ONE virtual address range striped
+ * over the devices; each device runs the per-pixel kernels on its band and reaches the other bands' records (border label
+ * equivalences included) through NVLink peer loads / stores / atomics; the spanning-forest "union pass" over all bands
+ * runs once on ctxs[0].  Result: identical to vcb_runner_run. */
+int vcb_runner_run_banded(vcb_ctx *const *ctxs, int nctx, const vcb_runner_config *cfg, const uint8_t *rgba,
+                          uint32_t width, uint32_t height, vcb_clusters **out);
+
 /* Device-resident variant: d_rgba points to n images of identical size stored back to back in device memory
  * of ctx's device.  Results stay on the device until an accessor is called. */
 int vcb_runner_run_device(vcb_ctx *ctx, const vcb_runner_config *cfg, const uint8_t *d_rgba,

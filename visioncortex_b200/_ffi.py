@@ -89,7 +89,7 @@ DEFAULT_LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "
 EXPORTED_SYMBOLS = [
     "vcb_strerror", "vcb_last_error", "vcb_abi_version", "vcb_runner_config_default",
     "vcb_ctx_create", "vcb_ctx_destroy", "vcb_ctx_device", "vcb_ctx_set_option", "vcb_clusters_take_image",
-    "vcb_runner_run", "vcb_runner_run_batch", "vcb_runner_run_device",
+    "vcb_runner_run", "vcb_runner_run_batch", "vcb_runner_run_device", "vcb_runner_run_banded",
     "vcb_clusters_info_get", "vcb_clusters_cluster_indices", "vcb_clusters_outputs", "vcb_clusters_records",
     "vcb_clusters_indices_pool", "vcb_clusters_holes_pool", "vcb_clusters_to_color_image",
     "vcb_clusters_device_labels", "vcb_clusters_free",
@@ -161,6 +161,7 @@ class Library:
             f("ctx_set_option").argtypes = [p, C.c_int, C.c_int64]
             f("clusters_take_image").argtypes = [p, p]
             f("runner_run_batch").argtypes = [p, C.POINTER(RunnerConfigC), p, p, p, C.c_size_t, p]
+            f("runner_run_banded").argtypes = [p, C.c_int, C.POINTER(RunnerConfigC), p, C.c_uint32, C.c_uint32, pp]
             f("runner_run_device").argtypes = [p, C.POINTER(RunnerConfigC), p, C.c_uint32, C.c_uint32, C.c_size_t, p]
             f("clusters_device_labels").argtypes = [p]
             f("clusters_device_labels").restype = p

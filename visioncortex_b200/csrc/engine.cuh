@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "stage2.cuh"
+#include "vmm.h"
 
 struct vcb_ctx {
     int device = 0;
@@ -26,6 +27,11 @@ struct vcb_ctx {
     size_t d_stage_cap = 0;
     int opt_materialize = 0;          // VCB_OPT_MATERIALIZE_INDICES
     u32 last_counters[8] = {};
+    // row-band mode: workspace arrays striped over the GPUs of the box (vmm.h)
+    rt::VmmArray bw_flags, bw_pc, bw_la, bw_ls, bw_lr, bw_ev, bw_rgba;
+    size_t bw_capN = 0;
+    int bw_ndev = 0;
+    u32 bw_split = 0;
     // stage-2 workspace
     size_t cap_s2_slots = 0, cap_s2_adj = 0;
     u32 *s2_fw = nullptr, *s2_mnext = nullptr, *s2_mtail = nullptr, *s2_mark = nullptr, *s2_adj_off = nullptr,
@@ -128,9 +134,37 @@ __global__ void k_meta_init(Dims d, Bufs b) {
     b.meta[img] = m;
 }
 
+// Row-band mode: the devices that share one image.  Device k physically owns pixels [k*split, (k+1)*split) of every striped
+// array and runs the per-pixel kernels on the rows that start inside that range; everything else runs on ctx[0].
+struct DevSet {
+    int n = 1;
+    vcb_ctx *ctx[8] = {};
+    u32 split = 0;
+    // first row handled by device k (k = n gives h)
+    u32 row_begin(int k, const Dims &d) const {
+        if (n <= 1) return k == 0 ? 0 : d.h;
+        if (k >= n) return d.h;
+        const u64 r = ((u64)k * split + d.w - 1) / d.w;
+        return r > d.h ? d.h : (u32)r;
+    }
+};
+inline int sync_devices(const DevSet &ds) {
+    int rc = 0;
+    for (int k = 0; k < ds.n; ++k) {
+        rt::set_device(ds.ctx[k]->device);
+        if (rt::stream_sync(ds.ctx[k]->st) != 0 || ds.ctx[k]->st.last_error) {
+            if (!rc) ds.ctx[0]->err = ds.ctx[k]->st.last_error ? ds.ctx[k]->st.last_error_text : std::string("stream synchronize failed");
+            ds.ctx[k]->st.last_error = 0;
+            rc = VCB_ERR_CUDA;
+        }
+    }
+    rt::set_device(ds.ctx[0]->device);
+    return rc;
+}
+
 // K1 with TMA staging: colour images whose row pitch is a multiple of 16 bytes (TMA global-stride rule).  Returns false
 // when the plain-load kernel has to be used instead (binary images, odd widths, host simulator).
-template <class P> inline bool launch_edges_tma(vcb_ctx *, const Dims &, const P &, const Bufs &, u32) { return false; }
+template <class P> inline bool launch_edges_tma(vcb_ctx *, const Dims &, const P &, const Bufs &, u32, u32) { return false; }
 #ifndef VCB_HOSTSIM
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -149,8 +183,9 @@ inline PFN_encodeTiled get_encode_tiled() {
     }
     return fn;
 }
-template <> inline bool launch_edges_tma<ColorPolicy>(vcb_ctx *c, const Dims &d, const ColorPolicy &pol, const Bufs &b, u32 tiles) {
-    if (d.w % 4 != 0 || ((uintptr_t)pol.rgba & 15) != 0) return false;
+template <> inline bool launch_edges_tma<ColorPolicy>(vcb_ctx *c, const Dims &d, const ColorPolicy &pol, const Bufs &b, u32 tile0, u32 tiles) {
+    static const bool no_tma = std::getenv("VCB_NO_TMA") != nullptr;
+    if (no_tma || d.w % 4 != 0 || ((uintptr_t)pol.rgba & 15) != 0) return false;
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return false;
     CUtensorMap tmap;
@@ -161,7 +196,7 @@ template <> inline bool launch_edges_tma<ColorPolicy>(vcb_ctx *c, const Dims &d,
     if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)pol.rgba, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return false;
-    rt::launch(c->st, "k_edges_tile", rt::THR, k_edges_tile_tma<ColorPolicy>, dim3(tiles), dim3(K1_THREADS), K1_SMEM, d, pol, b, tmap);
+    rt::launch(c->st, "k_edges_tile", rt::THR, k_edges_tile_tma<ColorPolicy>, dim3(tiles), dim3(K1_THREADS), K1_SMEM, d, pol, b, tmap, tile0);
     return true;
 }
 #endif
@@ -170,19 +205,39 @@ template <> inline bool launch_edges_tma<ColorPolicy>(vcb_ctx *c, const Dims &d,
 // base = 1 for the colour path (slot 0 = ZERO, builder.rs:44-45,189), 0 for the binary path.
 template <class P>
 inline int run_stage1(vcb_ctx *c, const Dims &d, const P &pol, u32 base, bool want_attr, int keep_key, BatchResult *res,
-                      std::vector<ImgMeta> &meta_out, Counters &ctr_out) {
+                      std::vector<ImgMeta> &meta_out, Counters &ctr_out, const DevSet *dsp = nullptr) {
     rt::Stream &st = c->st;
     Bufs b = c->b;
+    DevSet one; one.n = 1; one.ctx[0] = c;
+    const DevSet &ds = dsp ? *dsp : one;
+    const bool multi = ds.n > 1;
     const int g_img = (int)((d.nimg + 127) / 128);
     rt::launch(st, "k_meta_init", rt::SEQ, k_meta_init, dim3(g_img), dim3(128), 0, d, b);
 
-    const u32 tiles = ((d.w + TW - 1) / TW) * ((d.h + TH - 1) / TH) * d.nimg;
-    if (!launch_edges_tma(c, d, pol, b, tiles))
-        rt::launch(st, "k_edges_tile", rt::THR, k_edges_tile<P>, dim3(tiles), dim3(K1_THREADS), K1_SMEM, d, pol, b);
-    if (d.w % 4 == 0)
-        rt::launch(st, "k_flatten_events", rt::THR, k_flatten_events4, dim3(grid_for(c, d.N / 4, K2_THREADS, 16)), dim3(K2_THREADS), 0, d, b);
-    else
-        rt::launch(st, "k_flatten_events", rt::THR, k_flatten_events, dim3(grid_for(c, d.N, K2_THREADS, 16)), dim3(K2_THREADS), 0, d, b);
+    const u32 tiles_x = (d.w + TW - 1) / TW, tiles_y = (d.h + TH - 1) / TH;
+    if (multi) { const int e = sync_devices(ds); if (e) return e; }
+    for (int k = 0; k < ds.n; ++k) {                      // K1: device k takes the tile rows that start in its band
+        vcb_ctx *ck = ds.ctx[k];
+        u32 t0 = multi ? (ds.row_begin(k, d) + TH - 1) / TH : 0, t1 = multi ? (ds.row_begin(k + 1, d) + TH - 1) / TH : tiles_y * d.nimg;
+        if (multi && t1 > tiles_y) t1 = tiles_y;
+        if (t1 <= t0) continue;
+        rt::set_device(ck->device);
+        const u32 tile0 = t0 * tiles_x, tiles = (t1 - t0) * tiles_x;
+        if (!launch_edges_tma(ck, d, pol, b, tile0, tiles))
+            rt::launch(ck->st, "k_edges_tile", rt::THR, k_edges_tile<P>, dim3(tiles), dim3(K1_THREADS), K1_SMEM, d, pol, b, tile0);
+    }
+    if (multi) { const int e = sync_devices(ds); if (e) return e; }
+    for (int k = 0; k < ds.n; ++k) {                      // K2
+        vcb_ctx *ck = ds.ctx[k];
+        const u32 p0 = multi ? ds.row_begin(k, d) * d.w : 0, p1 = multi ? ds.row_begin(k + 1, d) * d.w : d.N;
+        if (p1 <= p0) continue;
+        rt::set_device(ck->device);
+        if (d.w % 4 == 0)
+            rt::launch(ck->st, "k_flatten_events", rt::THR, k_flatten_events4, dim3(grid_for(ck, (p1 - p0) / 4, K2_THREADS, 16)), dim3(K2_THREADS), 0, d, b, p0 / 4, p1 / 4);
+        else
+            rt::launch(ck->st, "k_flatten_events", rt::THR, k_flatten_events, dim3(grid_for(ck, p1 - p0, K2_THREADS, 16)), dim3(K2_THREADS), 0, d, b, p0, p1);
+    }
+    if (multi) { const int e = sync_devices(ds); if (e) return e; }
     prims::scan(st, "scan_new", NewScan{d, b}, c->chunksum, d.N, c->sms * 8);
     prims::scan(st, "scan_new", LeafScan{d, b}, c->chunksum, d.N, c->sms * 8);
     {
@@ -203,20 +258,39 @@ inline int run_stage1(vcb_ctx *c, const Dims &d, const P &pol, u32 base, bool wa
         if (nseg > d.h) nseg = d.h;
         u32 rows = (d.h + nseg - 1) / nseg;
         if (rows < 8 && d.h >= 8) rows = 8;
-        const u64 threads = (u64)d.nimg * ((d.h + rows - 1) / rows) * wpad;
-        const int g = grid_for(c, threads, K5_THREADS, 16);
-        if (want_attr)
-            rt::launch(st, "k_attribute", rt::THR, k_attribute<P, true>, dim3(g), dim3(K5_THREADS), 0, d, pol, b, rows, keep_key);
-        else
-            rt::launch(st, "k_attribute", rt::THR, k_attribute<P, false>, dim3(g), dim3(K5_THREADS), 0, d, pol, b, rows, keep_key);
+        const u32 nseg_t = (d.h + rows - 1) / rows;
+        if (multi) { const int e = sync_devices(ds); if (e) return e; }
+        for (int k = 0; k < ds.n; ++k) {                  // K5: device k takes the row segments that start in its band
+            vcb_ctx *ck = ds.ctx[k];
+            u32 s0 = multi ? (ds.row_begin(k, d) + rows - 1) / rows : 0, s1 = multi ? (ds.row_begin(k + 1, d) + rows - 1) / rows : nseg_t * d.nimg;
+            if (multi && s1 > nseg_t) s1 = nseg_t;
+            if (s1 <= s0) continue;
+            rt::set_device(ck->device);
+            const u64 t_lo = (u64)s0 * wpad, t_hi = (u64)s1 * wpad;
+            const int g = grid_for(ck, t_hi - t_lo, K5_THREADS, 16);
+            if (want_attr)
+                rt::launch(ck->st, "k_attribute", rt::THR, k_attribute<P, true>, dim3(g), dim3(K5_THREADS), 0, d, pol, b, rows, keep_key, t_lo, t_hi);
+            else
+                rt::launch(ck->st, "k_attribute", rt::THR, k_attribute<P, false>, dim3(g), dim3(K5_THREADS), 0, d, pol, b, rows, keep_key, t_lo, t_hi);
+        }
+        if (multi) { const int e = sync_devices(ds); if (e) return e; }
     }
     rt::launch(st, "k_tournament", rt::THR, k_tournament, dim3(grid_for(c, d.N / 4, K6_THREADS, 16)), dim3(K6_THREADS), 0, d, b);
     prims::scan(st, "scan_label", LabelScan{d, b}, c->chunksum, d.N, c->sms * 8);
     rt::launch(st, "k_image_meta", rt::SEQ, k_image_meta, dim3(g_img), dim3(128), 0, d, b, base);
     rt::launch(st, "k_leaf_labels", rt::SEQ, k_leaf_labels, dim3(grid_for(c, d.N / 4, K8_THREADS, 16)), dim3(K8_THREADS), 0, d, b, base);
     rt::launch(st, "k_leaf_final", rt::SEQ, k_leaf_final, dim3(grid_for(c, d.N / 4, K8_THREADS, 16)), dim3(K8_THREADS), 0, d, b);
-    if (res->labels)
-        rt::launch(st, "k_labels", rt::SEQ, k_labels, dim3(grid_for(c, d.N, K8_THREADS, 16)), dim3(K8_THREADS), 0, d, b, res->labels);
+    if (res->labels) {
+        if (multi) { const int e = sync_devices(ds); if (e) return e; }
+        for (int k = 0; k < ds.n; ++k) {
+            vcb_ctx *ck = ds.ctx[k];
+            const u32 p0 = multi ? ds.row_begin(k, d) * d.w : 0, p1 = multi ? ds.row_begin(k + 1, d) * d.w : d.N;
+            if (p1 <= p0) continue;
+            rt::set_device(ck->device);
+            rt::launch(ck->st, "k_labels", rt::SEQ, k_labels, dim3(grid_for(ck, p1 - p0, K8_THREADS, 16)), dim3(K8_THREADS), 0, d, b, res->labels, p0, p1);
+        }
+        if (multi) { const int e = sync_devices(ds); if (e) return e; }
+    }
 
     // one small read-back: per-image slot counts (sizes of the result) and the error flags
     ImgMeta *hm = (ImgMeta *)c->h_pinned;

@@ -143,10 +143,10 @@ template <class P> __device__ __forceinline__ void edges_tile_body(const Dims &d
                                                                     u32 x0, u32 y0);
 
 // staging by plain loads (any width, binary images, and the host simulator)
-template <class P> __global__ void __launch_bounds__(K1_THREADS) k_edges_tile(Dims d, P pol, Bufs b) {
+template <class P> __global__ void __launch_bounds__(K1_THREADS) k_edges_tile(Dims d, P pol, Bufs b, u32 tile0) {
     VCB_SMEM(u32, pix);
     const u32 tiles_x = (d.w + TW - 1) / TW, tiles_y = (d.h + TH - 1) / TH;
-    const u32 tile = blockIdx.x;
+    const u32 tile = blockIdx.x + tile0;
     const u32 img = tile / (tiles_x * tiles_y), tr = tile % (tiles_x * tiles_y);
     const u32 x0 = (tr % tiles_x) * TW, y0 = (tr / tiles_x) * TH;
     const u32 base = img * d.n;
@@ -166,11 +166,11 @@ template <class P> __global__ void __launch_bounds__(K1_THREADS) k_edges_tile(Di
 // out-of-image coordinates zero-filled by the hardware -- into shared memory and the CTA waits on an mbarrier.
 __device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 template <class P> __global__ void __launch_bounds__(K1_THREADS)
-k_edges_tile_tma(Dims d, P pol, Bufs b, const __grid_constant__ CUtensorMap tmap) {
+k_edges_tile_tma(Dims d, P pol, Bufs b, const __grid_constant__ CUtensorMap tmap, u32 tile0) {
     VCB_SMEM(u32, pix);
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(pix) + K1_SMEM - 16);
     const u32 tiles_x = (d.w + TW - 1) / TW, tiles_y = (d.h + TH - 1) / TH;
-    const u32 tile = blockIdx.x;
+    const u32 tile = blockIdx.x + tile0;
     const u32 img = tile / (tiles_x * tiles_y), tr = tile % (tiles_x * tiles_y);
     const u32 x0 = (tr % tiles_x) * TW, y0 = (tr / tiles_x) * TH;
     const u32 bar = smem_addr(mbar);
@@ -301,15 +301,15 @@ __device__ static __forceinline__ u32 pc_root_f(const u32 *pc, const u8 *flags, 
 }
 
 constexpr int K2_THREADS = 256;
-__global__ void __launch_bounds__(K2_THREADS) k_flatten_events(Dims d, Bufs b) {
+__global__ void __launch_bounds__(K2_THREADS) k_flatten_events(Dims d, Bufs b, u32 p_lo, u32 p_hi) {
     const u32 stride = gridDim.x * K2_THREADS;
     const int lane = threadIdx.x & 31;
-    const u32 nloop = (d.N + stride - 1) / stride;
+    const u32 nloop = (p_hi - p_lo + stride - 1) / stride;
     for (u32 it = 0; it < nloop; ++it) {
-        const u32 g = it * stride + blockIdx.x * K2_THREADS + threadIdx.x;
+        const u32 g = p_lo + it * stride + blockIdx.x * K2_THREADS + threadIdx.x;
         bool is_cand = false;
         u32 ea = 0, eb = 0;
-        if (g < d.N) {
+        if (g < p_hi) {
             const u32 f = b.flags[g];
             if ((f & J_MASK) != J_NONE && !(f & F_FINAL)) {
                 const u32 r = pc_root(b.pc, g);
@@ -344,13 +344,13 @@ __global__ void __launch_bounds__(K2_THREADS) k_flatten_events(Dims d, Bufs b) {
 
 // K2 for widths that are a multiple of 4: one thread per 4 consecutive pixels of a row, flags read as one 32-bit word
 // (own row and the row above), candidates compacted with one atomic per warp.
-__global__ void __launch_bounds__(K2_THREADS) k_flatten_events4(Dims d, Bufs b) {
-    const u32 groups = d.N / 4;
+__global__ void __launch_bounds__(K2_THREADS) k_flatten_events4(Dims d, Bufs b, u32 grp_lo, u32 grp_hi) {
+    const u32 groups = grp_hi;
     const u32 stride = gridDim.x * K2_THREADS;
     const int lane = threadIdx.x & 31;
-    const u32 nloop = (groups + stride - 1) / stride;
+    const u32 nloop = (grp_hi - grp_lo + stride - 1) / stride;
     for (u32 it = 0; it < nloop; ++it) {
-        const u32 grp = it * stride + blockIdx.x * K2_THREADS + threadIdx.x;
+        const u32 grp = grp_lo + it * stride + blockIdx.x * K2_THREADS + threadIdx.x;
         u32 ncand = 0, cg[4], ca[4], cb[4];
         if (grp < groups) {
             const u32 g4 = grp * 4;
@@ -588,13 +588,13 @@ struct LeafRun {
 
 constexpr int K5_THREADS = 128;
 template <class P, bool WRITE_ATTR>
-__global__ void __launch_bounds__(K5_THREADS) k_attribute(Dims d, P pol, Bufs b, u32 rows_per_seg, int keep_key) {
+__global__ void __launch_bounds__(K5_THREADS) k_attribute(Dims d, P pol, Bufs b, u32 rows_per_seg, int keep_key, u64 t_lo, u64 t_hi) {
     const u32 wpad = (d.w + 31) & ~31u;
     const u32 nseg = (d.h + rows_per_seg - 1) / rows_per_seg;
-    const u64 total = (u64)d.nimg * nseg * wpad;
+    const u64 total = t_hi;                               // work items [t_lo, t_hi) of nimg * nseg * wpad (multiples of 32)
     const u64 stride = (u64)gridDim.x * K5_THREADS;
     const int lane = threadIdx.x & 31;
-    for (u64 t0 = (u64)blockIdx.x * K5_THREADS + threadIdx.x - lane; t0 < total; t0 += stride) {
+    for (u64 t0 = t_lo + (u64)blockIdx.x * K5_THREADS + threadIdx.x - lane; t0 < total; t0 += stride) {
         const u64 t = t0 + lane;
         const u32 x = (u32)(t % wpad);
         const u32 seg = (u32)((t / wpad) % nseg), img = (u32)(t / ((u64)wpad * nseg));
@@ -848,9 +848,9 @@ __global__ void __launch_bounds__(K8_THREADS) k_leaf_final(Dims d, Bufs b) {
     }
 }
 // per pixel: cluster_indices (builder.rs:161; label 0 for keyed pixels, builder.rs:330-334)
-__global__ void __launch_bounds__(K8_THREADS) k_labels(Dims d, Bufs b, u32 *labels) {
+__global__ void __launch_bounds__(K8_THREADS) k_labels(Dims d, Bufs b, u32 *labels, u32 p_lo, u32 p_hi) {
     const u32 stride = gridDim.x * K8_THREADS;
-    for (u32 g = blockIdx.x * K8_THREADS + threadIdx.x; g < d.N; g += stride) {
+    for (u32 g = p_lo + blockIdx.x * K8_THREADS + threadIdx.x; g < p_hi; g += stride) {
         const u32 leaf = b.pc[g];
         labels[g] = leaf == NONE ? 0u : b.la[leaf].flabel;
     }

@@ -66,7 +66,7 @@ int fetch_last_record(vcb_clusters *h) {
 
 // colour path on device-resident images
 int run_color(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w, u32 h, size_t nimg, bool want_pool,
-              bool retain, std::shared_ptr<BatchResult> &out_br) {
+              bool retain, std::shared_ptr<BatchResult> &out_br, const DevSet *ds = nullptr) {
     int e = validate_cfg(c, cfg);
     if (e) return e;
     const u64 n64 = (u64)w * h;
@@ -97,7 +97,7 @@ int run_color(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w,
 
     std::vector<ImgMeta> meta;
     Counters ctr{};
-    e = run_stage1(c, d, pol, 1u, want_pool, keep ? 1 : 0, br.get(), meta, ctr);
+    e = run_stage1(c, d, pol, 1u, want_pool, keep ? 1 : 0, br.get(), meta, ctr, ds);
     if (e) return e;
     if (ctr.err & 1u) return fail(c, VCB_ERR_UNSUPPORTED, "key colour is not clean: a non-key pixel is color_same to the key (order-dependent in the reference)");
     if (ctr.err & 2u) return fail(c, VCB_ERR_UNSUPPORTED, "diagonal=true: a stale cluster_upleft label resurrects a dead slot in the reference (builder.rs:301-305,341-343); this input is fenced");
@@ -232,6 +232,7 @@ void vcb_ctx_destroy(vcb_ctx *c) {
     rt::dev_free(c->sv0); rt::dev_free(c->sv1); rt::dev_free(c->d_small); rt::dev_free(c->d_stage);
     rt::dev_free(c->s2_fw); rt::dev_free(c->s2_mnext); rt::dev_free(c->s2_mtail); rt::dev_free(c->s2_mark); rt::dev_free(c->s2_adj_off);
     rt::dev_free(c->s2_cursor); rt::dev_free(c->s2_adj); rt::dev_free(c->s2_over); rt::dev_free(c->s2_ist);
+    for (rt::VmmArray *a : {&c->bw_flags, &c->bw_pc, &c->bw_la, &c->bw_ls, &c->bw_lr, &c->bw_ev, &c->bw_rgba}) rt::vmm_free(*a);
     rt::host_free(c->h_pinned);
     rt::stream_destroy(c->st);
     delete c;
@@ -259,6 +260,79 @@ int vcb_runner_run(vcb_ctx *c, const vcb_runner_config *cfg, const uint8_t *rgba
     if (!d) return fail(c, VCB_ERR_NOMEM, "device out of memory (input)");
     rt::copy_h2d(c->st, d, rgba, bytes);
     return run_color_device(c, cfg, d, width, height, 1, out);
+}
+
+int vcb_runner_run_banded(vcb_ctx *const *ctxs, int nctx, const vcb_runner_config *cfg, const uint8_t *rgba, uint32_t width,
+                          uint32_t height, vcb_clusters **out) {
+    if (!ctxs || nctx < 1 || nctx > 8 || !ctxs[0]) return VCB_ERR_INVALID_ARG;
+    vcb_ctx *c = ctxs[0];
+    if (!out) return fail(c, VCB_ERR_INVALID_ARG, "null output");
+    *out = nullptr;
+    int e = validate_cfg(c, cfg);
+    if (e) return e;
+    const u64 n64 = (u64)width * height;
+    if (n64 == 0 || !rgba) return fail(c, VCB_ERR_INVALID_ARG, "empty image");
+    if (n64 >= 0x7fffff00ull) return fail(c, VCB_ERR_INVALID_ARG, "width*height must be below 2^31");
+    if (nctx == 1) return vcb_runner_run(c, cfg, rgba, width, height, out);
+    int devs[8];
+    for (int k = 0; k < nctx; ++k) {
+        if (!ctxs[k]) return fail(c, VCB_ERR_INVALID_ARG, "null context");
+        devs[k] = ctxs[k]->device;
+#ifndef VCB_HOSTSIM
+        for (int j = 0; j < k; ++j) if (devs[j] == devs[k]) return fail(c, VCB_ERR_INVALID_ARG, "contexts must be on distinct devices");
+#endif
+    }
+    if (!rt::vmm_available()) return fail(c, VCB_ERR_CUDA, "virtual memory management API unavailable");
+    if (rt::enable_peer_access(nctx, devs) != 0) return fail(c, VCB_ERR_CUDA, "peer access between the devices is not available");
+    rt::set_device(c->device);
+    const u32 N = (u32)n64;
+    // striped workspace: device k owns pixels [k * split, (k + 1) * split); split is a multiple of the mapping granularity
+    // for 1-byte elements, hence for every element size
+    if (N > c->bw_capN || nctx != c->bw_ndev) {
+        for (rt::VmmArray *a : {&c->bw_flags, &c->bw_pc, &c->bw_la, &c->bw_ls, &c->bw_lr, &c->bw_ev, &c->bw_rgba}) rt::vmm_free(*a);
+        size_t gran = 1;
+        for (int k = 0; k < nctx; ++k) gran = std::max(gran, rt::vmm_granularity(devs[k]));
+        size_t split = ((size_t)N + nctx - 1) / nctx;
+        split = (split + gran - 1) / gran * gran;
+        int rc = 0;
+        rc |= rt::vmm_alloc(c->bw_flags, split, 1, nctx, devs, N);
+        rc |= rt::vmm_alloc(c->bw_pc, split, 4, nctx, devs, N);
+        rc |= rt::vmm_alloc(c->bw_la, split, sizeof(LeafA), nctx, devs, N);
+        rc |= rt::vmm_alloc(c->bw_ls, split, sizeof(LeafS), nctx, devs, N);
+        rc |= rt::vmm_alloc(c->bw_lr, split, sizeof(LeafR), nctx, devs, N);
+        rc |= rt::vmm_alloc(c->bw_ev, split, sizeof(EvRec), nctx, devs, N);
+        rc |= rt::vmm_alloc(c->bw_rgba, split, 4, nctx, devs, N);
+        if (rc) { c->bw_capN = 0; return fail(c, VCB_ERR_NOMEM, "striped workspace allocation failed"); }
+        c->bw_capN = N; c->bw_ndev = nctx; c->bw_split = (u32)split;
+    }
+    e = ensure_workspace(c, N, 1);
+    if (e) return fail(c, e, "device out of memory (workspace)");
+    DevSet ds;
+    ds.n = nctx; ds.split = c->bw_split;
+    for (int k = 0; k < nctx; ++k) ds.ctx[k] = ctxs[k];
+    // every device loads its own band of the image from the host (no halo exchange: the row above a band is read in place
+    // through the shared address range)
+    for (int k = 0; k < nctx; ++k) {
+        const u64 p0 = std::min<u64>((u64)k * ds.split, N), p1 = std::min<u64>((u64)(k + 1) * ds.split, N);
+        if (p1 <= p0) continue;
+        rt::set_device(devs[k]);
+        rt::copy_h2d(ctxs[k]->st, (u8 *)c->bw_rgba.ptr + p0 * 4, rgba + p0 * 4, (size_t)(p1 - p0) * 4);
+    }
+    e = sync_devices(ds);
+    if (e) return e;
+    const Bufs saved = c->b;
+    c->b.flags = (u8 *)c->bw_flags.ptr; c->b.pc = (u32 *)c->bw_pc.ptr; c->b.la = (LeafA *)c->bw_la.ptr;
+    c->b.ls = (LeafS *)c->bw_ls.ptr; c->b.lr = (LeafR *)c->bw_lr.ptr; c->b.ev = (EvRec *)c->bw_ev.ptr;
+    std::shared_ptr<BatchResult> br;
+    e = run_color(c, cfg, (const u8 *)c->bw_rgba.ptr, width, height, 1, c->opt_materialize != 0, true, br, &ds);
+    if (!e) e = check_stream(c);
+    c->b = saved;
+    if (e) return e;
+    vcb_clusters *hd = new (std::nothrow) vcb_clusters();
+    if (!hd) return fail(c, VCB_ERR_NOMEM, "host out of memory");
+    hd->br = br; hd->img = 0;
+    *out = hd;
+    return VCB_OK;
 }
 
 int vcb_runner_run_batch(vcb_ctx *c, const vcb_runner_config *cfg, const uint8_t *const *rgba, const uint32_t *width,

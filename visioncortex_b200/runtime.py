@@ -140,3 +140,23 @@ class Context:
         arr = (C.c_uint32 * 8)()
         self.lib.check(self.lib.fn("ctx_last_counters")(self.handle, C.byref(arr)), self.handle)
         return {"candidate_events": arr[0], "new_events": arr[1], "leaves": arr[2], "msf_rounds": arr[3], "err": arr[4]}
+
+
+def runner_run_banded(contexts, rgba: np.ndarray, cfg: RunnerConfigC, pools: bool = False, color_image: bool = False) -> dict:
+    """One image split into row bands over several GPUs (contexts on distinct devices); result identical to runner_run."""
+    rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+    h, w = rgba.shape[:2]
+    lib = contexts[0].lib
+    arr = (C.c_void_p * len(contexts))(*[c.handle.value for c in contexts])
+    out = C.c_void_p()
+    st = lib.fn("runner_run_banded")(arr, len(contexts), C.byref(cfg), rgba.ctypes.data_as(C.c_void_p), w, h, C.byref(out))
+    lib.check(st, contexts[0].handle)
+    try:
+        res = lib.read_clusters(out, pools=pools, free=False, ctx=contexts[0].handle)
+        if color_image:
+            img = np.empty((h, w, 4), dtype=np.uint8)
+            lib.check(lib.fn("clusters_to_color_image")(out, img.ctypes.data_as(C.c_void_p)), contexts[0].handle)
+            res["color_image"] = img
+    finally:
+        lib.fn("clusters_free")(out)
+    return res

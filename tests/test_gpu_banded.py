@@ -18,7 +18,7 @@ def _contexts(n):
     return [Context(k) for k in range(n)]
 
 
-@pytest.mark.parametrize("ngpu", [2, 4])
+@pytest.mark.parametrize("ngpu", [2, 4, 8])
 def test_banded_matches_oracle(oracle, ngpu):
     ctxs = _contexts(ngpu)
     cases = [

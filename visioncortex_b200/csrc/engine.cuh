@@ -252,7 +252,7 @@ inline int run_stage1(vcb_ctx *c, const Dims &d, const P &pol, u32 base, bool wa
     {
         // rows per segment: enough threads to fill the machine, as few restarts as possible
         const u64 wpad = (d.w + 31) & ~31u;
-        const u64 target = (u64)c->sms * 2048;
+        const u64 target = (u64)c->sms * 2048 * (u64)ds.n;   // enough column walkers to fill every device
         u32 nseg = (u32)((target + wpad * d.nimg - 1) / (wpad * d.nimg));
         if (nseg < 1) nseg = 1;
         if (nseg > d.h) nseg = d.h;

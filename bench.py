@@ -191,31 +191,29 @@ def main():
         ctx.free_handles(hs)
 
     lib = ctx.lib
-    from visioncortex_b200._ffi import CLUSTER_REC_DTYPE, ClustersInfoC
+    from visioncortex_b200._ffi import CLUSTER_REC_DTYPE, HostResultC
 
-    # pinned host buffers for the results of one image (labels, records, clusters_output), reused for every image
-    pin_lab = torch.empty(NPX, dtype=torch.int32).pin_memory()
-    pin_rec = torch.empty(NPX // 4 * CLUSTER_REC_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
-    pin_out = torch.empty(NPX // 4, dtype=torch.int32).pin_memory()
+    # end-to-end leg: host images in pinned memory -> vcb_runner_run_batch_host -> labels, records and clusters_output of
+    # every image in pinned host memory.  The call pipelines H2D / compute / D2H over sub-batches.
+    REC_CAP = NPX // 8
+    pin_lab = torch.empty((B, NPX), dtype=torch.int32).pin_memory()
+    pin_rec = torch.empty((B, REC_CAP * CLUSTER_REC_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
+    pin_out = torch.empty((B, REC_CAP), dtype=torch.int32).pin_memory()
+    e2e_ptrs = (C.c_void_p * B)(*[im.ctypes.data for im in host_np])
+    e2e_res = (HostResultC * B)()
+    for k in range(B):
+        e2e_res[k].cluster_indices = pin_lab[k].data_ptr()
+        e2e_res[k].records = pin_rec[k].data_ptr()
+        e2e_res[k].outputs = pin_out[k].data_ptr()
+        e2e_res[k].records_cap = REC_CAP
+        e2e_res[k].outputs_cap = REC_CAP
 
     def step_e2e():
-        n = B
-        ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in host_np])
-        ws = (C.c_uint32 * n)(*([W] * n)); hs_ = (C.c_uint32 * n)(*([H] * n))
-        outs = (C.c_void_p * n)()
-        lib.check(lib.fn("runner_run_batch")(ctx.handle, C.byref(cfg), ptrs, ws, hs_, n, outs), ctx.handle)
+        lib.check(lib.fn("runner_run_batch_host")(ctx.handle, C.byref(cfg), e2e_ptrs, W, H, B, e2e_res), ctx.handle)
         d2h = 0
-        for k in range(n):
-            hnd = C.c_void_p(outs[k])
-            info = ClustersInfoC()
-            lib.check(lib.fn("clusters_info_get")(hnd, C.byref(info)), ctx.handle)
-            if info.num_slots > NPX // 4:
-                raise RuntimeError("result larger than the pinned staging buffers")
-            lib.check(lib.fn("clusters_cluster_indices")(hnd, C.c_void_p(pin_lab.data_ptr())), ctx.handle)
-            lib.check(lib.fn("clusters_records")(hnd, C.c_void_p(pin_rec.data_ptr())), ctx.handle)
-            lib.check(lib.fn("clusters_outputs")(hnd, C.c_void_p(pin_out.data_ptr())), ctx.handle)
-            d2h += NPX * 4 + info.num_slots * CLUSTER_REC_DTYPE.itemsize + info.num_outputs * 4
-            lib.fn("clusters_free")(hnd)
+        for k in range(B):
+            lib.check(e2e_res[k].status, ctx.handle)
+            d2h += NPX * 4 + e2e_res[k].info.num_slots * CLUSTER_REC_DTYPE.itemsize + e2e_res[k].info.num_outputs * 4
         return d2h
 
     # ---- device-resident timing (value)

@@ -124,6 +124,22 @@ int vcb_runner_run(vcb_ctx *ctx, const vcb_runner_config *cfg, const uint8_t *rg
 int vcb_runner_run_batch(vcb_ctx *ctx, const vcb_runner_config *cfg, const uint8_t *const *rgba,
                          const uint32_t *width, const uint32_t *height, size_t n, vcb_clusters **out);
 
+/* Host-to-host batch: n equally sized images in, the caller's result buffers out.  The images are processed in sub-batches;
+ * the host->device copy of the next sub-batch and the device->host copy of the previous results run on their own streams
+ * while the current sub-batch computes (full-duplex PCIe), so this is the call to use when everything lives in host memory
+ * (what the Rust shim does per image with vcb_runner_run + accessors).  records_cap / outputs_cap are capacities in
+ * elements; an image whose result does not fit gets status VCB_ERR_NOMEM (info is still filled).  Pinned buffers copy faster. */
+typedef struct vcb_host_result {
+    uint32_t        *cluster_indices;   /* width*height */
+    vcb_cluster_rec *records;           /* records_cap */
+    uint32_t        *outputs;           /* outputs_cap */
+    uint32_t         records_cap, outputs_cap;
+    vcb_clusters_info info;             /* out */
+    int              status;            /* out */
+} vcb_host_result;
+int vcb_runner_run_batch_host(vcb_ctx *ctx, const vcb_runner_config *cfg, const uint8_t *const *rgba, uint32_t width,
+                              uint32_t height, size_t n, vcb_host_result *results);
+
 /* One giant image split into row bands over the GPUs of one box (BASELINE config 5).  ctxs[0..nctx) are contexts on
  * distinct devices with peer access; ctxs[0] owns the result.  The workspace arrays are ONE virtual address range striped
  * over the devices; each device runs the per-pixel kernels on its band and reaches the other bands' records (border label

@@ -283,3 +283,15 @@ def test_c5_giant_image_single_gpu(gpu, oracle):
     ref = oracle.runner_run(img, cfg, pools=False)
     got = gpu.runner_run(img, cfg, pools=False)
     assert_same_clusters(got, ref, pools=False, ctx="C5 8192^2")
+
+
+def test_host_to_host_batch(gpu, oracle):
+    """vcb_runner_run_batch_host (pipelined H2D / compute / D2H over sub-batches) equals per-image runs."""
+    from visioncortex_b200.runtime import runner_run_batch_host
+
+    imgs = [synth.g2_scene(640, 360, seed=200 + k) for k in range(9)]
+    for cfg in (c2_config(640, 360), make_config()):
+        got = runner_run_batch_host(gpu, imgs, cfg, records_cap=640 * 360 // 2)
+        for k, im in enumerate(imgs):
+            ref = oracle.runner_run(im, cfg, pools=False)
+            assert_same_clusters(got[k], ref, pools=False, ctx=f"host batch image {k}")

@@ -49,6 +49,18 @@ class ClustersInfoC(C.Structure):
     ]
 
 
+class HostResultC(C.Structure):
+    _fields_ = [
+        ("cluster_indices", C.c_void_p),
+        ("records", C.c_void_p),
+        ("outputs", C.c_void_p),
+        ("records_cap", C.c_uint32),
+        ("outputs_cap", C.c_uint32),
+        ("info", ClustersInfoC),
+        ("status", C.c_int),
+    ]
+
+
 class BinClustersInfoC(C.Structure):
     _fields_ = [
         ("width", C.c_uint32),
@@ -89,7 +101,7 @@ DEFAULT_LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "
 EXPORTED_SYMBOLS = [
     "vcb_strerror", "vcb_last_error", "vcb_abi_version", "vcb_runner_config_default",
     "vcb_ctx_create", "vcb_ctx_destroy", "vcb_ctx_device", "vcb_ctx_set_option", "vcb_clusters_take_image",
-    "vcb_runner_run", "vcb_runner_run_batch", "vcb_runner_run_device", "vcb_runner_run_banded",
+    "vcb_runner_run", "vcb_runner_run_batch", "vcb_runner_run_device", "vcb_runner_run_banded", "vcb_runner_run_batch_host",
     "vcb_clusters_info_get", "vcb_clusters_cluster_indices", "vcb_clusters_outputs", "vcb_clusters_records",
     "vcb_clusters_indices_pool", "vcb_clusters_holes_pool", "vcb_clusters_to_color_image",
     "vcb_clusters_device_labels", "vcb_clusters_free",
@@ -161,6 +173,7 @@ class Library:
             f("ctx_set_option").argtypes = [p, C.c_int, C.c_int64]
             f("clusters_take_image").argtypes = [p, p]
             f("runner_run_batch").argtypes = [p, C.POINTER(RunnerConfigC), p, p, p, C.c_size_t, p]
+            f("runner_run_batch_host").argtypes = [p, C.POINTER(RunnerConfigC), p, C.c_uint32, C.c_uint32, C.c_size_t, p]
             f("runner_run_banded").argtypes = [p, C.c_int, C.POINTER(RunnerConfigC), p, C.c_uint32, C.c_uint32, pp]
             f("runner_run_device").argtypes = [p, C.POINTER(RunnerConfigC), p, C.c_uint32, C.c_uint32, C.c_size_t, p]
             f("clusters_device_labels").argtypes = [p]

@@ -27,6 +27,11 @@ struct vcb_ctx {
     size_t d_stage_cap = 0;
     int opt_materialize = 0;          // VCB_OPT_MATERIALIZE_INDICES
     u32 last_counters[8] = {};
+    // host-to-host pipeline (vcb_runner_run_batch_host)
+    rt::Stream st_h2d, st_d2h;
+    bool pipe_ready = false;
+    u8 *d_in[2] = {nullptr, nullptr};
+    size_t d_in_cap = 0;
     // row-band mode: workspace arrays striped over the GPUs of the box (vmm.h)
     rt::VmmArray bw_flags, bw_pc, bw_la, bw_ls, bw_lr, bw_ev, bw_rgba;
     size_t bw_capN = 0;

@@ -73,6 +73,11 @@ inline void *dev_malloc_async(Stream &, size_t n) { return std::malloc(n ? n : 1
 inline void dev_free_async(Stream &, void *p) { std::free(p); }
 inline int stream_create(Stream &) { return 0; }
 inline void stream_destroy(Stream &) {}
+struct Event { int dummy = 0; };
+inline int event_create(Event &) { return 0; }
+inline void event_destroy(Event &) {}
+inline void event_record(Event &, Stream &) {}
+inline void stream_wait(Stream &, Event &) {}
 inline int stream_sync(Stream &) { return 0; }
 inline int copy_h2d(Stream &, void *d, const void *h, size_t n) { std::memcpy(d, h, n); return 0; }
 inline int copy_d2h(Stream &, void *h, const void *d, size_t n) { std::memcpy(h, d, n); return 0; }
@@ -118,6 +123,11 @@ inline int stream_create(Stream &st) {
     return (int)cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking);
 }
 inline void stream_destroy(Stream &st) { if (st.s) cudaStreamDestroy(st.s); st.s = nullptr; }
+struct Event { cudaEvent_t e = nullptr; };
+inline int event_create(Event &ev) { return (int)cudaEventCreateWithFlags(&ev.e, cudaEventDisableTiming); }
+inline void event_destroy(Event &ev) { if (ev.e) cudaEventDestroy(ev.e); ev.e = nullptr; }
+inline void event_record(Event &ev, Stream &st) { cudaEventRecord(ev.e, st.s); }
+inline void stream_wait(Stream &st, Event &ev) { cudaStreamWaitEvent(st.s, ev.e, 0); }
 inline int stream_sync(Stream &st) {
     cudaError_t e = cudaStreamSynchronize(st.s);
     if (e != cudaSuccess && !st.last_error) { st.last_error = (int)e; st.last_error_text = std::string("stream synchronize: ") + cudaGetErrorString(e); }

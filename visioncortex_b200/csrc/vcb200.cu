@@ -232,6 +232,8 @@ void vcb_ctx_destroy(vcb_ctx *c) {
     rt::dev_free(c->sv0); rt::dev_free(c->sv1); rt::dev_free(c->d_small); rt::dev_free(c->d_stage);
     rt::dev_free(c->s2_fw); rt::dev_free(c->s2_mnext); rt::dev_free(c->s2_mtail); rt::dev_free(c->s2_mark); rt::dev_free(c->s2_adj_off);
     rt::dev_free(c->s2_cursor); rt::dev_free(c->s2_adj); rt::dev_free(c->s2_over); rt::dev_free(c->s2_ist);
+    rt::dev_free(c->d_in[0]); rt::dev_free(c->d_in[1]);
+    if (c->pipe_ready) { rt::stream_destroy(c->st_h2d); rt::stream_destroy(c->st_d2h); }
     for (rt::VmmArray *a : {&c->bw_flags, &c->bw_pc, &c->bw_la, &c->bw_ls, &c->bw_lr, &c->bw_ev, &c->bw_rgba}) rt::vmm_free(*a);
     rt::host_free(c->h_pinned);
     rt::stream_destroy(c->st);
@@ -260,6 +262,87 @@ int vcb_runner_run(vcb_ctx *c, const vcb_runner_config *cfg, const uint8_t *rgba
     if (!d) return fail(c, VCB_ERR_NOMEM, "device out of memory (input)");
     rt::copy_h2d(c->st, d, rgba, bytes);
     return run_color_device(c, cfg, d, width, height, 1, out);
+}
+
+int vcb_runner_run_batch_host(vcb_ctx *c, const vcb_runner_config *cfg, const uint8_t *const *rgba, uint32_t width,
+                              uint32_t height, size_t n, vcb_host_result *results) {
+    if (!c) return VCB_ERR_INVALID_ARG;
+    if (!rgba || !results) return fail(c, VCB_ERR_INVALID_ARG, "null argument");
+    int e = validate_cfg(c, cfg);
+    if (e) return e;
+    const u64 npx = (u64)width * height;
+    if (npx == 0) return fail(c, VCB_ERR_INVALID_ARG, "empty image");
+    if (n == 0) return VCB_OK;
+    rt::set_device(c->device);
+    if (!c->pipe_ready) {
+        if (rt::stream_create(c->st_h2d) != 0 || rt::stream_create(c->st_d2h) != 0) return fail(c, VCB_ERR_CUDA, "stream creation failed");
+        c->pipe_ready = true;
+    }
+    // sub-batches: at least 4 per call so that the copies overlap the compute, at most MAX_CHUNK_PX pixels each
+    size_t per = (size_t)std::max<u64>(1, std::min<u64>((n + 3) / 4, MAX_CHUNK_PX / npx));
+    const size_t bytes_img = (size_t)npx * 4;
+    if (per * bytes_img > c->d_in_cap) {
+        rt::dev_free(c->d_in[0]); rt::dev_free(c->d_in[1]);
+        c->d_in[0] = (u8 *)rt::dev_malloc(per * bytes_img);
+        c->d_in[1] = (u8 *)rt::dev_malloc(per * bytes_img);
+        c->d_in_cap = (c->d_in[0] && c->d_in[1]) ? per * bytes_img : 0;
+        if (!c->d_in_cap) return fail(c, VCB_ERR_NOMEM, "device out of memory (input staging)");
+    }
+    const size_t nchunks = (n + per - 1) / per;
+    std::vector<rt::Event> ev_in(nchunks), ev_done(nchunks);
+    for (auto &x : ev_in) rt::event_create(x);
+    for (auto &x : ev_done) rt::event_create(x);
+    std::vector<std::shared_ptr<BatchResult>> keep(nchunks);
+    auto upload = [&](size_t k) {
+        const size_t i0 = k * per, cnt = std::min(per, n - i0);
+        for (size_t i = 0; i < cnt; ++i) rt::copy_h2d(c->st_h2d, c->d_in[k & 1] + i * bytes_img, rgba[i0 + i], bytes_img);
+        rt::event_record(ev_in[k], c->st_h2d);
+    };
+    int rc = VCB_OK;
+    upload(0);
+    for (size_t k = 0; k < nchunks && rc == VCB_OK; ++k) {
+        const size_t i0 = k * per, cnt = std::min(per, n - i0);
+        if (k + 1 < nchunks) upload(k + 1);                     // the other input buffer: its last reader (chunk k-1) is finished
+        rt::stream_wait(c->st, ev_in[k]);
+        e = run_color(c, cfg, c->d_in[k & 1], width, height, cnt, false, false, keep[k]);
+        if (e) { rc = e; break; }
+        rt::event_record(ev_done[k], c->st);
+        rt::stream_wait(c->st_d2h, ev_done[k]);
+        const BatchResult *br = keep[k].get();
+        // the last record of every image carries the list totals: one small read for the whole sub-batch
+        for (size_t i = 0; i < cnt; ++i) {
+            vcb_host_result &r = results[i0 + i];
+            const u32 s0 = br->slot_base[i], s1 = br->slot_base[i + 1];
+            r.info.width = width; r.info.height = height;
+            r.info.num_slots = s1 - s0; r.info.num_outputs = br->nout[i];
+            r.info.indices_total = 0; r.info.holes_total = 0;
+            r.status = VCB_OK;
+            if (r.cluster_indices) rt::copy_d2h(c->st_d2h, r.cluster_indices, br->labels + i * npx, (size_t)npx * 4);
+            if (r.records) {
+                if (r.records_cap < s1 - s0) r.status = VCB_ERR_NOMEM;
+                else rt::copy_d2h(c->st_d2h, r.records, br->rec + s0, (size_t)(s1 - s0) * sizeof(vcb_cluster_rec));
+            }
+            if (r.outputs) {
+                if (r.outputs_cap < br->nout[i]) r.status = VCB_ERR_NOMEM;
+                else if (br->nout[i]) rt::copy_d2h(c->st_d2h, r.outputs, br->outputs + s0, (size_t)br->nout[i] * 4);
+            }
+        }
+    }
+    if (rt::stream_sync(c->st_d2h) != 0 || rt::stream_sync(c->st_h2d) != 0) rc = rc ? rc : VCB_ERR_CUDA;
+    if (rc == VCB_OK) {
+        for (size_t i = 0; i < n; ++i) {
+            vcb_host_result &r = results[i];
+            if (r.records && r.status == VCB_OK && r.info.num_slots) {
+                const vcb_cluster_rec &l = r.records[r.info.num_slots - 1];
+                r.info.indices_total = l.indices_off + l.indices_len; r.info.holes_total = l.holes_off + l.holes_len;
+            }
+        }
+    }
+    for (auto &x : ev_in) rt::event_destroy(x);
+    for (auto &x : ev_done) rt::event_destroy(x);
+    keep.clear();
+    const int e2 = check_stream(c);
+    return rc ? rc : e2;
 }
 
 int vcb_runner_run_banded(vcb_ctx *const *ctxs, int nctx, const vcb_runner_config *cfg, const uint8_t *rgba, uint32_t width,

@@ -160,3 +160,37 @@ def runner_run_banded(contexts, rgba: np.ndarray, cfg: RunnerConfigC, pools: boo
     finally:
         lib.fn("clusters_free")(out)
     return res
+
+
+def runner_run_batch_host(ctx: Context, images, cfg: RunnerConfigC, records_cap: int | None = None, buffers=None) -> list:
+    """vcb_runner_run_batch_host: equally sized host images in, host result buffers out, with the copies of neighbouring
+    sub-batches overlapping the compute.  `buffers` may hold preallocated (ideally pinned) arrays: a list of
+    (labels u32[w*h], records CLUSTER_REC_DTYPE[cap], outputs u32[cap]) per image."""
+    from ._ffi import CLUSTER_REC_DTYPE, HostResultC
+
+    imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+    n = len(imgs)
+    h, w = imgs[0].shape[:2]
+    cap = records_cap if records_cap is not None else w * h + 1
+    if buffers is None:
+        buffers = [(np.empty(w * h, dtype=np.uint32), np.zeros(cap, dtype=CLUSTER_REC_DTYPE), np.empty(cap, dtype=np.uint32))
+                   for _ in range(n)]
+    ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+    res = (HostResultC * n)()
+    for k in range(n):
+        lab, rec, out = buffers[k]
+        res[k].cluster_indices = lab.ctypes.data
+        res[k].records = rec.ctypes.data
+        res[k].outputs = out.ctypes.data
+        res[k].records_cap = len(rec)
+        res[k].outputs_cap = len(out)
+    st = ctx.lib.fn("runner_run_batch_host")(ctx.handle, C.byref(cfg), ptrs, w, h, n, res)
+    ctx.lib.check(st, ctx.handle)
+    out_list = []
+    for k in range(n):
+        ctx.lib.check(res[k].status, ctx.handle)
+        lab, rec, out = buffers[k]
+        info = res[k].info
+        out_list.append({"width": info.width, "height": info.height, "num_slots": info.num_slots, "cluster_indices": lab,
+                         "records": rec[: info.num_slots], "clusters_output": out[: info.num_outputs]})
+    return out_list

@@ -295,3 +295,17 @@ def test_host_to_host_batch(gpu, oracle):
         for k, im in enumerate(imgs):
             ref = oracle.runner_run(im, cfg, pools=False)
             assert_same_clusters(got[k], ref, pools=False, ctx=f"host batch image {k}")
+
+
+def test_empty_and_ragged_inputs(gpu, oracle):
+    """Images without pixels mirror the reference (one ZERO slot, nothing else, builder.rs:189); a batch may mix sizes."""
+    for shape in [(0, 0, 4), (0, 7, 4), (5, 0, 4)]:
+        img = np.zeros(shape, dtype=np.uint8)
+        for hier in (0, HM):
+            cfg = make_config(hierarchical=hier)
+            assert_same_clusters(gpu.runner_run(img, cfg, pools=True), oracle.runner_run(img, cfg, pools=True), pools=True, ctx=str(shape))
+    imgs = [synth.g2_scene(w, h, seed=300 + k) for k, (w, h) in enumerate([(64, 48), (64, 48), (100, 30), (64, 48), (33, 77), (33, 77)])]
+    cfg = c2_config(64, 48)
+    got = gpu.runner_run_batch(imgs, cfg)
+    for k, im in enumerate(imgs):
+        assert_same_clusters(got[k], oracle.runner_run(im, cfg, pools=False), pools=False, ctx=f"ragged batch image {k}")

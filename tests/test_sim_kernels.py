@@ -68,3 +68,28 @@ def test_sim_unclean_key_is_fenced(sim):
     with pytest.raises(VcbError) as e:
         sim.runner_run(img, cfg, pools=False)
     assert e.value.status == 3
+
+
+def test_sim_empty_colour_image(sim, oracle):
+    from visioncortex_b200.runtime import make_config
+
+    for shape in [(0, 0, 4), (0, 5, 4)]:
+        img = np.zeros(shape, dtype=np.uint8)
+        cfg = make_config(hierarchical=0)
+        assert_same_clusters(sim.runner_run(img, cfg, pools=True), oracle.runner_run(img, cfg, pools=True), pools=True)
+
+
+def test_sim_hierarchical_and_banded(sim, oracle):
+    """stage 2 (exact pop order) and the row-band driver (device set emulated on one simulated device)."""
+    from sim_lib import load_sim  # noqa: F401
+    from visioncortex_b200.runtime import Context, make_config, runner_run_banded
+
+    rng = np.random.default_rng(33)
+    ctxs = [sim, Context(0, lib=sim.lib)]
+    for k in range(4):
+        img, cfg = random_case(rng, max_side=26, keyed=(k == 2), hierarchical=[0xFFFFFFFF, 64][k % 2])
+        ref = oracle.runner_run(img, cfg, pools=True, color_image=True)
+        got = sim.runner_run(img, cfg, pools=True, color_image=True)
+        assert_same_clusters(got, ref, pools=True, ctx=f"hier {k}")
+        got2 = runner_run_banded(ctxs, img, cfg, pools=False)
+        assert_same_clusters(got2, ref, pools=False, ctx=f"banded {k}")

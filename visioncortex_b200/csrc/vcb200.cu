@@ -65,10 +65,30 @@ int fetch_last_record(vcb_clusters *h) {
 }
 
 // colour path on device-resident images
+// An image without pixels: the reference builds `clusters = [Cluster::new()]` (builder.rs:189), labels and outputs empty.
+int run_color_empty(vcb_ctx *c, const vcb_runner_config *cfg, u32 w, u32 h, size_t nimg, std::shared_ptr<BatchResult> &out_br) {
+    rt::set_device(c->device);
+    auto br = std::make_shared<BatchResult>();
+    br->ctx = c; br->cfg = *cfg;
+    br->d = Dims{w, h, 0u, (u32)nimg, 0u};
+    br->total_slots = (u32)nimg;
+    br->rec = (vcb_cluster_rec *)rt::dev_malloc_async(c->st, nimg * sizeof(vcb_cluster_rec));
+    if (!br->rec) return fail(c, VCB_ERR_NOMEM, "device out of memory");
+    rt::fill(c->st, br->rec, 0, nimg * sizeof(vcb_cluster_rec));
+    br->slot_base.resize(nimg + 1);
+    for (size_t i = 0; i <= nimg; ++i) br->slot_base[i] = (u32)i;
+    br->nout.assign(nimg, 0);
+    br->pool_base.assign(nimg + 1, 0);
+    br->hpool_base.assign(nimg + 1, 0);
+    out_br = br;
+    return check_stream(c);
+}
+
 int run_color(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w, u32 h, size_t nimg, bool want_pool,
               bool retain, std::shared_ptr<BatchResult> &out_br, const DevSet *ds = nullptr) {
     int e = validate_cfg(c, cfg);
     if (e) return e;
+    if ((u64)w * h == 0) return run_color_empty(c, cfg, w, h, nimg, out_br);
     const u64 n64 = (u64)w * h;
     if (n64 == 0 || n64 * nimg >= 0x7fffff00ull) return fail(c, VCB_ERR_INVALID_ARG, "width*height*n must be in 1..2^31");
     if (!d_rgba) return fail(c, VCB_ERR_INVALID_ARG, "null image");
@@ -133,8 +153,7 @@ int run_color_device(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba,
     if (!out) return fail(c, VCB_ERR_INVALID_ARG, "null output");
     if (nimg == 0) return VCB_OK;
     const u64 n64 = (u64)w * h;
-    if (n64 == 0) return fail(c, VCB_ERR_INVALID_ARG, "empty image");
-    size_t per_chunk = (size_t)(MAX_CHUNK_PX / n64);
+    size_t per_chunk = n64 ? (size_t)(MAX_CHUNK_PX / n64) : nimg;
     if (per_chunk < 1) per_chunk = 1;
     for (size_t i0 = 0; i0 < nimg; i0 += per_chunk) {
         const size_t cnt = nimg - i0 < per_chunk ? nimg - i0 : per_chunk;
@@ -156,7 +175,7 @@ int run_color_device(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba,
 
 // first request for Cluster.indices on a result computed without them: recompute from the retained image
 int ensure_pool(BatchResult *br) {
-    if (br->pool) return VCB_OK;
+    if (br->pool || br->d.n == 0) return VCB_OK;
     vcb_ctx *c = br->ctx;
     if (!br->pixels) return fail(c, VCB_ERR_INVALID_ARG, "result holds no image to rebuild the indices from");
     std::shared_ptr<BatchResult> tmp;
@@ -256,7 +275,8 @@ int vcb_runner_run(vcb_ctx *c, const vcb_runner_config *cfg, const uint8_t *rgba
     int e = validate_cfg(c, cfg);
     if (e) return e;
     const size_t bytes = (size_t)width * height * 4;
-    if (bytes == 0 || !rgba) return fail(c, VCB_ERR_INVALID_ARG, "empty image");
+    if (bytes == 0) return run_color_device(c, cfg, nullptr, width, height, 1, out);
+    if (!rgba) return fail(c, VCB_ERR_INVALID_ARG, "null image");
     rt::set_device(c->device);
     u8 *d = stage_input(c, bytes);
     if (!d) return fail(c, VCB_ERR_NOMEM, "device out of memory (input)");
@@ -466,6 +486,7 @@ int vcb_clusters_info_get(const vcb_clusters *hc, vcb_clusters_info *info) {
 int vcb_clusters_cluster_indices(const vcb_clusters *h, uint32_t *out) {
     if (!h || !out) return VCB_ERR_INVALID_ARG;
     const BatchResult *br = h->br.get();
+    if (br->d.n == 0) return VCB_OK;
     rt::copy_d2h(br->ctx->st, out, br->labels + (size_t)h->img * br->d.n, (size_t)br->d.n * 4);
     return check_stream(br->ctx);
 }
@@ -501,7 +522,9 @@ int vcb_clusters_indices_pool(const vcb_clusters *h, uint32_t *out) {
 }
 
 int vcb_clusters_take_image(const vcb_clusters *h, uint8_t *rgba_out) {
-    if (!h || !rgba_out) return VCB_ERR_INVALID_ARG;
+    if (!h) return VCB_ERR_INVALID_ARG;
+    if (h->br->d.n == 0) return VCB_OK;
+    if (!rgba_out) return VCB_ERR_INVALID_ARG;
     const BatchResult *br = h->br.get();
     if (!br->pixels) return fail(br->ctx, VCB_ERR_INVALID_ARG, "result holds no image");
     rt::copy_d2h(br->ctx->st, rgba_out, br->pixels + (size_t)h->img * br->d.n * 4, (size_t)br->d.n * 4);
@@ -533,6 +556,7 @@ int vcb_clusters_to_color_image(const vcb_clusters *h, uint8_t *rgba_out) {
     vcb_ctx *c = br->ctx;
     rt::set_device(c->device);
     const u32 n = br->d.n;
+    if (n == 0) return VCB_OK;
     u8 *d = stage_input(c, (size_t)n * 4);
     if (!d) return fail(c, VCB_ERR_NOMEM, "device out of memory");
     if (br->hier) {

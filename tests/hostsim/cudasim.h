@@ -52,13 +52,14 @@ struct ThreadCtx {
     dim3 tid, bid, bdim, gdim;
     BlockState *blk = nullptr;
     std::barrier<> *grid_bar = nullptr;
+    std::barrier<> *cluster_bar = nullptr;
     int lane = 0, warp = 0, warp_size = 32;
 };
 inline thread_local ThreadCtx tc;
 
 // Run `fn` for every thread of every block.  mode 0: sequential (no collectives allowed), 1: threaded per block,
 // 2: cooperative (all blocks concurrently, grid sync allowed).
-inline void launch(dim3 grid, dim3 block, size_t smem, int mode, const std::function<void()> &fn) {
+inline void launch(dim3 grid, dim3 block, size_t smem, int mode, const std::function<void()> &fn, unsigned cluster = 1) {
     const unsigned nthreads = block.x * block.y * block.z;
     const unsigned nblocks = grid.x * grid.y * grid.z;
     if (nblocks == 0 || nthreads == 0) return;
@@ -97,10 +98,13 @@ inline void launch(dim3 grid, dim3 block, size_t smem, int mode, const std::func
     std::vector<BlockState> bss(nblocks);
     for (auto &bs : bss) make_block(bs);
     std::barrier<> gbar(nthreads * nblocks);
+    // thread-block clusters: consecutive groups of `cluster` blocks share a hardware barrier
+    std::vector<std::unique_ptr<std::barrier<>>> cbars;
+    for (unsigned c = 0; c * cluster < nblocks; ++c) cbars.emplace_back(new std::barrier<>(nthreads * cluster));
     std::vector<std::thread> th;
     for (unsigned b = 0; b < nblocks; ++b)
         for (unsigned t = 0; t < nthreads; ++t)
-            th.emplace_back([&, b, t] { setup(tc, b, t); tc.blk = &bss[b]; tc.grid_bar = &gbar; fn(); });
+            th.emplace_back([&, b, t] { setup(tc, b, t); tc.blk = &bss[b]; tc.grid_bar = &gbar; tc.cluster_bar = cbars[b / cluster].get(); fn(); });
     for (auto &x : th) x.join();
 }
 inline void *smem_ptr() {

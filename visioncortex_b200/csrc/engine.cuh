@@ -427,6 +427,11 @@ inline int run_stage2(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg, b
     a.cfg.deepen_diff = cfg->deepen_diff; a.cfg.hollow_neighbours = cfg->hollow_neighbours;
     a.cfg.can_discard = (cfg->keying_action == VCB_KEYING_DISCARD && has_key) ? 1 : 0;
     a.cfg.hier_max = cfg->hierarchical == VCB_HIERARCHICAL_MAX;
+#ifdef VCB_HOSTSIM
+    a.cfg.help_min_px = 12;
+#else
+    a.cfg.help_min_px = std::getenv("VCB_S2_HELP_MIN") ? (u64)std::atoll(std::getenv("VCB_S2_HELP_MIN")) : 8192;
+#endif
     a.l1 = res->labels1; a.rec = res->rec; a.slot_base = res->d_slot_base; a.slot_img = res->d_slot_img; a.total_slots = total;
     a.childoff = res->childoff; a.holeoff = res->holeoff;
     a.fw = c->s2_fw; a.mpar = res->mpar; a.mnext = c->s2_mnext; a.mtail = c->s2_mtail; a.mark = c->s2_mark; a.outpos = res->outpos;
@@ -451,15 +456,22 @@ inline int run_stage2(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg, b
         rt::launch(st, "k_s2_collect", rt::THR, k_s2_collect, dim3(gs), dim3(256), 0, a, ep);
         const int nbits = a.idx_bits + ep + (d.nimg > 1 ? img_bits : 0);      // within an epoch only `ep` bits of the area vary
         const bool flipped = prims::radix_sort(st, c->sk0, c->sv0, c->sk1, c->sv1, d_count, total, nbits, c->rs_table, c->chunksum, c->sms * 8);
-        // few images: one fat CTA each (perimeter / neighbour scans are block-parallel); many images: more CTAs per SM
-        const int s2_threads =
+        // few images: a thread-block cluster of fat CTAs per image (the leader replays the merges, the others help with the
+        // large perimeter scans); many images: one CTA per image, more CTAs per SM
 #ifdef VCB_HOSTSIM
-            64;
+        const int s2_threads = 64;
+        const u32 G = d.nimg == 1 ? 2u : 1u;
 #else
-            d.nimg * 8 <= (u32)c->sms ? 1024 : d.nimg * 2 <= (u32)c->sms ? 512 : d.nimg <= (u32)c->sms ? 256 : 128;
+        const int s2_threads = d.nimg * 8 <= (u32)c->sms ? 1024 : d.nimg * 2 <= (u32)c->sms ? 512 : d.nimg <= (u32)c->sms ? 256 : 128;
+        u32 G = 1;
+        while (G < 8 && d.nimg * (G * 2) * 2 <= (u32)c->sms) G *= 2;
 #endif
-        rt::launch(st, "k_s2_epoch", rt::THR, k_s2_epoch, dim3(d.nimg), dim3(s2_threads), sizeof(S2Shared) + 16, a,
-                   (const u64 *)(flipped ? c->sk1 : c->sk0), ep);
+        if (G > 1)
+            rt::launch_cluster(st, "k_s2_epoch", k_s2_epoch, dim3(d.nimg * G), dim3(s2_threads), sizeof(S2Shared) + 16, G, a,
+                               (const u64 *)(flipped ? c->sk1 : c->sk0), ep, G);
+        else
+            rt::launch(st, "k_s2_epoch", rt::THR, k_s2_epoch, dim3(d.nimg), dim3(s2_threads), sizeof(S2Shared) + 16, a,
+                       (const u64 *)(flipped ? c->sk1 : c->sk0), ep, G);
     }
     rt::launch(st, "k_s2_labels", rt::SEQ, k_s2_labels, dim3(gp), dim3(256), 0, a, res->labels);
     // offsets of the per-slot lists after the merges

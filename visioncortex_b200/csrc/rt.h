@@ -25,6 +25,7 @@ typedef struct SimStream *cudaStream_t;
 #define cudaSuccess 0
 #define VCB_SMEM(T, name) T *name = (T *)sim::smem_ptr()
 #define VCB_GRID_SYNC() sim::tc.grid_bar->arrive_and_wait()
+#define VCB_CLUSTER_SYNC() sim::tc.cluster_bar->arrive_and_wait()
 template <class T> __device__ static inline T ldcg(const T *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
 template <class T> __device__ static inline void stcg(T *p, T v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
 __device__ static inline u8 ldcg8(const u8 *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
@@ -36,6 +37,7 @@ __device__ static inline u8 ldcg8(const u8 *p) { return __atomic_load_n(p, __ATO
     extern __shared__ __align__(128) unsigned char _vcb_smem[]; \
     T *name = reinterpret_cast<T *>(_vcb_smem)
 #define VCB_GRID_SYNC() cooperative_groups::this_grid().sync()
+#define VCB_CLUSTER_SYNC() cooperative_groups::this_cluster().sync()
 template <class T> __device__ static __forceinline__ T ldcg(const T *p) { return __ldcg(p); }
 template <class T> __device__ static __forceinline__ void stcg(T *p, T v) { __stcg(p, v); }
 __device__ static __forceinline__ u8 ldcg8(const u8 *p) { return __ldcg(p); }
@@ -95,6 +97,15 @@ inline void launch(Stream &st, const char *name, LaunchMode mode, void (*k)(KArg
     static const bool force_thr = std::getenv("VCB_SIM_FORCE_THR") != nullptr;   // exercise real races in the simulator
     if (force_thr && mode == SEQ) mode = THR;
     sim::launch(grid, block, smem, (int)mode, [&] { std::apply(k, t); });
+}
+// thread-block cluster launch: `cluster` consecutive CTAs form a cluster (grid.x must be a multiple of it)
+template <class... KArgs, class... Args>
+inline void launch_cluster(Stream &st, const char *name, void (*k)(KArgs...), dim3 grid, dim3 block, size_t smem, unsigned cluster,
+                           Args... args) {
+    (void)name;
+    st.launches++;
+    std::tuple<KArgs...> t(args...);
+    sim::launch(grid, block, smem, 2, [&] { std::apply(k, t); }, cluster);
 }
 #else
 inline int device_count() { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
@@ -174,6 +185,24 @@ inline void launch(Stream &st, const char *name, LaunchMode mode, void (*k)(KArg
             std::fprintf(stderr, "[vcb] kernel %s failed: %s\n", name, cudaGetErrorString(e));
         }
     }
+}
+// thread-block cluster launch: `cluster` consecutive CTAs form a cluster (grid.x must be a multiple of it)
+template <class... KArgs, class... Args>
+inline void launch_cluster(Stream &st, const char *name, void (*k)(KArgs...), dim3 grid, dim3 block, size_t smem, unsigned cluster,
+                           Args... args) {
+    st.launches++;
+    ProfEntry pe{name, nullptr, nullptr};
+    if (st.profiling) { cudaEventCreate(&pe.e0); cudaEventCreate(&pe.e1); cudaEventRecord(pe.e0, st.s); }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st.s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cluster > 8) cudaFuncSetAttribute((const void *)k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k, KArgs(args)...);
+    if (e != cudaSuccess && !st.last_error) { st.last_error = (int)e; st.last_error_text = std::string(name) + ": " + cudaGetErrorString(e); }
+    if (st.profiling) { cudaEventRecord(pe.e1, st.s); st.prof.push_back(pe); }
 }
 #endif
 

@@ -18,11 +18,13 @@ namespace vcb {
 
 struct S2Cfg {
     u32 hierarchical; u64 good_min, good_max; i32 deepen_diff; u64 hollow_neighbours; int can_discard; int hier_max;
+    u64 help_min_px;   // rects at least this large are counted by the whole thread-block cluster
 };
 
 struct S2ImgState {
     u32 stamp, nout, maxarea, nover;
-    u32 nmerge, pad[3];
+    u32 nmerge, task_c, task_quit, perim_acc;
+    i32 task_rect[4];
 };
 
 struct S2 {
@@ -179,11 +181,78 @@ struct S2Shared {
     u8 map[S2_MAPBYTES];
 };
 
-__global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_epoch(S2 a, const u64 *keys, int epoch) {
+// Perimeter of cluster c restricted to rect rows [row_lo, row_hi) (rect-relative), shape/geometry.rs:52-75 on
+// Cluster::to_image_with_hole: pixels of c (holes removed) with a 4-neighbour outside c.  Block-parallel; the membership
+// of the rows (+1 halo) is staged band by band into a shared byte map; pixels outside the rect are outside the cluster by
+// definition (the rect bounds it), pixels outside the image likewise.  Adds the block's count to sh->perim.
+__device__ static __forceinline__ void s2_perimeter_rows(const S2 &a, S2Shared *sh, u32 img, u32 base, u32 c, const i32 *rect,
+                                                         u32 row_lo, u32 row_hi) {
+    const Dims d = a.d;
+    const u32 tid = threadIdx.x, S2_THREADS = blockDim.x;
+    const i32 L = rect[0], T = rect[1], R = rect[2], B = rect[3];
+    const u32 rw = (u32)(R - L);
+    const u32 *l1 = a.l1 + (size_t)img * d.n;
+    u32 cntp = 0;
+    const u32 pw = rw + 2;
+    u32 band = S2_MAPBYTES / pw;
+    if (band < 3) band = 3;
+    const u32 inner = band - 2;                                   // rows counted per band
+    for (u32 r0 = row_lo; r0 < row_hi; r0 += inner) {
+        const u32 rows = (row_hi - r0 < inner) ? row_hi - r0 : inner;
+        const u32 cells = (rows + 2) * pw;
+        if (cells > S2_MAPBYTES) {                                // rect wider than the map: direct (slow) evaluation
+            for (u64 q = tid; q < (u64)rw * rows; q += S2_THREADS) {
+                const u32 x = (u32)L + (u32)(q % rw), y = (u32)T + r0 + (u32)(q / rw);
+                u32 fl;
+                if (s2_find(a.fw, base, l1[y * d.w + x], &fl) != c || fl) continue;
+                bool edge = (x == 0) || (y == 0) || (x + 1 == d.w) || (y + 1 == d.h);
+                if (!edge) {
+                    const i32 off[4] = {-1, 1, -(i32)d.w, (i32)d.w};
+#pragma unroll
+                    for (int k2 = 0; k2 < 4; ++k2) {
+                        u32 f2;
+                        if (s2_find(a.fw, base, l1[(i32)(y * d.w + x) + off[k2]], &f2) != c || f2) { edge = true; break; }
+                    }
+                }
+                if (edge) cntp++;
+            }
+            continue;
+        }
+        __syncthreads();
+        for (u32 q0 = tid; q0 < cells; q0 += 4 * S2_THREADS) {
+            // four independent cells per step: the label loads, then the forwarding loads, are all in flight together
+            u32 lab[4]; bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const u32 q = q0 + u * S2_THREADS;
+                const i32 mx = (i32)(q % pw) - 1, my = (i32)(q / pw) - 1;    // rect-relative
+                const i32 x = L + mx, y = T + (i32)r0 + my;
+                ok[u] = q < cells && mx >= 0 && mx < (i32)rw && y >= T && y < B;
+                lab[u] = ok[u] ? __ldg(&l1[(u32)y * d.w + (u32)x]) : 0u;
+            }
+            u32 fwv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) fwv[u] = ok[u] ? ldcg(&a.fw[base + lab[u]]) : 0xffffffffu;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const u32 q = q0 + u * S2_THREADS;
+                if (q < cells) sh->map[q] = (ok[u] && fwv[u] == c) ? 1 : 0;   // == c: root is c and the hollow flag is clear
+            }
+        }
+        __syncthreads();
+        for (u32 q = tid; q < rw * rows; q += S2_THREADS) {
+            const u32 mx = q % rw + 1, my = q / rw + 1;
+            const u32 idx = my * pw + mx;
+            if (sh->map[idx] && !(sh->map[idx - 1] && sh->map[idx + 1] && sh->map[idx - pw] && sh->map[idx + pw])) cntp++;
+        }
+    }
+    if (cntp) atomicAdd(&sh->perim, cntp);
+}
+
+__global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_epoch(S2 a, const u64 *keys, int epoch, u32 G) {
     const u32 S2_THREADS = blockDim.x;
     VCB_SMEM(S2Shared, sh);
-    const Dims d = a.d;
-    const u32 img = blockIdx.x, base = a.slot_base[img];
+    const u32 img = blockIdx.x / G, crank = blockIdx.x % G, base = a.slot_base[img];   // G CTAs (one cluster) per image
     const u32 nslots = a.slot_base[img + 1] - base;
     const u32 tid = threadIdx.x;
     S2ImgState *ist = a.ist + img;
@@ -191,6 +260,26 @@ __global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_epoch(S2 a, const u64 *ke
     const u64 idx_mask = (1ull << a.idx_bits) - 1ull;
     const u32 area_base = 1u << epoch;
     u64 *over = a.over + base;
+
+    if (crank != 0) {
+        // helper CTA of the image's cluster: sleeps in the cluster barrier; woken for a perimeter task or to quit
+        while (true) {
+            VCB_CLUSTER_SYNC();
+            if (ldcg(&ist->task_quit)) break;
+            if (tid == 0) sh->perim = 0;
+            i32 rect[4];
+            for (int k2 = 0; k2 < 4; ++k2) rect[k2] = ldcg(&ist->task_rect[k2]);
+            const u32 tc = ldcg(&ist->task_c);
+            __syncthreads();
+            const u32 rh = (u32)(rect[3] - rect[1]);
+            s2_perimeter_rows(a, sh, img, base, tc, rect, (u32)((u64)rh * crank / G), (u32)((u64)rh * (crank + 1) / G));
+            __syncthreads();
+            if (tid == 0) { if (sh->perim) atomicAdd(&ist->perim_acc, sh->perim); __threadfence(); }
+            __syncthreads();
+            VCB_CLUSTER_SYNC();
+        }
+        return;
+    }
 
     if (tid == 0) {
         const u32 cnt = *a.count;
@@ -316,69 +405,25 @@ __global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_epoch(S2 a, const u64 *ke
         const u32 target = sh->target;
         bool deepen = sh->deepen != 0;
         if (sh->want_perim) {
-            // perimeter (shape/geometry.rs:52-75 on Cluster::to_image_with_hole): pixels of c (holes removed) with a
-            // 4-neighbour outside c
-            const i32 L = sh->rect[0], T = sh->rect[1], R = sh->rect[2], B = sh->rect[3];
-            const u32 rw = (u32)(R - L), rh = (u32)(B - T);
-            const u32 *l1 = a.l1 + (size_t)img * d.n;
-            u32 cntp = 0;
-            // membership of the rect (+1 halo) is staged band by band into a shared byte map; pixels outside the rect
-            // are outside the cluster by definition (the rect bounds it), pixels outside the image likewise
-            const u32 pw = rw + 2;
-            u32 band = S2_MAPBYTES / pw;
-            if (band < 3) band = 3;
-            const u32 inner = band - 2;                               // rows counted per band
-            for (u32 r0 = 0; r0 < rh; r0 += inner) {
-                const u32 rows = (rh - r0 < inner) ? rh - r0 : inner;
-                const u32 cells = (rows + 2) * pw;
-                if (cells > S2_MAPBYTES) {                            // rect wider than the map: direct (slow) evaluation
-                    for (u64 q = tid; q < (u64)rw * rows; q += S2_THREADS) {
-                        const u32 x = (u32)L + (u32)(q % rw), y = (u32)T + r0 + (u32)(q / rw);
-                        u32 fl;
-                        if (s2_find(a.fw, base, l1[y * d.w + x], &fl) != c || fl) continue;
-                        bool edge = (x == 0) || (y == 0) || (x + 1 == d.w) || (y + 1 == d.h);
-                        if (!edge) {
-                            const i32 off[4] = {-1, 1, -(i32)d.w, (i32)d.w};
-#pragma unroll
-                            for (int k2 = 0; k2 < 4; ++k2) {
-                                u32 f2;
-                                if (s2_find(a.fw, base, l1[(i32)(y * d.w + x) + off[k2]], &f2) != c || f2) { edge = true; break; }
-                            }
-                        }
-                        if (edge) cntp++;
-                    }
-                    continue;
+            const u32 rh = (u32)(sh->rect[3] - sh->rect[1]), rwid = (u32)(sh->rect[2] - sh->rect[0]);
+            if (G > 1 && (u64)rh * rwid >= a.cfg.help_min_px) {
+                // large rect: the other CTAs of the cluster take row slices.  They sleep in the cluster barrier until now.
+                if (tid == 0) {
+                    stcg(&ist->task_c, c); stcg(&ist->task_quit, 0u);
+                    for (int k2 = 0; k2 < 4; ++k2) stcg(&ist->task_rect[k2], sh->rect[k2]);
+                    __threadfence();
                 }
                 __syncthreads();
-                for (u32 q0 = tid; q0 < cells; q0 += 4 * S2_THREADS) {
-                    // four independent cells per step: the label loads, then the forwarding loads, are all in flight together
-                    u32 lab[4]; bool ok[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const u32 q = q0 + u * S2_THREADS;
-                        const i32 mx = (i32)(q % pw) - 1, my = (i32)(q / pw) - 1;    // rect-relative
-                        const i32 x = L + mx, y = T + (i32)r0 + my;
-                        ok[u] = q < cells && mx >= 0 && mx < (i32)rw && y >= T && y < B;
-                        lab[u] = ok[u] ? __ldg(&l1[(u32)y * d.w + (u32)x]) : 0u;
-                    }
-                    u32 fwv[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) fwv[u] = ok[u] ? ldcg(&a.fw[base + lab[u]]) : 0xffffffffu;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const u32 q = q0 + u * S2_THREADS;
-                        if (q < cells) sh->map[q] = (ok[u] && fwv[u] == c) ? 1 : 0;   // == c: root is c and the hollow flag is clear
-                    }
-                }
+                VCB_CLUSTER_SYNC();                                   // task published (relabel stores of earlier pops included)
+                s2_perimeter_rows(a, sh, img, base, c, sh->rect, 0, rh / G);
                 __syncthreads();
-                for (u32 q = tid; q < rw * rows; q += S2_THREADS) {
-                    const u32 mx = q % rw + 1, my = q / rw + 1;
-                    const u32 idx = my * pw + mx;
-                    if (sh->map[idx] && !(sh->map[idx - 1] && sh->map[idx + 1] && sh->map[idx - pw] && sh->map[idx + pw])) cntp++;
-                }
+                VCB_CLUSTER_SYNC();                                   // all slices counted into ist->perim_acc
+                if (tid == 0) { sh->perim += ldcg(&ist->perim_acc); stcg(&ist->perim_acc, 0u); }
+                __syncthreads();
+            } else {
+                s2_perimeter_rows(a, sh, img, base, c, sh->rect, 0, rh);
+                __syncthreads();
             }
-            if (cntp) atomicAdd(&sh->perim, cntp);
-            __syncthreads();
             deepen = (u64)sh->perim < (u64)area;
         }
         const bool hollow = (u64)ndist <= a.cfg.hollow_neighbours;
@@ -457,6 +502,11 @@ __global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_epoch(S2 a, const u64 *ke
         __syncthreads();
     }
     (void)nslots;
+    if (G > 1) {                                                      // release the helper CTAs
+        if (tid == 0) { stcg(&ist->task_quit, 1u); __threadfence(); }
+        __syncthreads();
+        VCB_CLUSTER_SYNC();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------- finalisation

@@ -335,8 +335,7 @@ inline int build_records(vcb_ctx *c, const Dims &d, const std::vector<ImgMeta> &
     rt::launch(st, "k_rec_accum", rt::SEQ, k_rec_accum, dim3(grid_for(c, d.N / 4, REC_THREADS, 16)), dim3(REC_THREADS), 0, d, b, res->rec, res->d_slot_base);
     if (keep_key)
         rt::launch(st, "k_rec_key", rt::SEQ, k_rec_key, dim3((d.nimg + 127) / 128), dim3(128), 0, d, b, res->rec, res->d_slot_base);
-    rt::launch(st, "k_rec_final", rt::SEQ, k_rec_final, dim3(g), dim3(REC_THREADS), 0, res->rec, total);
-    prims::scan(st, "scan_off", OffScan{res->rec, res->d_slot_base, res->d_slot_img, total, nullptr}, c->chunksum, total, c->sms * 8);
+    prims::scan(st, "scan_off", OffScanFinal{res->rec, total}, c->chunksum, total, c->sms * 8);
     rt::launch(st, "k_off_rebase", rt::SEQ, k_off_rebase, dim3(g), dim3(REC_THREADS), 0, res->rec, res->d_slot_base, res->d_slot_img, total);
     rt::launch(st, "k_off_rebase0", rt::SEQ, k_off_rebase0, dim3((d.nimg + 127) / 128), dim3(128), 0, res->rec, res->d_slot_base, d.nimg);
 
@@ -464,7 +463,8 @@ inline int run_stage2(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg, b
 #else
         const int s2_threads = d.nimg * 8 <= (u32)c->sms ? 1024 : d.nimg * 2 <= (u32)c->sms ? 512 : d.nimg <= (u32)c->sms ? 256 : 128;
         u32 G = 1;
-        while (G < 8 && d.nimg * (G * 2) * 2 <= (u32)c->sms) G *= 2;
+        static const u32 maxg = std::getenv("VCB_S2_MAXG") ? (u32)std::atoi(std::getenv("VCB_S2_MAXG")) : 8u;
+        while (G < maxg && d.nimg * (G * 2) * 2 <= (u32)c->sms) G *= 2;
 #endif
         if (G > 1)
             rt::launch_cluster(st, "k_s2_epoch", k_s2_epoch, dim3(d.nimg * G), dim3(s2_threads), sizeof(S2Shared) + 16, G, a,

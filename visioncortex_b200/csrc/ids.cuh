@@ -604,9 +604,16 @@ __global__ void __launch_bounds__(K5_THREADS) k_attribute(Dims d, P pol, Bufs b,
         u32 run_node = NONE, run_cnt = 0;
         LeafRun lr; lr.leaf = NONE; lr.n = 0; lr.s[0] = lr.s[1] = lr.s[2] = lr.s[3] = 0; lr.miny = 0; lr.maxy = 0;
         u32 ks[4] = {0, 0, 0, 0}, kn = 0; i32 kminy = 0x7fffffff, kmaxy = -1;
+        // the loads of row y + 1 are issued before row y is processed (the per-row warp votes would otherwise serialise them)
+        u32 nf = J_NONE, npc = NONE, npix = 0;
+        if (valid && y0 < y1) {
+            const u32 p0 = img * d.n + y0 * d.w + x;
+            nf = b.flags[p0]; npc = b.pc[p0]; npix = pol.load(p0);
+        }
         for (u32 y = y0; y < y1; ++y) {
             const u32 p = img * d.n + y * d.w + (valid ? x : 0);
-            const u32 f = valid ? b.flags[p] : (u32)J_NONE;
+            const u32 f = nf, pc_p = npc, pix_p = npix;
+            if (valid && y + 1 < y1) { nf = b.flags[p + d.w]; npc = b.pc[p + d.w]; npix = pol.load(p + d.w); }
             const u32 j = f & J_MASK;
             u32 g = NONE, gpar = NONE;
             const u32 gl_n = __shfl_up_sync(0xffffffffu, gprev, 1), gl_p = __shfl_up_sync(0xffffffffu, gprev_par, 1);     // (x-1, y-1)
@@ -637,7 +644,7 @@ __global__ void __launch_bounds__(K5_THREADS) k_attribute(Dims d, P pol, Bufs b,
                     if (j == J_UP && upnode != NONE) { g = upnode; gpar = uppar; }
                     else if (j == J_UPLEFT && lane > 0 && gl_n != NONE) { g = gl_n; gpar = gl_p; }
                     else if (j == J_RUP && lane < 31 && gr_n != NONE) { g = gr_n; gpar = gr_p; }
-                    else { g = b.pc[p] | TAG; gpar = node_par_ro(b, g); }   // fresh start from the leaf
+                    else { g = pc_p | TAG; gpar = node_par_ro(b, g); }      // fresh start from the leaf
                     climb2(b, g, gpar, p);
                 }
             }
@@ -650,7 +657,7 @@ __global__ void __launch_bounds__(K5_THREADS) k_attribute(Dims d, P pol, Bufs b,
             if (valid) {
                 if (j == J_NONE) {
                     if (keep_key) {                                  // colour path: J_NONE = keyed pixel (builder.rs:330-334)
-                        u32 s[4]; pol.stats(pol.load(p), s);
+                        u32 s[4]; pol.stats(pix_p, s);
                         ks[0] += s[0]; ks[1] += s[1]; ks[2] += s[2]; ks[3] += s[3]; kn++;
                         if ((i32)y < kminy) kminy = (i32)y;
                         kmaxy = (i32)y;
@@ -663,9 +670,9 @@ __global__ void __launch_bounds__(K5_THREADS) k_attribute(Dims d, P pol, Bufs b,
                             if (run_cnt) atomicAdd((run_node & TAG) ? &b.la[run_node & ~TAG].cnt : &b.ev[run_node].cnt, run_cnt);
                             run_node = g; run_cnt = 1;
                         }
-                        const u32 leaf = b.pc[p];
+                        const u32 leaf = pc_p;
                         if (leaf != lr.leaf) { lr.flush(b, (i32)x); lr.leaf = leaf; lr.miny = (i32)y; lr.s[0] = lr.s[1] = lr.s[2] = lr.s[3] = 0; }
-                        u32 s[4]; pol.stats(pol.load(p), s);
+                        u32 s[4]; pol.stats(pix_p, s);
                         lr.s[0] += s[0]; lr.s[1] += s[1]; lr.s[2] += s[2]; lr.s[3] += s[3]; lr.n++; lr.maxy = (i32)y;
                     }
                 }

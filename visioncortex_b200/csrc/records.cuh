@@ -65,6 +65,22 @@ __global__ void __launch_bounds__(REC_THREADS) k_rec_final(vcb_cluster_rec *rec,
     }
 }
 
+// stage-1 finalisation fused into the offset scan: half-open rect, residue_sum = sum (prepare_stage_2, builder.rs:380-382),
+// indices_len = area, indices_off = exclusive scan (rebased per image afterwards)
+struct OffScanFinal {
+    vcb_cluster_rec *rec; u32 total;
+    __device__ u32 count() const { return total; }
+    __device__ u32 value(u32 s) const { return rec[s].sum[4]; }
+    __device__ void emit(u32 s, u32 ex, u32 v) const {
+        vcb_cluster_rec *r = rec + s;
+        if (v == 0) { r->rect[0] = r->rect[1] = r->rect[2] = r->rect[3] = 0; }
+        else { r->rect[2] += 1; r->rect[3] += 1; }
+        for (int k = 0; k < 5; ++k) r->residue_sum[k] = r->sum[k];
+        r->indices_len = v;
+        r->indices_off = ex;
+    }
+};
+
 // indices_off: exclusive scan of indices_len inside each image; live count per image
 struct OffScan {
     vcb_cluster_rec *rec; const u32 *slot_base; const u32 *slot_img; u32 total; u64 *img_off;

@@ -90,6 +90,8 @@ int run_color(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w,
     if (e) return e;
     if ((u64)w * h == 0) return run_color_empty(c, cfg, w, h, nimg, out_br);
     const u64 n64 = (u64)w * h;
+    if (cfg->hierarchical != 0 && n64 * nimg >= (1ull << 30))
+        return fail(c, VCB_ERR_INVALID_ARG, "hierarchical runs take at most 2^30 pixels per device batch (32-bit adjacency offsets)");
     if (n64 == 0 || n64 * nimg >= 0x7fffff00ull) return fail(c, VCB_ERR_INVALID_ARG, "width*height*n must be in 1..2^31");
     if (!d_rgba) return fail(c, VCB_ERR_INVALID_ARG, "null image");
     rt::set_device(c->device);
@@ -152,6 +154,7 @@ int run_color_device(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba,
                      vcb_clusters **out) {
     if (!out) return fail(c, VCB_ERR_INVALID_ARG, "null output");
     if (nimg == 0) return VCB_OK;
+    for (size_t i = 0; i < nimg; ++i) out[i] = nullptr;         // on failure every entry is null: nothing for the caller to free
     const u64 n64 = (u64)w * h;
     size_t per_chunk = n64 ? (size_t)(MAX_CHUNK_PX / n64) : nimg;
     if (per_chunk < 1) per_chunk = 1;
@@ -160,7 +163,7 @@ int run_color_device(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba,
         std::shared_ptr<BatchResult> br;
         int e = run_color(c, cfg, d_rgba + i0 * n64 * 4, w, h, cnt, c->opt_materialize != 0, true, br);
         if (e) {
-            for (size_t k = 0; k < i0; ++k) { delete out[k]; out[k] = nullptr; }
+            for (size_t k = 0; k < nimg; ++k) { delete out[k]; out[k] = nullptr; }
             return e;
         }
         for (size_t i = 0; i < cnt; ++i) {
@@ -255,6 +258,9 @@ void vcb_ctx_destroy(vcb_ctx *c) {
     if (c->pipe_ready) { rt::stream_destroy(c->st_h2d); rt::stream_destroy(c->st_d2h); }
     for (rt::VmmArray *a : {&c->bw_flags, &c->bw_pc, &c->bw_la, &c->bw_ls, &c->bw_lr, &c->bw_ev, &c->bw_rgba}) rt::vmm_free(*a);
     rt::host_free(c->h_pinned);
+#ifndef VCB_HOSTSIM
+    for (auto &ev : c->events) if (ev) cudaEventDestroy(ev);
+#endif
     rt::stream_destroy(c->st);
     delete c;
 }
@@ -445,21 +451,25 @@ int vcb_runner_run_batch(vcb_ctx *c, const vcb_runner_config *cfg, const uint8_t
     int e = validate_cfg(c, cfg);
     if (e) return e;
     rt::set_device(c->device);
-    // runs of equally sized images are processed as one device batch
+    for (size_t k = 0; k < n; ++k) out[k] = nullptr;
+    // runs of equally sized images are processed as one device batch; on failure every handle already produced is released
+    auto release_all = [&]() { for (size_t k = 0; k < n; ++k) { delete out[k]; out[k] = nullptr; } };
     size_t i = 0;
     while (i < n) {
         size_t j = i + 1;
         const size_t bytes = (size_t)width[i] * height[i] * 4;
         while (j < n && width[j] == width[i] && height[j] == height[i] && (j - i + 1) * (bytes / 4) <= MAX_CHUNK_PX) ++j;
-        if (bytes == 0) return fail(c, VCB_ERR_INVALID_ARG, "empty image");
-        u8 *d = stage_input(c, bytes * (j - i));
-        if (!d) return fail(c, VCB_ERR_NOMEM, "device out of memory (input)");
-        for (size_t k = i; k < j; ++k) {
-            if (!rgba[k]) return fail(c, VCB_ERR_INVALID_ARG, "null image");
-            rt::copy_h2d(c->st, d + (k - i) * bytes, rgba[k], bytes);
+        u8 *d = nullptr;
+        if (bytes) {
+            d = stage_input(c, bytes * (j - i));
+            if (!d) { release_all(); return fail(c, VCB_ERR_NOMEM, "device out of memory (input)"); }
+            for (size_t k = i; k < j; ++k) {
+                if (!rgba[k]) { release_all(); return fail(c, VCB_ERR_INVALID_ARG, "null image"); }
+                rt::copy_h2d(c->st, d + (k - i) * bytes, rgba[k], bytes);
+            }
         }
         e = run_color_device(c, cfg, d, width[i], height[i], j - i, out + i);
-        if (e) return e;
+        if (e) { out[i] = nullptr; release_all(); return e; }
         i = j;
     }
     return VCB_OK;

@@ -40,7 +40,7 @@ struct vcb_ctx {
     // stage-2 workspace
     size_t cap_s2_slots = 0, cap_s2_adj = 0;
     u32 *s2_fw = nullptr, *s2_mnext = nullptr, *s2_mtail = nullptr, *s2_mark = nullptr, *s2_adj_off = nullptr,
-        *s2_cursor = nullptr, *s2_adj = nullptr;
+        *s2_cursor = nullptr, *s2_adj = nullptr, *s2_tmin = nullptr, *s2_bnd_off = nullptr, *s2_bcur = nullptr, *s2_bnd_px = nullptr;
     u64 *s2_over = nullptr;
     vcb::S2ImgState *s2_ist = nullptr;
     size_t cap_s2_img = 0;
@@ -396,13 +396,13 @@ inline int run_stage2(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg, b
     const u32 total = res->total_slots;
     if (total > c->cap_s2_slots) {
         const size_t cap = (size_t)total + 64;
-        bool ok = grow(c->s2_fw, cap) & grow(c->s2_mnext, cap) & grow(c->s2_mtail, cap) & grow(c->s2_mark, cap) &
+        bool ok = grow(c->s2_fw, cap) & grow(c->s2_mnext, cap) & grow(c->s2_mtail, cap) & grow(c->s2_mark, cap) & grow(c->s2_tmin, cap) & grow(c->s2_bnd_off, cap + 1) & grow(c->s2_bcur, cap) &
                   grow(c->s2_adj_off, cap + 1) & grow(c->s2_cursor, cap) & grow(c->s2_over, cap);
         if (!ok) { c->cap_s2_slots = 0; return VCB_ERR_NOMEM; }
         c->cap_s2_slots = total;
     }
     if ((size_t)d.N * 4 > c->cap_s2_adj) {
-        if (!grow(c->s2_adj, (size_t)d.N * 4 + 64)) { c->cap_s2_adj = 0; return VCB_ERR_NOMEM; }
+        if (!grow(c->s2_adj, (size_t)d.N * 4 + 64) || !grow(c->s2_bnd_px, (size_t)d.N + 64)) { c->cap_s2_adj = 0; return VCB_ERR_NOMEM; }
         c->cap_s2_adj = (size_t)d.N * 4;
     }
     if (d.nimg > c->cap_s2_img) {
@@ -426,6 +426,8 @@ inline int run_stage2(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg, b
     a.cfg.deepen_diff = cfg->deepen_diff; a.cfg.hollow_neighbours = cfg->hollow_neighbours;
     a.cfg.can_discard = (cfg->keying_action == VCB_KEYING_DISCARD && has_key) ? 1 : 0;
     a.cfg.hier_max = cfg->hierarchical == VCB_HIERARCHICAL_MAX;
+    a.cfg.batch_rounds = std::getenv("VCB_S2_NOBATCH") ? 0 : 1;
+    a.cfg.rect_perim = std::getenv("VCB_S2_RECT_PERIM") ? 1 : 0;
 #ifdef VCB_HOSTSIM
     a.cfg.help_min_px = 12;
 #else
@@ -433,7 +435,8 @@ inline int run_stage2(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg, b
 #endif
     a.l1 = res->labels1; a.rec = res->rec; a.slot_base = res->d_slot_base; a.slot_img = res->d_slot_img; a.total_slots = total;
     a.childoff = res->childoff; a.holeoff = res->holeoff;
-    a.fw = c->s2_fw; a.mpar = res->mpar; a.mnext = c->s2_mnext; a.mtail = c->s2_mtail; a.mark = c->s2_mark; a.outpos = res->outpos;
+    a.fw = c->s2_fw; a.mpar = res->mpar; a.mnext = c->s2_mnext; a.mtail = c->s2_mtail; a.mark = c->s2_mark; a.tmin = c->s2_tmin; a.outpos = res->outpos;
+    a.bnd_off = c->s2_bnd_off; a.bcur = c->s2_bcur; a.bnd_px = c->s2_bnd_px;
     a.adj_off = c->s2_adj_off; a.adj = c->s2_adj; a.cursor = c->s2_cursor; a.outputs = res->outputs; a.over = c->s2_over;
     a.ist = c->s2_ist; a.keys = c->sk0; a.vals = c->sv0;
     u32 *d_count = c->d_small + 3 * (d.nimg + 2) + 3;
@@ -447,6 +450,7 @@ inline int run_stage2(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg, b
     rt::launch(st, "k_s2_init", rt::SEQ, k_s2_init, dim3(gs), dim3(256), 0, a);
     rt::launch(st, "k_rag_count", rt::SEQ, k_rag<false>, dim3(gp), dim3(256), 0, a);
     prims::scan(st, "scan_deg", DegScan{a}, c->chunksum, total, c->sms * 8);
+    prims::scan(st, "scan_deg", BndScan{a}, c->chunksum, total, c->sms * 8);
     rt::launch(st, "k_rag_fill", rt::SEQ, k_rag<true>, dim3(gp), dim3(256), 0, a);
     int max_epoch = 0;
     while ((2ull << max_epoch) <= (u64)d.n) ++max_epoch;
@@ -458,13 +462,13 @@ inline int run_stage2(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg, b
         // few images: a thread-block cluster of fat CTAs per image (the leader replays the merges, the others help with the
         // large perimeter scans); many images: one CTA per image, more CTAs per SM
 #ifdef VCB_HOSTSIM
-        const int s2_threads = 64;
-        const u32 G = d.nimg == 1 ? 2u : 1u;
+        const int s2_threads = 128;                                  // 4 warps: batch rounds of 4 candidates
+        const u32 G = (d.nimg == 1 && a.cfg.rect_perim) ? 2u : 1u;
 #else
         const int s2_threads = d.nimg * 8 <= (u32)c->sms ? 1024 : d.nimg * 2 <= (u32)c->sms ? 512 : d.nimg <= (u32)c->sms ? 256 : 128;
         u32 G = 1;
         static const u32 maxg = std::getenv("VCB_S2_MAXG") ? (u32)std::atoi(std::getenv("VCB_S2_MAXG")) : 8u;
-        while (G < maxg && d.nimg * (G * 2) * 2 <= (u32)c->sms) G *= 2;
+        while (a.cfg.rect_perim && G < maxg && d.nimg * (G * 2) * 2 <= (u32)c->sms) G *= 2;   // helpers only serve the rect-scan perimeter
 #endif
         if (G > 1)
             rt::launch_cluster(st, "k_s2_epoch", k_s2_epoch, dim3(d.nimg * G), dim3(s2_threads), sizeof(S2Shared) + 16, G, a,
@@ -486,6 +490,9 @@ inline int run_stage2(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg, b
     rt::copy_d2h(st, h, c->s2_ist, d.nimg * sizeof(S2ImgState));
     if (rt::stream_sync(st) != 0 || st.last_error) { c->err = st.last_error_text; st.last_error = 0; return VCB_ERR_CUDA; }
     for (u32 i = 0; i < d.nimg; ++i) res->nout[i] = h[i].nout;
+    if (std::getenv("VCB_S2_STATS"))
+        std::fprintf(stderr, "[vcb] stage 2 image 0: merges %u, outputs %u, batch rounds %u (candidates %u, committed %u), single pops %u\n",
+                     h[0].nmerge, h[0].nout, h[0].st_rounds, h[0].st_cands, h[0].st_committed, h[0].st_singles);
     if (res->pool1) {
         // ordered indices / holes pools from the stage-1 pool and the merge forest
         u32 *d_ib = c->d_small, *d_hb = c->d_small + (d.nimg + 2), *d_p1b = c->d_small + 2 * (d.nimg + 2);

@@ -19,12 +19,15 @@ namespace vcb {
 struct S2Cfg {
     u32 hierarchical; u64 good_min, good_max; i32 deepen_diff; u64 hollow_neighbours; int can_discard; int hier_max;
     u64 help_min_px;   // rects at least this large are counted by the whole thread-block cluster
+    int batch_rounds;  // parallel batch rounds on (default) / off
+    int rect_perim;    // 1: perimeter by scanning the bounding rect (cluster helpers); 0: by the boundary-pixel lists
 };
 
 struct S2ImgState {
     u32 stamp, nout, maxarea, nover;
     u32 nmerge, task_c, task_quit, perim_acc;
     i32 task_rect[4];
+    u32 st_rounds, st_committed, st_cands, st_singles;   // statistics of the batch rounds / single pops
 };
 
 struct S2 {
@@ -39,10 +42,12 @@ struct S2 {
     u32 *childoff, *holeoff;       // offset of the absorbed list inside to.indices / to.holes at merge time
     u32 *mnext, *mtail;            // member lists (stage-1 slots of a cluster)
     u32 *mark;                     // distinct-neighbour stamps
+    u32 *tmin;                     // batch rounds: smallest batch position that modifies the slot (NONE outside a round)
     u32 *outpos;                   // first position in clusters_output, NONE if absent
     u32 *adj_off;                  // total_slots + 1
     u32 *adj;                      // adjacency entries (image-local slot ids)
     u32 *cursor;                   // total_slots (fill cursors / degree counts)
+    u32 *bnd_off, *bnd_px, *bcur;  // per stage-1 slot: its boundary pixels (a neighbour with another label, or the image edge)
     u32 *outputs;                  // total_slots: clusters_output per image at slot_base[img]
     u64 *over;                     // total_slots: per-image overflow of the urgent list at slot_base[img]
     S2ImgState *ist;               // nimg
@@ -74,6 +79,14 @@ template <bool FILL> __global__ void __launch_bounds__(256) k_rag(S2 a) {
         const u32 img = g / d.n, p = g - img * d.n, x = p % d.w, y = p / d.w;
         const u32 base = a.slot_base[img];
         const u32 la = a.l1[g];
+        {   // boundary pixel of its stage-1 slot: only these can ever be on the perimeter of a merged cluster
+            const bool bnd = x == 0 || y == 0 || x + 1 == d.w || y + 1 == d.h || a.l1[g - 1] != la || a.l1[g + 1] != la ||
+                             a.l1[g - d.w] != la || a.l1[g + d.w] != la;
+            if (bnd) {
+                if (FILL) a.bnd_px[a.bnd_off[base + la] + atomicAdd(&a.bcur[base + la], 1u)] = p;
+                else atomicAdd(&a.bcur[base + la], 1u);
+            }
+        }
         if (x + 1 < d.w) {
             const u32 lb = a.l1[g + 1];
             if (la != lb && !(y > 0 && a.l1[g - d.w] == la && a.l1[g + 1 - d.w] == lb)) {
@@ -95,6 +108,17 @@ template <bool FILL> __global__ void __launch_bounds__(256) k_rag(S2 a) {
     }
 }
 
+struct BndScan {
+    S2 a;
+    __device__ u32 count() const { return a.total_slots; }
+    __device__ u32 value(u32 s) const { return a.bcur[s]; }
+    __device__ void emit(u32 s, u32 ex, u32 v) const {
+        a.bnd_off[s] = ex;
+        a.bcur[s] = 0;
+        if (s == a.total_slots - 1) a.bnd_off[a.total_slots] = ex + v;
+    }
+};
+
 struct DegScan {
     S2 a;
     __device__ u32 count() const { return a.total_slots; }
@@ -110,7 +134,7 @@ __global__ void __launch_bounds__(256) k_s2_init(S2 a) {
     const u32 stride = gridDim.x * 256;
     for (u32 s = blockIdx.x * 256 + threadIdx.x; s < a.total_slots; s += stride) {
         a.fw[s] = s - a.slot_base[a.slot_img[s]]; a.mpar[s] = NONE; a.mnext[s] = NONE; a.mtail[s] = s - a.slot_base[a.slot_img[s]];
-        a.mark[s] = 0; a.outpos[s] = NONE; a.cursor[s] = 0;
+        a.mark[s] = 0; a.tmin[s] = NONE; a.outpos[s] = NONE; a.cursor[s] = 0; a.bcur[s] = 0;
         const u32 area = a.rec[s].indices_len;
         if (area) atomicMax(&a.ist[a.slot_img[s]].maxarea, area);
     }
@@ -168,7 +192,12 @@ __device__ static __forceinline__ i32 color_diff(u32 a, u32 b) {     // runner.r
 constexpr int S2_MAX_THREADS = 1024;   // block size is chosen at launch: 1024 for a few large images, 128 for big batches
 constexpr int S2_MEMCHUNK = 256;
 constexpr int S2_URGENT = 64;
-constexpr u32 S2_MAPBYTES = 40960;
+constexpr u32 S2_MAPBYTES = 28672;
+constexpr int S2_NB = 32;                 // candidates per batch round (one warp each)
+constexpr int S2_CAPN = 32;               // neighbour roots kept per candidate
+constexpr int S2_CAPM = 32;               // member slots kept per candidate
+constexpr u64 S2_PERIM_WARP_MAX = 2048;   // rects up to this size are counted by the candidate's own warp
+enum : u32 { BF_SLOW = 1, BF_OUTONLY = 2, BF_ISOLATED = 4, BF_DEEPEN = 8, BF_HOLLOW = 16, BF_CONFLICT = 32, BF_MERGE = 64 };
 
 struct S2Shared {
     unsigned long long best;
@@ -178,8 +207,362 @@ struct S2Shared {
     u32 deg[S2_MEMCHUNK + 1];
     u32 cur, area, ndist, perim, nmem, more, mycolor, nurg, lo, hi, stamp, nchunks, newfw, target, want_perim, deepen, single;
     i32 rect[4];
+    // batch rounds
+    unsigned long long bbest[S2_NB], bkey[S2_NB];
+    u32 bc[S2_NB], barea[S2_NB], btarget[S2_NB], bndist[S2_NB], bflags[S2_NB], bnewarea[S2_NB], bpos[S2_NB], bseg[S2_NB], bstamp[S2_NB], bnmem[S2_NB];
+    u32 bnbr[S2_NB][S2_CAPN];
+    u32 bmem[S2_NB][S2_CAPM];
+    u32 nb, ncommit, mode, force_single, brounds, bdone, boff;
     u8 map[S2_MAPBYTES];
 };
+
+// ---------------------------------------------------------------------------------------------------------------
+// Batch round: the next candidates of the sorted stream are evaluated IN PARALLEL (one warp each) and the longest prefix
+// that is provably independent is committed in parallel.  Candidate k depends on an earlier candidate i of the batch
+// iff i modifies a slot that k reads: i's own slot c_i (absorbed) or its target t_i (sums / area / neighbourhood change),
+// where k reads c_k and its neighbour roots N(c_k) -- the distance-2 rule of SURVEY Appendix D.  tmin[slot] holds the
+// smallest batch position modifying the slot, so the test is `min over {c_k} U N(c_k) of tmin < k`.  A merge also creates
+// a new key (new area, target); the prefix additionally stops before the first candidate whose key exceeds a new key made
+// earlier in the batch, so the global (area, index) pop order is never violated.  Everything else of a pop (outputs in
+// candidate order, the running maximum area of builder.rs:446, list offsets) is a prefix scan over the batch.
+__device__ static __forceinline__ bool s2_in_cluster(const S2 &a, const u32 *l1, u32 base, u32 q, u32 c) {
+    return ldcg(&a.fw[base + __ldg(&l1[q])]) == c;
+}
+__device__ static __forceinline__ unsigned long long warp_min64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
+    return v;
+}
+
+__device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh, S2ImgState *ist, const u64 *keys, int epoch,
+                                                      u32 img, u32 base, u64 *over) {
+    const Dims d = a.d;
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 W = (blockDim.x >> 5) < (u32)S2_NB ? (blockDim.x >> 5) : (u32)S2_NB;
+    const int kshift = a.idx_bits + epoch;
+    const u64 idx_mask = (1ull << a.idx_bits) - 1ull;
+    const u32 area_base = 1u << epoch;
+    // ---- F: warp 0 takes the next entries of the sorted segment that precede every pending urgent key
+    if (warp == 0) {
+        unsigned long long umin = ~0ull;
+        for (u32 i = lane; i < sh->nurg; i += 32) umin = sh->urgent[i] < umin ? sh->urgent[i] : umin;
+        const u32 nover = ist->nover;
+        for (u32 i = lane; i < nover; i += 32) umin = over[i] < umin ? over[i] : umin;
+        umin = warp_min64(umin);
+        const bool use = sh->force_single == 0 && sh->boff == 0;
+        const u32 lo = sh->lo, hi = sh->hi;
+        unsigned long long kb = ~0ull;
+        bool inrange = false, valid = false;
+        u32 idx = 0, ar = 0;
+        if (use && lane < W && lo + lane < hi) {
+            kb = (keys[lo + lane] & ((1ull << kshift) - 1ull)) + ((unsigned long long)area_base << a.idx_bits);
+            inrange = kb < umin;
+            if (inrange) {
+                idx = (u32)(kb & idx_mask); ar = (u32)(kb >> a.idx_bits);
+                valid = a.fw[base + idx] == idx && a.rec[base + idx].indices_len == ar;
+            }
+        }
+        const u32 m_in = __ballot_sync(0xffffffffu, inrange);
+        const u32 npre = (~m_in) ? (u32)(__ffs((int)~m_in) - 1) : 32u;       // consecutive entries from the head
+        const u32 vmask = __ballot_sync(0xffffffffu, valid && lane < npre);
+        const u32 nb = (u32)__popc(vmask);
+        if (use && npre > 0) {
+            if (valid && lane < npre) {
+                const u32 slot = (u32)__popc(vmask & ((1u << lane) - 1u));
+                sh->bc[slot] = idx; sh->barea[slot] = ar; sh->bseg[slot] = lo + lane; sh->bkey[slot] = kb;
+                sh->bstamp[slot] = ist->stamp + 1 + slot; sh->bflags[slot] = 0; sh->bbest[slot] = ~0ull; sh->bndist[slot] = 0;
+                sh->btarget[slot] = NONE; sh->bnewarea[slot] = 0; sh->bnmem[slot] = 0;
+            }
+            __syncwarp();
+            if (lane == 0) { ist->stamp += nb; sh->lo = lo + npre; sh->nb = nb; sh->mode = nb ? 1u : 2u; }
+        } else if (lane == 0) { sh->mode = 0; sh->force_single = 0; }
+    }
+    __syncthreads();
+    if (sh->mode == 0) return false;
+    if (sh->mode == 2) return true;
+    const u32 nb = sh->nb;
+    // ---- P: one warp per candidate: neighbours, arg-min, deepen / hollow, new area
+    if (warp < nb) {
+        const u32 c = sh->bc[warp], area = sh->barea[warp], stamp = sh->bstamp[warp];
+        u32 flags = 0;
+        if (area > a.cfg.hierarchical) flags = BF_OUTONLY;
+        else if (c == 0) flags = BF_SLOW;                            // clusters[0]: its merge turns label-0 pixels into neighbours
+        else {
+            bool slow = false;
+            if (lane == 0) {
+                u32 n = 0, m = c;
+                while (m != NONE && n < (u32)S2_CAPM) { sh->bmem[warp][n++] = m; m = a.mnext[base + m]; }
+                sh->bnmem[warp] = n;
+                if (m != NONE) sh->bnmem[warp] = 0xffffffffu;
+            }
+            __syncwarp();
+            const u32 nm = sh->bnmem[warp];
+            if (nm == 0xffffffffu) slow = true;
+            else {
+                const u32 mycolor = avg_color(a.rec[base + c].sum);
+                // distinct neighbour roots are collected in the candidate's own list (the global mark[] stamps cannot be
+                // shared by candidates that are scanned concurrently)
+                u32 n = 0;                                           // warp-uniform
+                for (u32 i = 0; i < nm; ++i) {
+                    const u32 sl = sh->bmem[warp][i];
+                    const u32 e0 = a.adj_off[base + sl], e1 = a.adj_off[base + sl + 1];
+                    for (u32 eb = e0; eb < e1; eb += 32) {
+                        const u32 e = eb + lane;
+                        u32 o = NONE;
+                        if (e < e1) {
+                            u32 fl;
+                            o = s2_find(a.fw, base, a.adj[e], &fl);
+                            if (o == c || o == 0) o = NONE;
+                        }
+                        u32 pending = __ballot_sync(0xffffffffu, o != NONE);
+                        while (pending) {
+                            const int src = __ffs((int)pending) - 1;
+                            const u32 v = __shfl_sync(0xffffffffu, o, src);
+                            const bool found = __any_sync(0xffffffffu, lane < n && lane < (u32)S2_CAPN && sh->bnbr[warp][lane] == v);
+                            if (!found) {
+                                if ((int)lane == src) {
+                                    if (n < (u32)S2_CAPN) sh->bnbr[warp][n] = v;
+                                    const i32 df = color_diff(mycolor, avg_color(a.rec[base + v].sum));
+                                    const unsigned long long k = ((unsigned long long)((u32)df * 65535u + v) << 32) | v;
+                                    if (k < sh->bbest[warp]) sh->bbest[warp] = k;
+                                }
+                                ++n;
+                                __syncwarp();
+                            }
+                            pending &= ~__ballot_sync(0xffffffffu, o == v);
+                        }
+                    }
+                }
+                if (lane == 0) sh->bndist[warp] = n;
+                __syncwarp();
+                const u32 nd = sh->bndist[warp];
+                if (nd > (u32)S2_CAPN) slow = true;
+                else if (nd == 0) flags = BF_ISOLATED;
+                else {
+                    const unsigned long long best = sh->bbest[warp];
+                    const u32 tg = (u32)best;
+                    const i32 md = (i32)(((u32)(best >> 32) - tg) / 65535u);
+                    bool deepen = false;
+                    if (a.cfg.hier_max && a.cfg.good_min < (u64)area && (u64)area < a.cfg.good_max && md > a.cfg.deepen_diff) {
+                        if (a.cfg.good_min == 0) deepen = true;
+                        else {
+                            // perimeter from the members' boundary-pixel lists (see s2_perimeter_bnd), by this warp
+                            const u32 *l1 = a.l1 + (size_t)img * d.n;
+                            u32 items = 0;
+                            for (u32 i = 0; i < nm; ++i) {
+                                const u32 m = sh->bmem[warp][i];
+                                if (ldcg(&a.fw[base + m]) == c) items += a.bnd_off[base + m + 1] - a.bnd_off[base + m];
+                            }
+                            if ((u64)items > S2_PERIM_WARP_MAX) slow = true;
+                            else {
+                                u32 cnt = 0;
+                                for (u32 i = 0; i < nm; ++i) {
+                                    const u32 m = sh->bmem[warp][i];
+                                    if (ldcg(&a.fw[base + m]) != c) continue;
+                                    const u32 b0 = a.bnd_off[base + m], b1 = a.bnd_off[base + m + 1];
+                                    for (u32 k = b0 + lane; k < b1; k += 32) {
+                                        const u32 p = a.bnd_px[k];
+                                        const u32 x = p % d.w, y = p / d.w;
+                                        bool edge = x == 0 || y == 0 || x + 1 == d.w || y + 1 == d.h;
+                                        if (!edge) edge = !s2_in_cluster(a, l1, base, p - 1, c) || !s2_in_cluster(a, l1, base, p + 1, c) ||
+                                                          !s2_in_cluster(a, l1, base, p - d.w, c) || !s2_in_cluster(a, l1, base, p + d.w, c);
+                                        if (edge) cnt++;
+                                    }
+                                }
+#pragma unroll
+                                for (int o2 = 16; o2 > 0; o2 >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o2);
+                                deepen = (u64)cnt < (u64)area;
+                            }
+                        }
+                    }
+                    if (!slow) {
+                        flags = BF_MERGE | (deepen ? BF_DEEPEN : 0u) | (((u64)nd <= a.cfg.hollow_neighbours) ? BF_HOLLOW : 0u);
+                        if (lane == 0) {
+                            sh->btarget[warp] = tg;
+                            sh->bnewarea[warp] = a.rec[base + tg].indices_len + area;
+                            atomicMin(&a.tmin[base + tg], warp);
+                            atomicMin(&a.tmin[base + c], warp);
+                        }
+                    }
+                }
+            }
+            if (slow) flags = BF_SLOW;
+        }
+        if (lane == 0) sh->bflags[warp] = flags;
+    }
+    __threadfence_block();
+    __syncthreads();
+    // ---- C: conflicts with earlier candidates of the batch
+    if (warp < nb) {
+        const u32 c = sh->bc[warp];
+        u32 f = sh->bflags[warp];
+        bool conf = (f & BF_SLOW) != 0;                              // a slow candidate is handled alone by the single-pop path
+        if (lane == 0 && ldcg(&a.tmin[base + c]) < warp) conf = true;
+        if (f & BF_MERGE) {
+            const u32 nd = sh->bndist[warp];
+            for (u32 i = lane; i < nd; i += 32) if (ldcg(&a.tmin[base + sh->bnbr[warp][i]]) < warp) conf = true;
+        }
+        if (__any_sync(0xffffffffu, conf) && lane == 0) sh->bflags[warp] = f | BF_CONFLICT;
+    }
+    __syncthreads();
+    // ---- D: warp 0 decides the committed prefix, output positions and the running maximum area
+    if (warp == 0) {
+        const bool in = lane < nb;
+        const u32 f = in ? sh->bflags[lane] : 0u;
+        const u32 stopm = __ballot_sync(0xffffffffu, in && (f & BF_CONFLICT));
+        u32 J = stopm ? (u32)(__ffs((int)stopm) - 1) : nb;
+        // pop order: a candidate whose key exceeds a key created earlier in the batch must wait
+        const unsigned long long key = in ? sh->bkey[lane] : 0ull;
+        unsigned long long nk = (in && (f & BF_MERGE)) ? (((unsigned long long)sh->bnewarea[lane] << a.idx_bits) | sh->btarget[lane]) : ~0ull;
+        unsigned long long inc = nk;                                  // inclusive prefix min
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o); if ((int)lane >= o && t < inc) inc = t; }
+        unsigned long long pm = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) pm = ~0ull;
+        const u32 violm = __ballot_sync(0xffffffffu, in && key > pm);
+        if (violm) { const u32 j2 = (u32)(__ffs((int)violm) - 1); if (j2 < J) J = j2; }
+        const bool committed = lane < J;
+        // running maximum area (builder.rs:446: `iteration == cluster_areas.len() - 1`)
+        const u32 na = (committed && (f & BF_MERGE)) ? sh->bnewarea[lane] : 0u;
+        u32 imax = na;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, imax, o); if ((int)lane >= o && t > imax) imax = t; }
+        u32 pmax = __shfl_up_sync(0xffffffffu, imax, 1);
+        if (lane == 0) pmax = 0;
+        const u32 maxbefore = pmax > ist->maxarea ? pmax : ist->maxarea;
+        const bool outp = committed && ((f & BF_OUTONLY) || (f & BF_DEEPEN) ||
+                                        ((f & BF_ISOLATED) && (sh->barea[lane] == maxbefore || a.cfg.can_discard)));
+        const u32 outm = __ballot_sync(0xffffffffu, outp);
+        if (in) sh->bpos[lane] = outp ? ist->nout + (u32)__popc(outm & ((1u << lane) - 1u)) : NONE;
+        const u32 allmax = __shfl_sync(0xffffffffu, imax, 31);
+        const u32 nmerge = (u32)__popc(__ballot_sync(0xffffffffu, committed && (f & BF_MERGE)));
+        __syncwarp();
+        if (lane == 0) {
+            ist->nout += (u32)__popc(outm);
+            if (allmax > ist->maxarea) ist->maxarea = allmax;
+            ist->nmerge += nmerge;
+            sh->ncommit = J;
+            if (J < nb) sh->lo = sh->bseg[J];                         // the rest is read again next round
+            if (J == 0) sh->force_single = 1;                         // head candidate needs the single-pop path
+            // adaptive: where neighbouring candidates keep conflicting (dense small clusters around one big cluster) a round
+            // commits one or two pops and costs more than the single-pop path; give up for the rest of the epoch
+            sh->brounds += 1; sh->bdone += J;
+            ist->st_rounds += 1; ist->st_committed += J; ist->st_cands += nb;
+            if (sh->brounds >= 6 && sh->bdone < 6 * sh->brounds) sh->boff = 1;
+        }
+    }
+    __syncthreads();
+    // ---- E: commit the prefix in parallel (independent by construction), then clear the tmin marks
+    const u32 J = sh->ncommit;
+    if (warp < nb) {
+        const u32 c = sh->bc[warp], f = sh->bflags[warp], area = sh->barea[warp];
+        if (warp < J) {
+            u32 newfw = 0;
+            if (lane == 0) {
+                const u32 pos = sh->bpos[warp];
+                if (pos != NONE) { a.outputs[base + pos] = c; if (a.outpos[base + c] == NONE) a.outpos[base + c] = pos; }
+                if (f & BF_MERGE) {
+                    const u32 target = sh->btarget[warp];
+                    const bool deepen = (f & BF_DEEPEN) != 0, hollow = (f & BF_HOLLOW) != 0;
+                    vcb_cluster_rec *rf = a.rec + base + c, *rt_ = a.rec + base + target;
+                    if (!deepen) for (int k2 = 0; k2 < 5; ++k2) rt_->residue_sum[k2] += rf->residue_sum[k2];
+                    for (int k2 = 0; k2 < 5; ++k2) rt_->sum[k2] += rf->sum[k2];
+                    if (!(rf->rect[2] - rf->rect[0] == 0 && rf->rect[3] - rf->rect[1] == 0)) {
+                        if (rt_->rect[2] - rt_->rect[0] == 0 && rt_->rect[3] - rt_->rect[1] == 0) {
+                            for (int k2 = 0; k2 < 4; ++k2) rt_->rect[k2] = rf->rect[k2];
+                        } else {
+                            rt_->rect[0] = rt_->rect[0] < rf->rect[0] ? rt_->rect[0] : rf->rect[0];
+                            rt_->rect[1] = rt_->rect[1] < rf->rect[1] ? rt_->rect[1] : rf->rect[1];
+                            rt_->rect[2] = rt_->rect[2] > rf->rect[2] ? rt_->rect[2] : rf->rect[2];
+                            rt_->rect[3] = rt_->rect[3] > rf->rect[3] ? rt_->rect[3] : rf->rect[3];
+                        }
+                    }
+                    a.childoff[base + c] = rt_->indices_len;
+                    a.holeoff[base + c] = rt_->holes_len;
+                    rt_->indices_len += area;
+                    if (!deepen) {
+                        for (int k2 = 0; k2 < 5; ++k2) rf->sum[k2] = 0;
+                        for (int k2 = 0; k2 < 4; ++k2) rf->rect[k2] = 0;
+                        rf->indices_len = 0;
+                    } else {
+                        if (hollow) { rt_->holes_len += area; rt_->num_holes += 1; }
+                        rf->merged_into = target;
+                        rt_->depth += 1;
+                    }
+                    newfw = target | ((deepen && hollow) ? FLAGBIT : 0u);
+                    a.mpar[base + c] = target | (deepen ? FLAGBIT : 0u) | ((deepen && hollow) ? HOLLOWBIT : 0u);
+                    a.mnext[base + a.mtail[base + target]] = c;
+                    a.mtail[base + target] = a.mtail[base + c];
+                    const u32 na = rt_->indices_len;
+                    if ((31 - __clz((int)na)) == epoch) {             // same epoch: must still be popped in order
+                        const unsigned long long k = ((unsigned long long)na << a.idx_bits) | target;
+                        const u32 slot = atomicAdd(&sh->nurg, 1u);
+                        if (slot < (u32)S2_URGENT) sh->urgent[slot] = k;
+                        else { atomicSub(&sh->nurg, 1u); over[atomicAdd(&ist->nover, 1u)] = k; }
+                    }
+                }
+            }
+            newfw = __shfl_sync(0xffffffffu, newfw, 0);
+            if (f & BF_MERGE) {
+                const u32 nm = sh->bnmem[warp];
+                for (u32 i = lane; i < nm; i += 32) stcg(&a.fw[base + sh->bmem[warp][i]], newfw);
+            }
+        }
+        if (lane == 0) {
+            stcg(&a.tmin[base + c], NONE);
+            if (f & BF_MERGE) stcg(&a.tmin[base + sh->btarget[warp]], NONE);
+        }
+    }
+    __threadfence_block();
+    __syncthreads();
+    return true;
+}
+
+// Perimeter of cluster c from the boundary-pixel lists of its member slots (block-parallel).  A pixel whose four
+// neighbours carry its own stage-1 label stays interior whatever merges happen, so only the stage-1 boundary pixels of the
+// members need to be looked at: the cost is the boundary length of the members, not the area of the bounding rect.
+// Members that are holes of c (forwarding word != c) are skipped whole.  Adds the block's count to sh->perim.
+__device__ static __forceinline__ void s2_perimeter_bnd(const S2 &a, S2Shared *sh, u32 img, u32 base, u32 c) {
+    const Dims d = a.d;
+    const u32 tid = threadIdx.x, T = blockDim.x;
+    const u32 *l1 = a.l1 + (size_t)img * d.n;
+    u32 cntp = 0;
+    if (tid == 0) sh->more = c;
+    __syncthreads();
+    while (true) {
+        if (tid == 0) {
+            u32 n = 0, m = sh->more;
+            while (m != NONE && n < S2_MEMCHUNK) { sh->mem[n++] = m; m = a.mnext[base + m]; }
+            sh->nmem = n; sh->more = m;
+        }
+        __syncthreads();
+        for (u32 i = tid; i < sh->nmem; i += T) {
+            const u32 m = sh->mem[i];
+            const bool in = ldcg(&a.fw[base + m]) == c;              // root is c and the slot is not one of its holes
+            sh->eoff[i] = a.bnd_off[base + m];
+            sh->deg[i] = in ? a.bnd_off[base + m + 1] - a.bnd_off[base + m] : 0u;
+        }
+        __syncthreads();
+        if (tid == 0) { const u32 nm0 = sh->nmem; u32 acc = 0; for (u32 i = 0; i < nm0; ++i) { const u32 dg = sh->deg[i]; sh->deg[i] = acc; acc += dg; } sh->deg[nm0] = acc; }
+        __syncthreads();
+        const u32 nm = sh->nmem, nitems = sh->deg[nm];
+        for (u32 it = tid; it < nitems; it += T) {
+            u32 lo = 0, hi = nm;
+            while (hi - lo > 1) { const u32 mid = (lo + hi) / 2; if (sh->deg[mid] <= it) lo = mid; else hi = mid; }
+            const u32 p = a.bnd_px[sh->eoff[lo] + (it - sh->deg[lo])];
+            const u32 x = p % d.w, y = p / d.w;
+            bool edge = x == 0 || y == 0 || x + 1 == d.w || y + 1 == d.h;
+            if (!edge) edge = !s2_in_cluster(a, l1, base, p - 1, c) || !s2_in_cluster(a, l1, base, p + 1, c) ||
+                              !s2_in_cluster(a, l1, base, p - d.w, c) || !s2_in_cluster(a, l1, base, p + d.w, c);
+            if (edge) cntp++;
+        }
+        __syncthreads();
+        const bool last = sh->more == NONE;
+        __syncthreads();
+        if (last) break;
+    }
+    if (cntp) atomicAdd(&sh->perim, cntp);
+}
 
 // Perimeter of cluster c restricted to rect rows [row_lo, row_hi) (rect-relative), shape/geometry.rs:52-75 on
 // Cluster::to_image_with_hole: pixels of c (holes removed) with a 4-neighbour outside c.  Block-parallel; the membership
@@ -290,11 +673,12 @@ __global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_epoch(S2 a, const u64 *ke
         u32 l2 = lo;
         while (l2 < hi) { const u32 mid = (l2 + hi) / 2; if ((u32)(keys[mid] >> kshift) <= img) l2 = mid + 1; else hi = mid; }
         sh->hi = l2;
-        sh->nurg = 0;
+        sh->nurg = 0; sh->force_single = 0; sh->mode = 0; sh->brounds = 0; sh->bdone = 0; sh->boff = 0;
     }
     __syncthreads();
 
     while (true) {
+        if (a.cfg.batch_rounds && sh->boff == 0 && s2_batch_round(a, sh, ist, keys, epoch, img, base, over)) continue;
         if (tid == 0) {
             // next pop = smallest valid key among: sorted segment head, urgent list, overflow list
             u32 c = NONE, carea = 0;
@@ -312,6 +696,7 @@ __global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_epoch(S2 a, const u64 *ke
             }
             sh->cur = c; sh->area = carea;
             if (c != NONE) {
+                ist->st_singles += 1;
                 sh->best = ~0ull; sh->ndist = 0; sh->perim = 0;
                 sh->stamp = ++ist->stamp;
                 sh->mycolor = avg_color(a.rec[base + c].sum);
@@ -406,7 +791,10 @@ __global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_epoch(S2 a, const u64 *ke
         bool deepen = sh->deepen != 0;
         if (sh->want_perim) {
             const u32 rh = (u32)(sh->rect[3] - sh->rect[1]), rwid = (u32)(sh->rect[2] - sh->rect[0]);
-            if (G > 1 && (u64)rh * rwid >= a.cfg.help_min_px) {
+            if (!a.cfg.rect_perim) {
+                s2_perimeter_bnd(a, sh, img, base, c);
+                __syncthreads();
+            } else if (G > 1 && (u64)rh * rwid >= a.cfg.help_min_px) {
                 // large rect: the other CTAs of the cluster take row slices.  They sleep in the cluster barrier until now.
                 if (tid == 0) {
                     stcg(&ist->task_c, c); stcg(&ist->task_quit, 0u);

@@ -253,7 +253,7 @@ void vcb_ctx_destroy(vcb_ctx *c) {
     rt::dev_free(c->chunksum); rt::dev_free(c->rs_table); rt::dev_free(c->sk0); rt::dev_free(c->sk1);
     rt::dev_free(c->sv0); rt::dev_free(c->sv1); rt::dev_free(c->d_small); rt::dev_free(c->d_stage);
     rt::dev_free(c->s2_fw); rt::dev_free(c->s2_mnext); rt::dev_free(c->s2_mtail); rt::dev_free(c->s2_mark); rt::dev_free(c->s2_adj_off);
-    rt::dev_free(c->s2_cursor); rt::dev_free(c->s2_adj); rt::dev_free(c->s2_over); rt::dev_free(c->s2_ist);
+    rt::dev_free(c->s2_cursor); rt::dev_free(c->s2_adj); rt::dev_free(c->s2_tmin); rt::dev_free(c->s2_bnd_off); rt::dev_free(c->s2_bcur); rt::dev_free(c->s2_bnd_px); rt::dev_free(c->s2_over); rt::dev_free(c->s2_ist);
     rt::dev_free(c->d_in[0]); rt::dev_free(c->d_in[1]);
     if (c->pipe_ready) { rt::stream_destroy(c->st_h2d); rt::stream_destroy(c->st_d2h); }
     for (rt::VmmArray *a : {&c->bw_flags, &c->bw_pc, &c->bw_la, &c->bw_ls, &c->bw_lr, &c->bw_ev, &c->bw_rgba}) rt::vmm_free(*a);

@@ -309,3 +309,38 @@ def test_empty_and_ragged_inputs(gpu, oracle):
     got = gpu.runner_run_batch(imgs, cfg)
     for k, im in enumerate(imgs):
         assert_same_clusters(got[k], oracle.runner_run(im, cfg, pools=False), pools=False, ctx=f"ragged batch image {k}")
+
+
+def test_stage2_execution_modes_agree(gpu, oracle):
+    """The hierarchical stage has three execution strategies (parallel batch rounds, single pops only, rect-scan perimeter with
+    a thread-block cluster per image); all must reproduce the reference."""
+    import os
+
+    img = synth.g3_posterised(1500, 1100, seed=8, cell=80, key=(40, 200, 120, 255))
+    noisy = synth.g2_scene(900, 700, seed=12)
+    cases = [(img, make_config(is_same_color_a=2, deepen_diff=16, good_max_area=1500 * 1100, key_color=(40, 200, 120, 255))),
+             (noisy, make_config())]
+    for k, (im, cfg) in enumerate(cases):
+        ref = oracle.runner_run(im, cfg, pools=False, color_image=True)
+        for env in ({}, {"VCB_S2_NOBATCH": "1"}, {"VCB_S2_RECT_PERIM": "1"}, {"VCB_S2_RECT_PERIM": "1", "VCB_S2_NOBATCH": "1"}):
+            for name in ("VCB_S2_NOBATCH", "VCB_S2_RECT_PERIM"):
+                os.environ.pop(name, None)
+            os.environ.update(env)
+            try:
+                got = gpu.runner_run(im, cfg, pools=False, color_image=True)
+            finally:
+                for name in env:
+                    os.environ.pop(name, None)
+            assert_same_clusters(got, ref, pools=False, ctx=f"case {k} env {env}")
+
+
+def test_invalid_arguments(gpu):
+    """Error behaviour at the boundary: the reference's assert!(is_same_color_a < 8) (runner.rs:78) and the never-terminating
+    batch_size == 0 become VCB_ERR_INVALID_ARG; nothing aborts."""
+    img = np.zeros((4, 4, 4), dtype=np.uint8)
+    for bad in (dict(is_same_color_a=8), dict(is_same_color_a=-1), dict(batch_size=0)):
+        with pytest.raises(VcbError) as e:
+            gpu.runner_run(img, make_config(hierarchical=0, **bad), pools=False)
+        assert e.value.status == 1
+    res = gpu.runner_run(img, make_config(hierarchical=0, is_same_color_a=7), pools=False)   # still usable afterwards
+    assert res["num_slots"] >= 2

@@ -255,8 +255,12 @@ def main():
     if top:
         per_launch_ms = prof[top]["ms"] / prof[top]["launches"]
         achieved = ALGO_BYTES_PER_PX * B * NPX / (per_launch_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")     # dram read+write bytes per launch from the committed ncu capture
+        if os.path.exists(tpath) and B == 64:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch", {}).get(top)
         roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel_ms_per_launch": per_launch_ms,
+                "traffic": traffic, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX * B * NPX, "peak_source": peak_src, "kernel_ms_per_launch": per_launch_ms,
                 "share_of_step": prof[top]["ms"] / sum(v["ms"] for v in prof.values()),
                 "whole_step_frac": (ALGO_BYTES_PER_PX * B * NPX / (ms_step * 1e-3) / 1e9) / peak}
 

@@ -723,68 +723,102 @@ struct LeafScan {
 // child parks its (area, carrier) and leaves, the second one decides the winner and carries on).
 // builder.rs:313-325: `if area(left) <= area(up) { combine(left -> up) } else { combine(up -> left) }`.
 constexpr int K6_THREADS = 256;
+struct TWalk { bool have; u32 child, W, car, v; };
+
+// one level of a walk whose exchange result `other` and record head are already in registers
+__device__ static __forceinline__ void tournament_step(const Bufs &b, TWalk &w, const uint4 head, const unsigned long long other) {
+    if (other == ~0ull) { w.have = false; return; }       // first to arrive: the sibling will pick this up
+    EvRec *e = b.ev + w.v;
+    const bool up = head.z == w.child;                    // childU
+    const u32 stale = head.w & 3u;                        // side of the up-left pixel's cluster (UPLEFT join at an event), 0 = none
+    const u32 Wo = (u32)other, co = (u32)(other >> 32);
+    const u32 WL = up ? Wo : w.W, WU = up ? w.W : Wo;
+    const u32 cL = up ? co : w.car, cU = up ? w.car : co;
+    u32 lwin = 0;
+    if (WL <= WU) {                                       // left loses: its label dies as the left side (builder.rs:313-318)
+        stcg(&b.la[cL].death, w.v | TAG);
+        w.car = cU;
+        if (stale == 1) atomicOr(&b.ctr->err, 2u);
+    } else {
+        stcg(&b.la[cU].death, w.v);
+        w.car = cL;
+        lwin = EV_LWIN;
+        if (stale == 2) atomicOr(&b.ctr->err, 2u);
+    }
+    stcg(&e->arrive, stale | lwin);
+    stcg(&e->a_wl, WL); stcg(&e->b_wu, WU);               // both child areas, for the listing pass
+    w.W = WL + WU + head.y;                               // + cnt(v)
+    w.child = w.v;
+    w.v = head.x;                                         // parE
+}
+__device__ static __forceinline__ void tournament_root(const Bufs &b, TWalk &w) {
+    const u32 root = uf_find(b.la, w.car);                // any leaf of the cluster; ufp is (nearly) flat after k_boruvka's epilogue
+    stcg(&b.la[root].best0, w.car);                       // carrier of the component (best0 is free after K3)
+    stcg(&b.la[root].best1, w.W);                         // final area
+    w.have = false;
+}
+
 __global__ void __launch_bounds__(K6_THREADS) k_tournament(Dims d, Bufs b) {
     const u32 lt = ldcg(&b.ctr->lt);
     const int lane = threadIdx.x & 31;
-    // Every lane walks its own leaf-to-root path one level per iteration; a lane whose walk ends (first to arrive at an
-    // event, or root reached) immediately claims the next leaf from a global counter, so the warp stays full even though
-    // most walks are one level long and a few are thousands.
-    bool have = false;
-    u32 child = 0, W = 0, car = 0, v = NONE;
+    // Every lane walks leaf-to-root paths one level per iteration, TWO walks at a time so that the round trips of one overlap
+    // those of the other; a walk that ends (first to arrive at an event, or root reached) is replaced at once by the next
+    // leaf claimed from a global counter, so the warp stays full although most walks are one level long and a few are
+    // thousands.  Per level: the head of the event record (parE, cnt, childU, stale side) is loaded while the 64-bit exchange
+    // that parks / collects the sibling's (area, carrier) in the (carL, carU) mailbox is in flight: one round trip.
+    TWalk w[2];
+    w[0].have = w[1].have = false;
+    w[0].v = w[1].v = NONE;
     WarpWork ww;
     while (true) {
-        const u32 k = ww.claim(&b.ctr->twork, lt, !have, lane);
-        if (k != NONE) {
-            const u32 leaf = b.leaflist[k];
-            const uint4 la4 = __ldcg(reinterpret_cast<const uint4 *>(&b.la[leaf].cnt));   // cnt, death, label, flabel
-            child = leaf | TAG; W = la4.x; car = leaf;
-            v = ldcg(&b.la[leaf].parL);
-            have = true;
+        // 1. issue the level step of the walks in progress
+        bool act[2];
+        uint4 head[2];
+        unsigned long long other[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            act[s] = w[s].have && w[s].v != NONE;
+            if (act[s]) {
+                EvRec *e = b.ev + w[s].v;
+                head[s] = __ldcg(reinterpret_cast<const uint4 *>(e));
+                other[s] = atomicExch(reinterpret_cast<unsigned long long *>(&e->carL), ((unsigned long long)w[s].car << 32) | w[s].W);
+            }
         }
-        if (!__any_sync(0xffffffffu, have)) {
+        // 2. walks that reached a root; empty slots claim new leaves (their loads overlap the exchanges above)
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            if (w[s].have && !act[s]) tournament_root(b, w[s]);
+            const bool was_empty = !w[s].have;
+            const u32 k = ww.claim(&b.ctr->twork, lt, was_empty, lane);
+            if (k != NONE) {
+                const u32 leaf = b.leaflist[k];
+                w[s].child = leaf | TAG; w[s].W = ldcg(&b.la[leaf].cnt); w[s].car = leaf;
+                w[s].v = ldcg(&b.la[leaf].parL);
+                w[s].have = true;
+            }
+        }
+        // 3. consume the exchanges
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+            if (act[s]) tournament_step(b, w[s], head[s], other[s]);
+        if (!__any_sync(0xffffffffu, w[0].have || w[1].have)) {
             if (ww.exhausted && ww.pos >= ww.end) break;
             continue;
         }
-        const bool drained = ww.exhausted && ww.pos >= ww.end;   // nothing left to claim: finish the own walk in a tight loop
-        while (have) {
-            if (v == NONE) {                              // reached the root of a final cluster
-                const u32 root = uf_find(b.la, car);      // any leaf of the cluster; ufp is (nearly) flat after k_boruvka's epilogue
-                stcg(&b.la[root].best0, car);             // carrier of the component (best0 is free after K3)
-                stcg(&b.la[root].best1, W);               // final area
-                have = false;
-                break;
+        if (ww.exhausted && ww.pos >= ww.end) {
+            // nothing left to claim: finish the own walks in a tight loop
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                while (w[s].have) {
+                    if (w[s].v == NONE) { tournament_root(b, w[s]); break; }
+                    EvRec *e = b.ev + w[s].v;
+                    const uint4 hd = __ldcg(reinterpret_cast<const uint4 *>(e));
+                    const unsigned long long ot = atomicExch(reinterpret_cast<unsigned long long *>(&e->carL), ((unsigned long long)w[s].car << 32) | w[s].W);
+                    tournament_step(b, w[s], hd, ot);
+                }
             }
-            EvRec *e = b.ev + v;
-            // one round trip per level: the head of the record (parE, cnt, childU, stale side) is loaded while the exchange
-            // that parks / collects the sibling's (area, carrier) is in flight.  (carL, carU) = 64-bit mailbox, NONE/NONE = empty.
-            const uint4 head = __ldcg(reinterpret_cast<const uint4 *>(e));
-            const unsigned long long mine = ((unsigned long long)car << 32) | W;
-            const unsigned long long other = atomicExch(reinterpret_cast<unsigned long long *>(&e->carL), mine);
-            if (other == ~0ull) { have = false; break; }  // first to arrive: the sibling will pick this up
-            const bool up = head.z == child;              // childU
-            const u32 stale = head.w & 3u;                // side of the up-left pixel's cluster (UPLEFT join at an event), 0 = none
-            const u32 Wo = (u32)other, co = (u32)(other >> 32);
-            const u32 WL = up ? Wo : W, WU = up ? W : Wo;
-            const u32 cL = up ? co : car, cU = up ? car : co;
-            u32 lwin = 0;
-            if (WL <= WU) {                               // left loses: its label dies as the left side (builder.rs:313-318)
-                stcg(&b.la[cL].death, v | TAG);
-                car = cU;
-                if (stale == 1) atomicOr(&b.ctr->err, 2u);
-            } else {
-                stcg(&b.la[cU].death, v);
-                car = cL;
-                lwin = EV_LWIN;
-                if (stale == 2) atomicOr(&b.ctr->err, 2u);
-            }
-            stcg(&e->arrive, stale | lwin);
-            stcg(&e->a_wl, WL); stcg(&e->b_wu, WU);       // both child areas, for the listing pass
-            W = WL + WU + head.y;                         // + cnt(v)
-            child = v;
-            v = head.x;                                   // parE
-            if (!drained) break;
+            break;
         }
-        if (drained) break;
     }
 }
 

@@ -813,7 +813,10 @@ __global__ void __launch_bounds__(K6_THREADS) k_tournament(Dims d, Bufs b) {
                     if (w[s].v == NONE) { tournament_root(b, w[s]); break; }
                     EvRec *e = b.ev + w[s].v;
                     const uint4 hd = __ldcg(reinterpret_cast<const uint4 *>(e));
-                    const unsigned long long ot = atomicExch(reinterpret_cast<unsigned long long *>(&e->carL), ((unsigned long long)w[s].car << 32) | w[s].W);
+                    const uint4 tl = __ldcg(reinterpret_cast<const uint4 *>(e) + 1);      // a_wl, b_wu, carL, carU (same 32-byte sector)
+                    unsigned long long ot = ((unsigned long long)tl.w << 32) | tl.z;
+                    // a filled mailbox is final (only the sibling writes it, once): consume it without an atomic; otherwise park
+                    if (ot == ~0ull) ot = atomicExch(reinterpret_cast<unsigned long long *>(&e->carL), ((unsigned long long)w[s].car << 32) | w[s].W);
                     tournament_step(b, w[s], hd, ot);
                 }
             }

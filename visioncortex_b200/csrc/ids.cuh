@@ -779,9 +779,11 @@ __global__ void __launch_bounds__(K6_THREADS) k_tournament(Dims d, Bufs b) {
         for (int s = 0; s < 2; ++s) {
             act[s] = w[s].have && w[s].v != NONE;
             if (act[s]) {
-                EvRec *e = b.ev + w[s].v;
+                // the whole 32-byte record in one sector: head (parE, cnt, childU, stale side) + tail (child areas, mailbox)
+                const EvRec *e = b.ev + w[s].v;
                 head[s] = __ldcg(reinterpret_cast<const uint4 *>(e));
-                other[s] = atomicExch(reinterpret_cast<unsigned long long *>(&e->carL), ((unsigned long long)w[s].car << 32) | w[s].W);
+                const uint4 tl = __ldcg(reinterpret_cast<const uint4 *>(e) + 1);
+                other[s] = ((unsigned long long)tl.w << 32) | tl.z;
             }
         }
         // 2. walks that reached a root; empty slots claim new leaves (their loads overlap the exchanges above)
@@ -798,6 +800,11 @@ __global__ void __launch_bounds__(K6_THREADS) k_tournament(Dims d, Bufs b) {
             }
         }
         // 3. consume the exchanges
+        // a filled mailbox is final (only the sibling writes it, once) and is consumed as loaded; an empty one is exchanged
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+            if (act[s] && other[s] == ~0ull)
+                other[s] = atomicExch(reinterpret_cast<unsigned long long *>(&b.ev[w[s].v].carL), ((unsigned long long)w[s].car << 32) | w[s].W);
 #pragma unroll
         for (int s = 0; s < 2; ++s)
             if (act[s]) tournament_step(b, w[s], head[s], other[s]);

@@ -536,7 +536,9 @@ __global__ void __launch_bounds__(K4_THREADS) k_chain_insert(Dims d, Bufs b) {
         }
         const bool drained = ww.exhausted && ww.pos >= ww.end;   // nothing left to claim: finish the own walk in a tight loop
         while (have) {
-            const u32 old = atomicMin(slot, g);           // one round trip per step
+            // walking up past lighter ancestors needs only loads; the atomic is issued when g has to be installed
+            u32 old = ldcg(slot);
+            if (old > g) old = atomicMin(slot, g);
             if (old == g || old == NONE) { have = false; break; }
             if (old > g) { slot = &b.ev[g].parE; g = old; }   // installed g below `old`: now insert the displaced ancestor above g
             else slot = &b.ev[old].parE;                  // a lighter ancestor is already there: g is also its ancestor

@@ -427,10 +427,14 @@ __global__ void __launch_bounds__(K3_THREADS) k_boruvka(Bufs b) {
             const u32 ra = uf_find(b.la, b.ea[e]), rb = uf_find(b.la, b.eb[e]);
             if (ra == rb) { b.cand[e] = p | TAG; continue; }
             b.ea[e] = ra; b.eb[e] = rb;
+            // (best0, best1) sit in one sector: one load tells whether this edge can still win and whether the other
+            // parity still has to be cleared, so most edges of a big component issue no atomic and no store at all
             u32 *ba = par ? &b.la[ra].best1 : &b.la[ra].best0, *bb = par ? &b.la[rb].best1 : &b.la[rb].best0;
-            atomicMin(ba, p); atomicMin(bb, p);
-            stcg(par ? &b.la[ra].best0 : &b.la[ra].best1, NONE);
-            stcg(par ? &b.la[rb].best0 : &b.la[rb].best1, NONE);
+            u32 *oa = par ? &b.la[ra].best0 : &b.la[ra].best1, *ob = par ? &b.la[rb].best0 : &b.la[rb].best1;
+            if (ldcg(ba) > p) atomicMin(ba, p);
+            if (ldcg(bb) > p) atomicMin(bb, p);
+            if (ldcg(oa) != NONE) stcg(oa, NONE);
+            if (ldcg(ob) != NONE) stcg(ob, NONE);
             any = true;
         }
         if (any) stcg(&b.ctr->live[par], 1u);

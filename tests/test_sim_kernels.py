@@ -93,3 +93,20 @@ def test_sim_hierarchical_and_banded(sim, oracle):
         assert_same_clusters(got, ref, pools=True, ctx=f"hier {k}")
         got2 = runner_run_banded(ctxs, img, cfg, pools=False)
         assert_same_clusters(got2, ref, pools=False, ctx=f"banded {k}")
+
+
+def test_sim_batch_matches_single(sim, oracle):
+    """several images in one launch sequence: per-image slot ranges, list offsets and the fused NEW / leaf compaction
+    across image boundaries (one image is keyed away completely and owns a single slot)."""
+    from visioncortex_b200.runtime import make_config
+
+    rng = np.random.default_rng(44)
+    for hier in (0, 0xFFFFFFFF):
+        imgs = [rng.integers(0, 4, size=(13, 18, 4), dtype=np.uint8) * 60 for _ in range(4)]
+        imgs[2][:] = (0, 0, 0, 0)
+        imgs[2][..., 3] = 0
+        cfg = make_config(hierarchical=hier, is_same_color_a=0, is_same_color_b=1)
+        got = sim.runner_run_batch(imgs, cfg, pools=True)
+        for k, im in enumerate(imgs):
+            ref = oracle.runner_run(im, cfg, pools=True)
+            assert_same_clusters(got[k], ref, pools=True, ctx=f"hier {hier} image {k}")

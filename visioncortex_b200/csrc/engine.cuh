@@ -243,8 +243,20 @@ inline int run_stage1(vcb_ctx *c, const Dims &d, const P &pol, u32 base, bool wa
             rt::launch(ck->st, "k_flatten_events", rt::THR, k_flatten_events, dim3(grid_for(ck, p1 - p0, K2_THREADS, 16)), dim3(K2_THREADS), 0, d, b, p0, p1);
     }
     if (multi) { const int e = sync_devices(ds); if (e) return e; }
-    prims::scan(st, "scan_new", NewScan{d, b}, c->chunksum, d.N, c->sms * 8);
-    prims::scan(st, "scan_new", LeafScan{d, b}, c->chunksum, d.N, c->sms * 8);
+    {
+        static const bool plain = getenv("VCB_NO_FUSED_SCAN") != nullptr;
+        if (plain) {
+            prims::scan(st, "scan_new", NewScan{d, b}, c->chunksum, d.N, c->sms * 8);
+            prims::scan(st, "scan_new", LeafScan{d, b}, c->chunksum, d.N, c->sms * 8);
+        } else {
+            u64 *cs = reinterpret_cast<u64 *>(c->rs_table);           // free until the first sort
+            const u32 nchunks = (d.N + NL_CHUNK - 1) / NL_CHUNK;
+            const u32 grid = std::min<u32>(nchunks, (u32)c->sms * 8);
+            rt::launch(st, "scan_new", rt::THR, k_newleaf_sums, dim3(grid), dim3(NL_THREADS), 128, d, b, cs);
+            rt::launch(st, "scan_new", rt::THR, k_newleaf_chunks, dim3(1), dim3(NL_THREADS), 128, d, cs);
+            rt::launch(st, "scan_new", rt::THR, k_newleaf_apply, dim3(grid), dim3(NL_THREADS), 128, d, b, cs);
+        }
+    }
     {
         static int coop_blocks = 0;
         if (!coop_blocks) coop_blocks = rt::max_coop_blocks((const void *)k_boruvka, K3_THREADS, 0, c->device);
@@ -335,9 +347,16 @@ inline int build_records(vcb_ctx *c, const Dims &d, const std::vector<ImgMeta> &
     rt::launch(st, "k_rec_accum", rt::SEQ, k_rec_accum, dim3(grid_for(c, d.N / 4, REC_THREADS, 16)), dim3(REC_THREADS), 0, d, b, res->rec, res->d_slot_base);
     if (keep_key)
         rt::launch(st, "k_rec_key", rt::SEQ, k_rec_key, dim3((d.nimg + 127) / 128), dim3(128), 0, d, b, res->rec, res->d_slot_base);
-    prims::scan(st, "scan_off", OffScanFinal{res->rec, total}, c->chunksum, total, c->sms * 8);
-    rt::launch(st, "k_off_rebase", rt::SEQ, k_off_rebase, dim3(g), dim3(REC_THREADS), 0, res->rec, res->d_slot_base, res->d_slot_img, total);
-    rt::launch(st, "k_off_rebase0", rt::SEQ, k_off_rebase0, dim3((d.nimg + 127) / 128), dim3(128), 0, res->rec, res->d_slot_base, d.nimg);
+    {
+        u32 *d_img_base = c->d_small + 2 * (d.nimg + 2);   // nimg entries; the counters below use the first 2 * (nimg + 2)
+        prims::scan_prefixes(st, "scan_off", OffScanFinal{res->rec, total}, c->chunksum, total, c->sms * 8);
+        rt::launch(st, "k_img_base", rt::THR, k_img_base, dim3((d.nimg * 32 + REC_THREADS - 1) / REC_THREADS), dim3(REC_THREADS), 0,
+                   (const vcb_cluster_rec *)res->rec, (const u32 *)res->d_slot_base, d.nimg, (const u32 *)c->chunksum, d_img_base);
+        const u32 nchunks = (total + prims::SCAN_CHUNK - 1) / prims::SCAN_CHUNK;
+        const u32 gf = std::max<u32>(1, std::min<u32>(nchunks, (u32)c->sms * 8));
+        rt::launch(st, "k_rec_finalize", rt::THR, k_rec_finalize, dim3(gf), dim3(REC_THREADS), RF_SMEM, res->rec, total,
+                   (const u32 *)c->chunksum, (const u32 *)res->d_slot_img, (const u32 *)d_img_base);
+    }
 
     res->nout.assign(d.nimg, 0);
     res->indices_total.assign(d.nimg, 0);

@@ -355,12 +355,34 @@ __global__ void __launch_bounds__(K2_THREADS) k_flatten_events4(Dims d, Bufs b, 
         if (grp < groups) {
             const u32 g4 = grp * 4;
             const u32 f4 = *reinterpret_cast<const u32 *>(b.flags + g4);
+            // bit 8k set: pixel k still needs the global resolution (joined, and its tile-local root is not a NEW pixel)
+            u32 open = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const u32 f = (f4 >> (8 * k)) & 255u;
-                if ((f & J_MASK) != J_NONE && !(f & F_FINAL)) stcg(b.pc + g4 + k, pc_root(b.pc, g4 + k));
+                if ((f & J_MASK) != J_NONE && !(f & F_FINAL)) open |= 1u << k;
             }
-            if (f4 & 0x08080808u) {                       // some pixel carries a merge flag (implies a row above)
+            const bool any_m = (f4 & 0x08080808u) != 0;
+            u32 root[4] = {NONE, NONE, NONE, NONE};
+            if (open || (f4 & 0x08080800u)) {             // own leaves are needed: to be resolved, or as the left side of an event
+                const uint4 raw = *reinterpret_cast<const uint4 *>(b.pc + g4);
+                root[0] = raw.x; root[1] = raw.y; root[2] = raw.z; root[3] = raw.w;
+                // neighbouring pixels of one region share the tile-local root: walk each distinct chain once
+                u32 last_raw = NONE, last_root = NONE;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (!(open & (1u << k))) continue;
+                    const u32 rw = root[k];
+                    if (rw != last_raw) {
+                        u32 r = rw;
+                        while (true) { const u32 t = ldcg(b.pc + r); if (t == r) break; r = t; }
+                        last_raw = rw; last_root = r;
+                    }
+                    root[k] = last_root;
+                    stcg(b.pc + g4 + k, last_root);
+                }
+            }
+            if (any_m) {                                  // some pixel carries a merge flag (implies a row above)
                 const u32 fu4 = *reinterpret_cast<const u32 *>(b.flags + g4 - d.w);
                 u32 fleft = 0;
                 if (f4 & F_M) fleft = b.flags[g4 - 1];
@@ -372,7 +394,9 @@ __global__ void __launch_bounds__(K2_THREADS) k_flatten_events4(Dims d, Bufs b, 
                     const u32 fu = (fu4 >> (8 * k)) & 255u;
                     if ((fl & J_MASK) == J_UP && (fu & J_MASK) == J_UP && (fu & F_M)) continue;   // duplicate of the event one row up
                     const u32 g = g4 + k;
-                    const u32 ea = pc_root_f(b.pc, b.flags, g - 1), eb = pc_root_f(b.pc, b.flags, g - d.w);
+                    // a merge flag implies joined (non-keyed / set) left and up pixels, so both have a leaf
+                    const u32 ea = k ? root[k - 1] : ((fl & F_FINAL) ? ldcg(b.pc + g - 1) : pc_root(b.pc, g - 1));
+                    const u32 eb = (fu & F_FINAL) ? ldcg(b.pc + g - d.w) : pc_root(b.pc, g - d.w);
                     if (ea != eb) { cg[ncand] = g; ca[ncand] = ea; cb[ncand] = eb; ++ncand; }
                 }
             }
@@ -713,6 +737,73 @@ struct NewScan {
     }
 };
 
+// Both compactions in one two-pass scan: 8 flag bytes per thread read as one 64-bit word, (NEW events, real leaves)
+// counted side by side in the two halves of a 64-bit sum.  Used for whole batches; NewScan / LeafScan remain the
+// restatement the simulator tests compare against (VCB_NO_FUSED_SCAN=1).
+constexpr int NL_THREADS = 256, NL_ITEMS = 8, NL_CHUNK = NL_THREADS * NL_ITEMS;
+__device__ static __forceinline__ u64 nl_load(const Bufs &b, u32 i0, u32 cnt) {
+    if (i0 + NL_ITEMS <= cnt) return *reinterpret_cast<const u64 *>(b.flags + i0);
+    u64 w = 0;
+    for (int k = 0; k < NL_ITEMS; ++k) w |= (u64)((i0 + k < cnt) ? b.flags[i0 + k] : (u8)J_NONE) << (8 * k);
+    return w;
+}
+__device__ static __forceinline__ u64 nl_count(u64 w) {
+    u64 s = 0;
+#pragma unroll
+    for (int k = 0; k < NL_ITEMS; ++k) {
+        const u32 j = (u32)(w >> (8 * k)) & J_MASK;
+        s += (j == J_NEW ? 0x100000001ull : 0ull) + (j == J_RUP ? 1ull : 0ull);   // low half: NEW events, high half: leaves
+    }
+    return s;
+}
+__global__ void __launch_bounds__(NL_THREADS) k_newleaf_sums(Dims d, Bufs b, u64 *chunksum) {
+    VCB_SMEM(u64, sh);
+    const u32 nchunks = (d.N + NL_CHUNK - 1) / NL_CHUNK;
+    for (u32 c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const u32 i0 = c * NL_CHUNK + threadIdx.x * NL_ITEMS;
+        u64 total;
+        prims::block_exscan(nl_count(nl_load(b, i0, d.N)), sh, &total);
+        if (threadIdx.x == 0) chunksum[c] = total;
+    }
+}
+__global__ void __launch_bounds__(NL_THREADS) k_newleaf_chunks(Dims d, u64 *chunksum) {
+    VCB_SMEM(u64, sh);
+    const u32 nchunks = (d.N + NL_CHUNK - 1) / NL_CHUNK;
+    u64 carry = 0;
+    for (u32 base = 0; base < nchunks; base += NL_THREADS) {
+        const u32 i = base + threadIdx.x;
+        const u64 v = i < nchunks ? chunksum[i] : 0;
+        u64 total;
+        const u64 ex = prims::block_exscan(v, sh, &total);
+        if (i < nchunks) chunksum[i] = carry + ex;
+        carry += total;
+    }
+}
+__global__ void __launch_bounds__(NL_THREADS) k_newleaf_apply(Dims d, Bufs b, const u64 *chunkpref) {
+    VCB_SMEM(u64, sh);
+    const u32 nchunks = (d.N + NL_CHUNK - 1) / NL_CHUNK;
+    for (u32 c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const u32 i0 = c * NL_CHUNK + threadIdx.x * NL_ITEMS;
+        const u64 w = nl_load(b, i0, d.N);
+        u64 total;
+        const u64 ex = prims::block_exscan(nl_count(w), sh, &total) + chunkpref[c];
+        u32 xn = (u32)ex, xl = (u32)(ex >> 32);
+        // image starts inside this thread's 8 pixels (at most a few per launch: the division runs once per thread)
+        u32 img_next = i0 < d.N ? (i0 + d.n - 1) / d.n : 0;        // first image starting at or after i0
+        u32 next_start = img_next * d.n;
+#pragma unroll
+        for (int k = 0; k < NL_ITEMS; ++k) {
+            const u32 i = i0 + k;
+            if (i >= d.N) break;
+            if (i == next_start) { b.meta[img_next].leaf_begin = xn; ++img_next; next_start += d.n; }
+            const u32 j = (u32)(w >> (8 * k)) & J_MASK;
+            if (j == J_NEW) { b.newlist[xn++] = i; b.leaflist[xl++] = i; }
+            else if (j == J_RUP) b.newlist[xn++] = i | TAG;
+            if (i == d.N - 1) { b.ctr->kt = xn; b.ctr->lt = xl; }
+        }
+    }
+}
+
 // ordered compaction of the real leaves only (the per-leaf kernels run over this list)
 struct LeafScan {
     Dims d; Bufs b;
@@ -856,6 +947,9 @@ struct LabelScan {
         if (nxt / d.n != img) return 0u;
         return (death & ~TAG) <= nxt ? 0u : 1u;
     }
+    // the first pass parks the value in labex[] (rewritten by emit) so that the second pass does not chase death again
+    __device__ u32 value_first(u32 k) const { const u32 v = value(k); b.labex[k] = v; return v; }
+    __device__ u32 value_again(u32 k) const { return b.labex[k]; }
     __device__ void emit(u32 k, u32 ex, u32 v) const {
         const u32 e = b.newlist[k];
         b.labex[k] = ex;

@@ -15,33 +15,39 @@ constexpr int SCAN_CHUNK = SCAN_THREADS * SCAN_ITEMS;   // 2048
 
 // Exclusive scan of one value per thread across a 256-thread block.  `sh` needs 9 u32.  Returns the exclusive prefix;
 // *total receives the block sum.
-__device__ static __forceinline__ u32 block_exscan(u32 v, u32 *sh, u32 *total) {
+template <class T> __device__ static __forceinline__ T block_exscan(T v, T *sh, T *total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u32 inc = v;
+    T inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        u32 t = __shfl_up_sync(0xffffffffu, inc, d);
+        T t = __shfl_up_sync(0xffffffffu, inc, d);
         if (lane >= d) inc += t;
     }
     if (lane == 31) sh[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-        u32 w = lane < (SCAN_THREADS / 32) ? sh[lane] : 0;
-        u32 winc = w;
+        T w = lane < (SCAN_THREADS / 32) ? sh[lane] : 0;
+        T winc = w;
 #pragma unroll
         for (int d = 1; d < 8; d <<= 1) {
-            u32 t = __shfl_up_sync(0xffffffffu, winc, d);
+            T t = __shfl_up_sync(0xffffffffu, winc, d);
             if (lane >= d) winc += t;
         }
         if (lane < (SCAN_THREADS / 32)) sh[lane] = winc - w;
         if (lane == (SCAN_THREADS / 32) - 1) sh[8] = winc;
     }
     __syncthreads();
-    u32 res = sh[warp] + inc - v;
+    T res = sh[warp] + inc - v;
     *total = sh[8];
     __syncthreads();
     return res;
 }
+
+// optional functor methods: value_first(i) in the summing pass, value_again(i) in the applying pass (default: value(i))
+template <class F> __device__ static __forceinline__ auto scan_value_first(const F &f, u32 i, int) -> decltype(f.value_first(i)) { return f.value_first(i); }
+template <class F> __device__ static __forceinline__ u32 scan_value_first(const F &f, u32 i, long) { return f.value(i); }
+template <class F> __device__ static __forceinline__ auto scan_value_again(const F &f, u32 i, int) -> decltype(f.value_again(i)) { return f.value_again(i); }
+template <class F> __device__ static __forceinline__ u32 scan_value_again(const F &f, u32 i, long) { return f.value(i); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // Functor protocol for scans:  u32 F::count() const  (number of items; may read device memory)
@@ -57,7 +63,7 @@ template <class F> __global__ void k_scan_sums(F f, u32 *chunksum) {
         u32 s = 0;
 #pragma unroll
         for (int k = 0; k < SCAN_ITEMS; ++k)
-            if (i0 + k < cnt) s += f.value(i0 + k);
+            if (i0 + k < cnt) s += scan_value_first(f, i0 + k, 0);
         u32 total;
         block_exscan(s, sh, &total);
         if (threadIdx.x == 0) chunksum[c] = total;
@@ -91,7 +97,7 @@ template <class F> __global__ void k_scan_apply(F f, const u32 *chunkpref) {
         u32 s = 0;
 #pragma unroll
         for (int k = 0; k < SCAN_ITEMS; ++k) {
-            v[k] = (i0 + k < cnt) ? f.value(i0 + k) : 0;
+            v[k] = (i0 + k < cnt) ? scan_value_again(f, i0 + k, 0) : 0;
             s += v[k];
         }
         u32 total;
@@ -112,6 +118,15 @@ template <class F> inline void scan(rt::Stream &st, const char *name, F f, u32 *
     rt::launch(st, name, rt::THR, k_scan_sums<F>, dim3(grid), dim3(SCAN_THREADS), 64, f, chunksum);
     rt::launch(st, name, rt::THR, k_scan_chunks<F>, dim3(1), dim3(SCAN_THREADS), 64, f, chunksum);
     rt::launch(st, name, rt::THR, k_scan_apply<F>, dim3(grid), dim3(SCAN_THREADS), 64, f, chunksum);
+}
+
+// first two passes only: chunksum[c] = exclusive prefix of chunk c, chunksum[nchunks] = total; the caller applies them
+template <class F> inline void scan_prefixes(rt::Stream &st, const char *name, F f, u32 *chunksum, u32 max_items, int grid_cap) {
+    u32 maxchunks = (max_items + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    if (maxchunks == 0) maxchunks = 1;
+    const u32 grid = maxchunks < (u32)grid_cap ? maxchunks : (u32)grid_cap;
+    rt::launch(st, name, rt::THR, k_scan_sums<F>, dim3(grid), dim3(SCAN_THREADS), 64, f, chunksum);
+    rt::launch(st, name, rt::THR, k_scan_chunks<F>, dim3(1), dim3(SCAN_THREADS), 64, f, chunksum);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -8,16 +8,18 @@ namespace vcb {
 
 constexpr int REC_THREADS = 256;
 
-// per slot: zero, rect sentinels for the atomic min/max accumulation
+// per slot: zero, rect sentinels for the atomic min/max accumulation.  The array is written as a flat run of 16-byte words
+// (a record is six of them: words 10-11 = rect left/top = INT_MAX, words 12-13 = rect right/bottom = -1).
+static_assert(sizeof(vcb_cluster_rec) == 96, "record layout");
 __global__ void __launch_bounds__(REC_THREADS) k_rec_init(vcb_cluster_rec *rec, u32 total) {
-    const u32 stride = gridDim.x * REC_THREADS;
-    for (u32 s = blockIdx.x * REC_THREADS + threadIdx.x; s < total; s += stride) {
-        vcb_cluster_rec r;
-        for (int k = 0; k < 5; ++k) { r.sum[k] = 0; r.residue_sum[k] = 0; }
-        r.rect[0] = 0x7fffffff; r.rect[1] = 0x7fffffff; r.rect[2] = -1; r.rect[3] = -1;
-        r.num_holes = 0; r.depth = 0; r.merged_into = 0; r.indices_len = 0; r.indices_off = 0; r.holes_off = 0;
-        r.holes_len = 0; r._pad = 0;
-        rec[s] = r;
+    uint4 *p = reinterpret_cast<uint4 *>(rec);
+    const u64 nvec = (u64)total * 6, stride = (u64)gridDim.x * REC_THREADS;
+    for (u64 i = (u64)blockIdx.x * REC_THREADS + threadIdx.x; i < nvec; i += stride) {
+        const u32 q = (u32)(i % 6);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (q == 2) { v.z = 0x7fffffffu; v.w = 0x7fffffffu; }
+        else if (q == 3) { v.x = 0xffffffffu; v.y = 0xffffffffu; }
+        p[i] = v;
     }
 }
 
@@ -81,6 +83,59 @@ struct OffScanFinal {
     }
 };
 
+// total area of the images before image i (= global exclusive prefix at the image's first slot): the prefix of the 2048-slot
+// chunk the slot lies in plus the areas between the chunk start and the slot.  One warp per image.
+__global__ void __launch_bounds__(REC_THREADS) k_img_base(const vcb_cluster_rec *rec, const u32 *slot_base, u32 nimg,
+                                                          const u32 *chunkpref, u32 *img_base) {
+    const u32 img = (blockIdx.x * REC_THREADS + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (img >= nimg) return;                               // whole warps
+    const u32 s1 = slot_base[img], c = s1 / (u32)prims::SCAN_CHUNK;
+    u32 acc = 0;
+    for (u32 s = c * (u32)prims::SCAN_CHUNK + lane; s < s1; s += 32) acc += rec[s].sum[4];
+#pragma unroll
+    for (int dlt = 16; dlt; dlt >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, dlt);
+    if (lane == 0) img_base[img] = chunkpref[c] + acc;      // c == number of chunks is the grand total (k_scan_chunks)
+}
+
+// Last pass of the stage-1 record scan (OffScanFinal::emit for every slot, rebased per image) with the records moved
+// through shared memory: 256 records = 1536 16-byte words are loaded and stored fully coalesced, each thread edits its own.
+constexpr int RF_WORDS = 24;
+constexpr size_t RF_SMEM = (size_t)REC_THREADS * RF_WORDS * 4 + 64;
+__global__ void __launch_bounds__(REC_THREADS) k_rec_finalize(vcb_cluster_rec *rec, u32 total, const u32 *chunkpref,
+                                                              const u32 *slot_img, const u32 *img_base) {
+    VCB_SMEM(u32, sm);
+    u32 *sh = sm + REC_THREADS * RF_WORDS;
+    uint4 *sm4 = reinterpret_cast<uint4 *>(sm);
+    const u32 nchunks = (total + prims::SCAN_CHUNK - 1) / prims::SCAN_CHUNK;
+    for (u32 c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        u32 carry = chunkpref[c];
+        for (u32 s0 = c * (u32)prims::SCAN_CHUNK; s0 < (c + 1) * (u32)prims::SCAN_CHUNK && s0 < total; s0 += REC_THREADS) {
+            const u32 cnt = total - s0 < (u32)REC_THREADS ? total - s0 : (u32)REC_THREADS;
+            uint4 *g4 = reinterpret_cast<uint4 *>(rec + s0);
+            for (u32 i = threadIdx.x; i < cnt * 6; i += REC_THREADS) sm4[i] = g4[i];
+            __syncthreads();
+            u32 *r = sm + threadIdx.x * RF_WORDS;
+            const bool mine = threadIdx.x < cnt;
+            const u32 v = mine ? r[4] : 0u;
+            u32 tot;
+            const u32 ex = prims::block_exscan(v, sh, &tot) + carry;
+            if (mine) {
+                if (v == 0) { r[10] = r[11] = r[12] = r[13] = 0; }
+                else { r[12] += 1; r[13] += 1; }
+#pragma unroll
+                for (int k = 0; k < 5; ++k) r[5 + k] = r[k];
+                r[17] = v;
+                r[18] = ex - img_base[slot_img[s0 + threadIdx.x]]; r[19] = 0;
+            }
+            __syncthreads();
+            for (u32 i = threadIdx.x; i < cnt * 6; i += REC_THREADS) g4[i] = sm4[i];
+            __syncthreads();
+            carry += tot;
+        }
+    }
+}
+
 // indices_off: exclusive scan of indices_len inside each image; live count per image
 struct OffScan {
     vcb_cluster_rec *rec; const u32 *slot_base; const u32 *slot_img; u32 total; u64 *img_off;
@@ -98,7 +153,7 @@ __global__ void __launch_bounds__(REC_THREADS) k_off_rebase(vcb_cluster_rec *rec
 }
 __global__ void k_off_rebase0(vcb_cluster_rec *rec, const u32 *slot_base, u32 nimg) {
     const u32 img = blockIdx.x * blockDim.x + threadIdx.x;
-    if (img < nimg) rec[slot_base[img]].indices_off = 0;
+    if (img < nimg && slot_base[img] < slot_base[img + 1]) rec[slot_base[img]].indices_off = 0;   // an image may own no slot at all
 }
 __global__ void __launch_bounds__(REC_THREADS) k_slot_img(u32 *slot_img, const u32 *slot_base, u32 nimg) {
     // slot_img[s] = image owning slot s

@@ -304,8 +304,10 @@ int vcb_runner_run_batch_host(vcb_ctx *c, const vcb_runner_config *cfg, const ui
         if (rt::stream_create(c->st_h2d) != 0 || rt::stream_create(c->st_d2h) != 0) return fail(c, VCB_ERR_CUDA, "stream creation failed");
         c->pipe_ready = true;
     }
-    // sub-batches: at least 4 per call so that the copies overlap the compute, at most MAX_CHUNK_PX pixels each
-    size_t per = (size_t)std::max<u64>(1, std::min<u64>((n + 3) / 4, MAX_CHUNK_PX / npx));
+    // sub-batches: 8 per call (VCB_HOST_CHUNKS) so that the copies overlap the compute, at most MAX_CHUNK_PX pixels each
+    u64 want_chunks = 8;
+    if (const char *ev = getenv("VCB_HOST_CHUNKS")) want_chunks = std::max<u64>(1, (u64)atoll(ev));
+    size_t per = (size_t)std::max<u64>(1, std::min<u64>((n + want_chunks - 1) / want_chunks, MAX_CHUNK_PX / npx));
     const size_t bytes_img = (size_t)npx * 4;
     if (per * bytes_img > c->d_in_cap) {
         rt::dev_free(c->d_in[0]); rt::dev_free(c->d_in[1]);

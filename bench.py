@@ -25,7 +25,7 @@ W, H = 1920, 1080
 NPX = W * H
 ALGO_BYTES_PER_PX = 8          # RGBA8 read once + u32 cluster_indices written once
 KERNELS = ["k_meta_init", "k_edges_tile", "k_flatten_events", "k_boruvka", "k_chain_insert", "scan_new", "k_attribute",
-           "k_tournament", "scan_label", "k_image_meta", "k_leaf_labels", "k_leaf_final", "k_labels", "k_rec_init",
+           "k_tournament", "scan_label", "k_image_meta", "k_leaf_final", "k_labels", "k_rec_init",
            "k_slot_img", "k_rec_accum", "k_rec_key", "k_rec_final", "scan_off", "k_img_base", "k_rec_finalize", "k_off_rebase", "k_off_rebase0",
            "k_out_keys", "rs_hist", "rs_scan", "rs_scatter"]
 

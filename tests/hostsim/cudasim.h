@@ -33,6 +33,8 @@ struct dim3 {
 };
 struct uint4 { unsigned x, y, z, w; };
 struct uint2 { unsigned x, y; };
+struct int2 { int x, y; };
+static inline int2 make_int2(int a, int b) { return int2{a, b}; }
 struct uchar4 { unsigned char x, y, z, w; };
 static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return uint4{a, b, c, d}; }
 static inline uint2 make_uint2(unsigned a, unsigned b) { return uint2{a, b}; }
@@ -159,6 +161,16 @@ static inline int __all_sync(unsigned m, int p) {
     int n = (int)std::min<unsigned>(32, blockDim.x * blockDim.y * blockDim.z - sim::tc.warp * 32);
     unsigned full = n == 32 ? 0xffffffffu : ((1u << n) - 1);
     return __ballot_sync(m, p) == full;
+}
+static inline unsigned __vabsdiffu4(unsigned a, unsigned b) {
+    unsigned r = 0;
+    for (int k = 0; k < 4; ++k) { int x = (a >> (8 * k)) & 255, y = (b >> (8 * k)) & 255; r |= (unsigned)(x > y ? x - y : y - x) << (8 * k); }
+    return r;
+}
+static inline unsigned __vsubus4(unsigned a, unsigned b) {
+    unsigned r = 0;
+    for (int k = 0; k < 4; ++k) { int x = (a >> (8 * k)) & 255, y = (b >> (8 * k)) & 255; r |= (unsigned)(x > y ? x - y : 0) << (8 * k); }
+    return r;
 }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }

@@ -344,3 +344,17 @@ def test_invalid_arguments(gpu):
         assert e.value.status == 1
     res = gpu.runner_run(img, make_config(hierarchical=0, is_same_color_a=7), pools=False)   # still usable afterwards
     assert res["num_slots"] >= 2
+
+
+def test_colour_threshold_extremes(gpu, oracle):
+    """color_same (runner.rs:116-129) over its whole parameter range, on the byte-wise SIMD path of the tile kernel."""
+    from visioncortex_b200.runtime import make_config
+
+    rng = np.random.default_rng(45)
+    img = rng.integers(0, 256, size=(90, 130, 4), dtype=np.uint8)
+    img[20:60, 30:100] = (img[20:60, 30:100] // 64) * 64
+    for shift, thres in [(0, -1), (0, 300), (0, 255), (0, 254), (7, 0), (7, 1), (3, 5), (1, 127), (0, 0), (2, 3)]:
+        cfg = make_config(hierarchical=0, is_same_color_a=shift, is_same_color_b=thres)
+        ref = oracle.runner_run(img, cfg, pools=True)
+        got = gpu.runner_run(img, cfg, pools=True)
+        assert_same_clusters(got, ref, pools=True, ctx=f"shift {shift} thres {thres}")

@@ -110,3 +110,17 @@ def test_sim_batch_matches_single(sim, oracle):
         for k, im in enumerate(imgs):
             ref = oracle.runner_run(im, cfg, pools=True)
             assert_same_clusters(got[k], ref, pools=True, ctx=f"hier {hier} image {k}")
+
+
+def test_sim_colour_threshold_extremes(sim, oracle):
+    """color_same (runner.rs:116-129) at the ends of its parameter range: the byte-wise SIMD restatement must agree for a
+    negative threshold (nothing is the same colour), one above 255 (everything is) and every shift."""
+    from visioncortex_b200.runtime import make_config
+
+    rng = np.random.default_rng(45)
+    img = rng.integers(0, 256, size=(11, 14, 4), dtype=np.uint8)
+    for shift, thres in [(0, -1), (0, 300), (0, 255), (0, 254), (7, 0), (7, 1), (3, 5), (1, 127), (0, 0)]:
+        cfg = make_config(hierarchical=0, is_same_color_a=shift, is_same_color_b=thres)
+        ref = oracle.runner_run(img, cfg, pools=True)
+        got = sim.runner_run(img, cfg, pools=True)
+        assert_same_clusters(got, ref, pools=True, ctx=f"shift {shift} thres {thres}")

@@ -295,8 +295,7 @@ inline int run_stage1(vcb_ctx *c, const Dims &d, const P &pol, u32 base, bool wa
     rt::launch(st, "k_tournament", rt::THR, k_tournament, dim3(grid_for(c, d.N / 4, K6_THREADS, 16)), dim3(K6_THREADS), 0, d, b);
     prims::scan(st, "scan_label", LabelScan{d, b}, c->chunksum, d.N, c->sms * 8);
     rt::launch(st, "k_image_meta", rt::SEQ, k_image_meta, dim3(g_img), dim3(128), 0, d, b, base);
-    rt::launch(st, "k_leaf_labels", rt::SEQ, k_leaf_labels, dim3(grid_for(c, d.N / 4, K8_THREADS, 16)), dim3(K8_THREADS), 0, d, b, base);
-    rt::launch(st, "k_leaf_final", rt::SEQ, k_leaf_final, dim3(grid_for(c, d.N / 4, K8_THREADS, 16)), dim3(K8_THREADS), 0, d, b);
+    rt::launch(st, "k_leaf_final", rt::SEQ, k_leaf_final, dim3(grid_for(c, d.N / 4, K8_THREADS, 16)), dim3(K8_THREADS), 0, d, b, base);
     if (res->labels) {
         if (multi) { const int e = sync_devices(ds); if (e) return e; }
         for (int k = 0; k < ds.n; ++k) {

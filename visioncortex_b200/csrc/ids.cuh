@@ -68,15 +68,17 @@ struct ColorPolicy {
     u32 key;
 
     __device__ __forceinline__ u32 load(u32 g) const { return __ldg(rgba + g); }
-    // color_same (color_clusters/runner.rs:116-129): alpha ignored
+    // color_same (color_clusters/runner.rs:116-129): alpha ignored.  The three channel tests run as one byte-wise SIMD
+    // absolute difference: m4 keeps the shifted r, g, b bytes (alpha cleared), t4 holds the threshold in every byte.
+    u32 m4, t4;
+    __host__ __device__ void prepare() {
+        m4 = 0x00010101u * (u32)(255 >> shift);
+        t4 = 0x00010101u * (u32)(thres > 255 ? 255 : (thres < 0 ? 0 : thres));
+    }
     __device__ __forceinline__ bool same(u32 a, u32 b) const {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const int x = (int)((a >> (8 * c)) & 255u) >> shift, y = (int)((b >> (8 * c)) & 255u) >> shift;
-            const int dlt = x - y;
-            if ((dlt < 0 ? -dlt : dlt) > thres) return false;
-        }
-        return true;
+        if (thres < 0) return false;                      // |x - y| > thres always
+        const u32 dlt = __vabsdiffu4((a >> shift) & m4, (b >> shift) & m4);
+        return __vsubus4(dlt, t4) == 0u;                  // no byte exceeds the threshold
     }
     // builder.rs:286-354 restated as static predicates
     __device__ __forceinline__ u32 classify(u32 c, u32 up, u32 left, u32 ul, bool vu, bool vl, u32 *err) const {
@@ -977,25 +979,16 @@ __global__ void k_image_meta(Dims d, Bufs b, u32 base) {
     b.meta[img].maxlabel = maxlabel;
 }
 
-// per leaf: image-relative label
 constexpr int K8_THREADS = 256;
-__global__ void __launch_bounds__(K8_THREADS) k_leaf_labels(Dims d, Bufs b, u32 base) {
-    const u32 lt = ldcg(&b.ctr->lt);
-    const u32 stride = gridDim.x * K8_THREADS;
-    for (u32 k = blockIdx.x * K8_THREADS + threadIdx.x; k < lt; k += stride) {
-        const u32 p = b.leaflist[k];
-        b.la[p].label = base + b.la[p].label - b.meta[p / d.n].notd_base;
-    }
-}
-// per leaf: label of the carrier of its final cluster
-__global__ void __launch_bounds__(K8_THREADS) k_leaf_final(Dims d, Bufs b) {
+// per leaf: image-relative label of the carrier of its final cluster (la[].label holds the raw scan value of LabelScan)
+__global__ void __launch_bounds__(K8_THREADS) k_leaf_final(Dims d, Bufs b, u32 base) {
     const u32 lt = ldcg(&b.ctr->lt);
     const u32 stride = gridDim.x * K8_THREADS;
     for (u32 k = blockIdx.x * K8_THREADS + threadIdx.x; k < lt; k += stride) {
         const u32 p = b.leaflist[k];
         const u32 root = uf_find(b.la, p);
         const u32 car = ldcg(&b.la[root].best0);
-        b.la[p].flabel = ldcg(&b.la[car].label);
+        b.la[p].flabel = base + ldcg(&b.la[car].label) - b.meta[p / d.n].notd_base;
     }
 }
 // per pixel: cluster_indices (builder.rs:161; label 0 for keyed pixels, builder.rs:330-334)

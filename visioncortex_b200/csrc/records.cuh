@@ -30,9 +30,18 @@ __global__ void __launch_bounds__(REC_THREADS) k_rec_accum(Dims d, Bufs b, vcb_c
     const u32 stride = gridDim.x * REC_THREADS;
     for (u32 k = blockIdx.x * REC_THREADS + threadIdx.x; k < lt; k += stride) {
         const u32 p = b.leaflist[k];
-        vcb_cluster_rec *r = rec + slot_base[p / d.n] + b.la[p].flabel;
+        const LeafA a = b.la[p];
+        vcb_cluster_rec *r = rec + slot_base[p / d.n] + a.flabel;
         const LeafS s = b.ls[p];
         const LeafR q = b.lr[p];
+        if (a.parL == NONE) {
+            // no effective event ever touched this leaf: it is the whole cluster and the only writer of its slot
+            *reinterpret_cast<uint4 *>(&r->sum[0]) = make_uint4(s.sum[0], s.sum[1], s.sum[2], s.sum[3]);
+            r->sum[4] = s.npx;
+            *reinterpret_cast<int2 *>(&r->rect[0]) = make_int2(q.minx, q.miny);
+            *reinterpret_cast<int2 *>(&r->rect[2]) = make_int2(q.maxx, q.maxy);
+            continue;
+        }
         if (s.sum[0]) atomicAdd(&r->sum[0], s.sum[0]);
         if (s.sum[1]) atomicAdd(&r->sum[1], s.sum[1]);
         if (s.sum[2]) atomicAdd(&r->sum[2], s.sum[2]);

@@ -112,6 +112,7 @@ int run_color(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w,
     ColorPolicy pol;
     pol.rgba = (const u32 *)d_rgba;
     pol.shift = cfg->is_same_color_a; pol.thres = cfg->is_same_color_b; pol.diagonal = cfg->diagonal != 0;
+    pol.prepare();
     pol.key = (u32)cfg->key_color[0] | ((u32)cfg->key_color[1] << 8) | ((u32)cfg->key_color[2] << 16) | ((u32)cfg->key_color[3] << 24);
     pol.has_key = pol.key != 0;
     const bool keep = pol.has_key && cfg->keying_action == VCB_KEYING_KEEP;

@@ -274,6 +274,9 @@ inline int run_stage1(vcb_ctx *c, const Dims &d, const P &pol, u32 base, bool wa
         if (nseg < 1) nseg = 1;
         if (nseg > d.h) nseg = d.h;
         u32 rows = (d.h + nseg - 1) / nseg;
+        static const int env_rows = getenv("VCB_ATTR_ROWS") ? atoi(getenv("VCB_ATTR_ROWS")) : 0;
+        static const int env_per_sm = getenv("VCB_ATTR_PER_SM") ? atoi(getenv("VCB_ATTR_PER_SM")) : 16;
+        if (env_rows > 0 && (u32)env_rows < rows) rows = (u32)env_rows;
         if (rows < 8 && d.h >= 8) rows = 8;
         const u32 nseg_t = (d.h + rows - 1) / rows;
         if (multi) { const int e = sync_devices(ds); if (e) return e; }
@@ -284,7 +287,7 @@ inline int run_stage1(vcb_ctx *c, const Dims &d, const P &pol, u32 base, bool wa
             if (s1 <= s0) continue;
             rt::set_device(ck->device);
             const u64 t_lo = (u64)s0 * wpad, t_hi = (u64)s1 * wpad;
-            const int g = grid_for(ck, t_hi - t_lo, K5_THREADS, 16);
+            const int g = grid_for(ck, t_hi - t_lo, K5_THREADS, env_per_sm);
             if (want_attr)
                 rt::launch(ck->st, "k_attribute", rt::THR, k_attribute<P, true>, dim3(g), dim3(K5_THREADS), 0, d, pol, b, rows, keep_key, t_lo, t_hi);
             else

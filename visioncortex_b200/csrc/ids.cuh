@@ -386,8 +386,11 @@ __global__ void __launch_bounds__(K2_THREADS) k_flatten_events4(Dims d, Bufs b, 
             }
             if (any_m) {                                  // some pixel carries a merge flag (implies a row above)
                 const u32 fu4 = *reinterpret_cast<const u32 *>(b.flags + g4 - d.w);
+                const uint4 upraw = *reinterpret_cast<const uint4 *>(b.pc + g4 - d.w);     // w % 4 == 0: aligned
+                const u32 up[4] = {upraw.x, upraw.y, upraw.z, upraw.w};
                 u32 fleft = 0;
                 if (f4 & F_M) fleft = b.flags[g4 - 1];
+                u32 last_raw = NONE, last_root = NONE;    // the pixels above usually share one tile-local root as well
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const u32 f = (f4 >> (8 * k)) & 255u;
@@ -398,7 +401,15 @@ __global__ void __launch_bounds__(K2_THREADS) k_flatten_events4(Dims d, Bufs b, 
                     const u32 g = g4 + k;
                     // a merge flag implies joined (non-keyed / set) left and up pixels, so both have a leaf
                     const u32 ea = k ? root[k - 1] : ((fl & F_FINAL) ? ldcg(b.pc + g - 1) : pc_root(b.pc, g - 1));
-                    const u32 eb = (fu & F_FINAL) ? ldcg(b.pc + g - d.w) : pc_root(b.pc, g - d.w);
+                    u32 eb = up[k];                       // a stale or a resolved value: both lead to the same root
+                    if (!(fu & F_FINAL)) {
+                        if (eb != last_raw) {
+                            u32 r = eb;
+                            while (true) { const u32 t = ldcg(b.pc + r); if (t == r) break; r = t; }
+                            last_raw = eb; last_root = r;
+                        }
+                        eb = last_root;
+                    }
                     if (ea != eb) { cg[ncand] = g; ca[ncand] = ea; cb[ncand] = eb; ++ncand; }
                 }
             }

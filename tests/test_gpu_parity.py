@@ -358,3 +358,22 @@ def test_colour_threshold_extremes(gpu, oracle):
         ref = oracle.runner_run(img, cfg, pools=True)
         got = gpu.runner_run(img, cfg, pools=True)
         assert_same_clusters(got, ref, pools=True, ctx=f"shift {shift} thres {thres}")
+
+
+def test_batch_of_many_small_odd_images(gpu, oracle):
+    """150 images of 37 x 23 (width not a multiple of 4: plain-load staging and the one-pixel-per-thread event kernel) in one
+    batch: several images share a 2048-slot scan chunk, some own a single slot, and the per-image list offsets restart."""
+    rng = np.random.default_rng(77)
+    imgs = []
+    for k in range(150):
+        im = (rng.integers(0, 3, size=(23, 37, 4), dtype=np.uint8) * 90)
+        im[..., 3] = 255
+        if k % 17 == 0:
+            im[:] = (10, 20, 30, 255)
+        imgs.append(im)
+    for hier in (0, 0xFFFFFFFF):
+        cfg = make_config(hierarchical=hier, is_same_color_a=0, is_same_color_b=1)
+        got = gpu.runner_run_batch(imgs, cfg, pools=True)
+        for k in range(0, 150, 7):
+            ref = oracle.runner_run(imgs[k], cfg, pools=True)
+            assert_same_clusters(got[k], ref, pools=True, ctx=f"hier {hier} image {k}")

@@ -349,31 +349,32 @@ inline int build_records(vcb_ctx *c, const Dims &d, const std::vector<ImgMeta> &
     rt::launch(st, "k_rec_accum", rt::SEQ, k_rec_accum, dim3(grid_for(c, d.N / 4, REC_THREADS, 16)), dim3(REC_THREADS), 0, d, b, res->rec, res->d_slot_base);
     if (keep_key)
         rt::launch(st, "k_rec_key", rt::SEQ, k_rec_key, dim3((d.nimg + 127) / 128), dim3(128), 0, d, b, res->rec, res->d_slot_base);
+    u32 *d_live = c->d_small;            // nimg counters
+    u32 *d_total = c->d_small + d.nimg + 1;
+    int key_bits = 1, img_bits = 1;
+    if (flat_outputs) {
+        while ((1ull << key_bits) <= (u64)d.n * 65535ull + d.n + 1) ++key_bits;
+        while ((1u << img_bits) < d.nimg) ++img_bits;
+        rt::fill(st, d_live, 0, (d.nimg + 2) * sizeof(u32));
+        rt::copy_h2d(st, d_total, &res->total_slots, sizeof(u32));
+    }
     {
-        u32 *d_img_base = c->d_small + 2 * (d.nimg + 2);   // nimg entries; the counters below use the first 2 * (nimg + 2)
+        u32 *d_img_base = c->d_small + 2 * (d.nimg + 2);   // nimg entries; the counters above use the first 2 * (nimg + 2)
         prims::scan_prefixes(st, "scan_off", OffScanFinal{res->rec, total}, c->chunksum, total, c->sms * 8);
         rt::launch(st, "k_img_base", rt::THR, k_img_base, dim3((d.nimg * 32 + REC_THREADS - 1) / REC_THREADS), dim3(REC_THREADS), 0,
                    (const vcb_cluster_rec *)res->rec, (const u32 *)res->d_slot_base, d.nimg, (const u32 *)c->chunksum, d_img_base);
         const u32 nchunks = (total + prims::SCAN_CHUNK - 1) / prims::SCAN_CHUNK;
         const u32 gf = std::max<u32>(1, std::min<u32>(nchunks, (u32)c->sms * 8));
+        // the sort keys of stage_1_output (k_out_keys) come out of the same pass
         rt::launch(st, "k_rec_finalize", rt::THR, k_rec_finalize, dim3(gf), dim3(REC_THREADS), RF_SMEM, res->rec, total,
-                   (const u32 *)c->chunksum, (const u32 *)res->d_slot_img, (const u32 *)d_img_base);
+                   (const u32 *)c->chunksum, (const u32 *)res->d_slot_img, (const u32 *)d_img_base, (const u32 *)res->d_slot_base,
+                   key_bits, flat_outputs ? c->sk0 : (u64 *)nullptr, c->sv0, d_live);
     }
 
     res->nout.assign(d.nimg, 0);
     res->indices_total.assign(d.nimg, 0);
     res->holes_total.assign(d.nimg, 0);
-    u32 *d_live = c->d_small;            // nimg counters
-    u32 *d_total = c->d_small + d.nimg + 1;
     if (flat_outputs) {
-        int key_bits = 1;
-        while ((1ull << key_bits) <= (u64)d.n * 65535ull + d.n + 1) ++key_bits;
-        int img_bits = 1;
-        while ((1u << img_bits) < d.nimg) ++img_bits;
-        rt::fill(st, d_live, 0, (d.nimg + 2) * sizeof(u32));
-        rt::copy_h2d(st, d_total, &res->total_slots, sizeof(u32));
-        rt::launch(st, "k_out_keys", rt::THR, k_out_keys, dim3(g), dim3(REC_THREADS), 0, res->rec, res->d_slot_base,
-                   res->d_slot_img, total, key_bits, c->sk0, c->sv0, d_live);
         const bool flipped = prims::radix_sort(st, c->sk0, c->sv0, c->sk1, c->sv1, d_total, total, key_bits + (d.nimg > 1 ? img_bits : 0),
                                                c->rs_table, c->chunksum, c->sms * 8);
         rt::copy_d2d(st, res->outputs, flipped ? c->sv1 : c->sv0, (size_t)total * sizeof(u32));

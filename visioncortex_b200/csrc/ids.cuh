@@ -753,7 +753,7 @@ struct NewScan {
 // Both compactions in one two-pass scan: 8 flag bytes per thread read as one 64-bit word, (NEW events, real leaves)
 // counted side by side in the two halves of a 64-bit sum.  Used for whole batches; NewScan / LeafScan remain the
 // restatement the simulator tests compare against (VCB_NO_FUSED_SCAN=1).
-constexpr int NL_THREADS = 256, NL_ITEMS = 8, NL_CHUNK = NL_THREADS * NL_ITEMS;
+constexpr int NL_THREADS = 256, NL_ITEMS = 8, NL_WORDS = 4, NL_CHUNK = NL_THREADS * NL_ITEMS * NL_WORDS;   // 32 pixels per thread
 __device__ static __forceinline__ u64 nl_load(const Bufs &b, u32 i0, u32 cnt) {
     if (i0 + NL_ITEMS <= cnt) return *reinterpret_cast<const u64 *>(b.flags + i0);
     u64 w = 0;
@@ -773,9 +773,12 @@ __global__ void __launch_bounds__(NL_THREADS) k_newleaf_sums(Dims d, Bufs b, u64
     VCB_SMEM(u64, sh);
     const u32 nchunks = (d.N + NL_CHUNK - 1) / NL_CHUNK;
     for (u32 c = blockIdx.x; c < nchunks; c += gridDim.x) {
-        const u32 i0 = c * NL_CHUNK + threadIdx.x * NL_ITEMS;
+        const u32 i0 = c * NL_CHUNK + threadIdx.x * NL_ITEMS * NL_WORDS;
+        u64 s = 0;
+#pragma unroll
+        for (int q = 0; q < NL_WORDS; ++q) s += nl_count(nl_load(b, i0 + q * NL_ITEMS, d.N));
         u64 total;
-        prims::block_exscan(nl_count(nl_load(b, i0, d.N)), sh, &total);
+        prims::block_exscan(s, sh, &total);
         if (threadIdx.x == 0) chunksum[c] = total;
     }
 }
@@ -796,23 +799,29 @@ __global__ void __launch_bounds__(NL_THREADS) k_newleaf_apply(Dims d, Bufs b, co
     VCB_SMEM(u64, sh);
     const u32 nchunks = (d.N + NL_CHUNK - 1) / NL_CHUNK;
     for (u32 c = blockIdx.x; c < nchunks; c += gridDim.x) {
-        const u32 i0 = c * NL_CHUNK + threadIdx.x * NL_ITEMS;
-        const u64 w = nl_load(b, i0, d.N);
+        const u32 i0 = c * NL_CHUNK + threadIdx.x * NL_ITEMS * NL_WORDS;
+        u64 w[NL_WORDS], s = 0;
+#pragma unroll
+        for (int q = 0; q < NL_WORDS; ++q) { w[q] = nl_load(b, i0 + q * NL_ITEMS, d.N); s += nl_count(w[q]); }
         u64 total;
-        const u64 ex = prims::block_exscan(nl_count(w), sh, &total) + chunkpref[c];
+        const u64 ex = prims::block_exscan(s, sh, &total) + chunkpref[c];
         u32 xn = (u32)ex, xl = (u32)(ex >> 32);
-        // image starts inside this thread's 8 pixels (at most a few per launch: the division runs once per thread)
+        // image starts inside this thread's 32 pixels (at most a few per launch: the division runs once per thread)
         u32 img_next = i0 < d.N ? (i0 + d.n - 1) / d.n : 0;        // first image starting at or after i0
         u32 next_start = img_next * d.n;
 #pragma unroll
-        for (int k = 0; k < NL_ITEMS; ++k) {
-            const u32 i = i0 + k;
-            if (i >= d.N) break;
-            if (i == next_start) { b.meta[img_next].leaf_begin = xn; ++img_next; next_start += d.n; }
-            const u32 j = (u32)(w >> (8 * k)) & J_MASK;
-            if (j == J_NEW) { b.newlist[xn++] = i; b.leaflist[xl++] = i; }
-            else if (j == J_RUP) b.newlist[xn++] = i | TAG;
-            if (i == d.N - 1) { b.ctr->kt = xn; b.ctr->lt = xl; }
+        for (int q = 0; q < NL_WORDS; ++q) {
+#pragma unroll
+            for (int k = 0; k < NL_ITEMS; ++k) {
+                const u32 i = i0 + q * NL_ITEMS + k;
+                if (i < d.N) {
+                    if (i == next_start) { b.meta[img_next].leaf_begin = xn; ++img_next; next_start += d.n; }
+                    const u32 j = (u32)(w[q] >> (8 * k)) & J_MASK;
+                    if (j == J_NEW) { b.newlist[xn++] = i; b.leaflist[xl++] = i; }
+                    else if (j == J_RUP) b.newlist[xn++] = i | TAG;
+                    if (i == d.N - 1) { b.ctr->kt = xn; b.ctr->lt = xl; }
+                }
+            }
         }
     }
 }

@@ -111,8 +111,10 @@ __global__ void __launch_bounds__(REC_THREADS) k_img_base(const vcb_cluster_rec 
 // through shared memory: 256 records = 1536 16-byte words are loaded and stored fully coalesced, each thread edits its own.
 constexpr int RF_WORDS = 24;
 constexpr size_t RF_SMEM = (size_t)REC_THREADS * RF_WORDS * 4 + 64;
+// With keys != nullptr the sort keys of stage_1_output (k_out_keys below) are produced in the same pass.
 __global__ void __launch_bounds__(REC_THREADS) k_rec_finalize(vcb_cluster_rec *rec, u32 total, const u32 *chunkpref,
-                                                              const u32 *slot_img, const u32 *img_base) {
+                                                              const u32 *slot_img, const u32 *img_base, const u32 *slot_base,
+                                                              int key_bits, u64 *keys, u32 *vals, u32 *live) {
     VCB_SMEM(u32, sm);
     u32 *sh = sm + REC_THREADS * RF_WORDS;
     uint4 *sm4 = reinterpret_cast<uint4 *>(sm);
@@ -129,13 +131,31 @@ __global__ void __launch_bounds__(REC_THREADS) k_rec_finalize(vcb_cluster_rec *r
             const u32 v = mine ? r[4] : 0u;
             u32 tot;
             const u32 ex = prims::block_exscan(v, sh, &tot) + carry;
+            u32 img = 0xffffffffu;
             if (mine) {
                 if (v == 0) { r[10] = r[11] = r[12] = r[13] = 0; }
                 else { r[12] += 1; r[13] += 1; }
 #pragma unroll
                 for (int k = 0; k < 5; ++k) r[5 + k] = r[k];
                 r[17] = v;
-                r[18] = ex - img_base[slot_img[s0 + threadIdx.x]]; r[19] = 0;
+                img = slot_img[s0 + threadIdx.x];
+                r[18] = ex - img_base[img]; r[19] = 0;
+            }
+            if (keys) {                                  // uniform; stage_1_output key (builder.rs:366-377), as in k_out_keys
+                const u32 s = s0 + threadIdx.x;
+                if (mine) {
+                    const u32 idx = s - slot_base[img];
+                    const u64 key = v ? (u64)v * 65535ull + idx : ((1ull << key_bits) - 1ull);
+                    keys[s] = ((u64)img << key_bits) | key;
+                    vals[s] = idx;
+                }
+                const int lane = threadIdx.x & 31;
+                const bool alive = mine && v != 0;
+                const u32 img0 = __shfl_sync(0xffffffffu, img, 0);
+                const bool uniform = __all_sync(0xffffffffu, img == img0 || !mine);
+                const u32 m = __ballot_sync(0xffffffffu, alive);
+                if (uniform) { if (lane == 0 && m && img0 != 0xffffffffu) atomicAdd(&live[img0], (u32)__popc(m)); }
+                else if (alive) atomicAdd(&live[img], 1u);
             }
             __syncthreads();
             for (u32 i = threadIdx.x; i < cnt * 6; i += REC_THREADS) g4[i] = sm4[i];

@@ -60,7 +60,7 @@ class ClockSampler:
                 ["nvidia-smi", "-i", str(self.dev),
                  "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
                  "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
-                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "--format=csv,noheader,nounits", "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -68,27 +68,40 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Clocks / throttle reasons of the samples taken inside [t0, t1] (the timed region).  nvidia-smi needs a few hundred
+        ms to start, so the sampler runs from before the warm-up; if the timed region was too short to catch a sample, the
+        samples of the whole loaded period (warm-up, timed steps, end-to-end leg) are reported and `window` says so."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+
+        def parse(lines):
+            sm, mx, reasons = [], [], set()
+            for ln in lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 6:
+                    continue
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+
+        window = "timed steps"
+        inside = [ln for ts, ln in self.lines if t0 is None or (t0 <= ts <= t1 + 0.03)]
+        sm, mx, reasons = parse(inside)
+        if not sm:
+            window = "warm-up + timed steps + end-to-end leg (timed region shorter than one sampling period)"
+            sm, mx, reasons = parse([ln for _, ln in self.lines])
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def cpu_oracle_rate(images, cfg, seconds, threads):
@@ -217,11 +230,11 @@ def main():
         return d2h
 
     # ---- device-resident timing (value)
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step_device()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     l0 = ctx.kernel_launches()
     ctx.event_record(0)
     t0 = time.time()
@@ -232,7 +245,7 @@ def main():
     barrier()
     wall = time.time() - t0
     launches = ctx.kernel_launches() - l0
-    clocks = sampler.stop()
+    t_timed = (t0, t0 + wall)
     ms_step = ms_dev / args.steps
     tt = torch.tensor([ms_step], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
@@ -278,6 +291,7 @@ def main():
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     e2e = world * B * NPX / float(tt.item()) / 1e6
+    clocks = sampler.stop(*t_timed)
 
     cpu = None
     if rank == 0 and world == 1 and args.cpu_seconds > 0:

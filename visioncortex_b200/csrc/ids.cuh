@@ -804,7 +804,7 @@ __global__ void __launch_bounds__(NL_THREADS) k_newleaf_chunks(Dims d, u64 *chun
         carry += total;
     }
 }
-__global__ void __launch_bounds__(NL_THREADS) k_newleaf_apply(Dims d, Bufs b, const u64 *chunkpref) {
+__global__ void __launch_bounds__(NL_THREADS, 6) k_newleaf_apply(Dims d, Bufs b, const u64 *chunkpref) {
     VCB_SMEM(u64, sh);
     const u32 nchunks = (d.N + NL_CHUNK - 1) / NL_CHUNK;
     for (u32 c = blockIdx.x; c < nchunks; c += gridDim.x) {

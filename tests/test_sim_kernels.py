@@ -124,3 +124,25 @@ def test_sim_colour_threshold_extremes(sim, oracle):
         ref = oracle.runner_run(img, cfg, pools=True)
         got = sim.runner_run(img, cfg, pools=True)
         assert_same_clusters(got, ref, pools=True, ctx=f"shift {shift} thres {thres}")
+
+
+def test_sim_chunked_batches_overlap_stage2(sim, oracle, monkeypatch):
+    """a hierarchical batch split into device batches whose stage 2 runs on rotating workspace sets (two sets, chunks of two
+    images: the third chunk has to complete the first one before it reuses its set), and the fused kernel's global-memory key path"""
+    from visioncortex_b200.runtime import make_config, runner_run_batch_host
+
+    rng = np.random.default_rng(46)
+    imgs = [rng.integers(0, 4, size=(12, 16, 4), dtype=np.uint8) * 60 for _ in range(7)]
+    cfg = make_config(is_same_color_a=0, is_same_color_b=1, good_min_area=2, deepen_diff=16)
+    refs = [oracle.runner_run(im, cfg, pools=True) for im in imgs]
+    monkeypatch.setenv("VCB_CHUNK_IMAGES", "2")
+    monkeypatch.setenv("VCB_S2_SETS", "2")
+    for keycap in ("2048", "3"):
+        monkeypatch.setenv("VCB_S2_KEYCAP", keycap)
+        got = sim.runner_run_batch(imgs, cfg, pools=True)
+        for k in range(len(imgs)):
+            assert_same_clusters(got[k], refs[k], pools=True, ctx=f"keycap {keycap} image {k}")
+    monkeypatch.setenv("VCB_HOST_CHUNKS", "4")
+    got = runner_run_batch_host(sim, imgs, cfg)
+    for k in range(len(imgs)):
+        assert_same_clusters(got[k], refs[k], pools=False, ctx=f"host batch image {k}")

@@ -7,6 +7,26 @@
 #include "stage2.cuh"
 #include "vmm.h"
 
+namespace vcb {
+struct BatchResult;
+// One set of stage-2 workspace with its own stream, scan scratch and pinned read-back block.  Stage 2 is one persistent
+// CTA per image and latency bound, so it leaves most of every SM idle: running it on a side stream lets it overlap the
+// stage-1 kernels of the next device batch (and the stage 2 of the previous ones).
+struct S2Set {
+    rt::Stream st;
+    rt::Event ev_in, ev_done;
+    bool ready = false;
+    size_t cap_slots = 0, cap_adj = 0, cap_img = 0, cap_scan = 0;
+    u32 *fw = nullptr, *mnext = nullptr, *mtail = nullptr, *mark = nullptr, *adj_off = nullptr, *cursor = nullptr, *adj = nullptr,
+        *tmin = nullptr, *bnd_off = nullptr, *bcur = nullptr, *bnd_px = nullptr, *live = nullptr, *chunksum = nullptr, *small = nullptr;
+    u64 *over = nullptr, *keys = nullptr;
+    S2ImgState *ist = nullptr;
+    void *h_pinned = nullptr;
+    size_t h_pinned_cap = 0;
+    BatchResult *busy = nullptr;      // result whose stage 2 is in flight on this set
+};
+}  // namespace vcb
+
 struct vcb_ctx {
     int device = 0;
     int sms = 1;
@@ -37,13 +57,12 @@ struct vcb_ctx {
     size_t bw_capN = 0;
     int bw_ndev = 0;
     u32 bw_split = 0;
-    // stage-2 workspace
-    size_t cap_s2_slots = 0, cap_s2_adj = 0;
-    u32 *s2_fw = nullptr, *s2_mnext = nullptr, *s2_mtail = nullptr, *s2_mark = nullptr, *s2_adj_off = nullptr,
-        *s2_cursor = nullptr, *s2_adj = nullptr, *s2_tmin = nullptr, *s2_bnd_off = nullptr, *s2_bcur = nullptr, *s2_bnd_px = nullptr;
-    u64 *s2_over = nullptr;
-    vcb::S2ImgState *s2_ist = nullptr;
-    size_t cap_s2_img = 0;
+    // stage-2 workspace sets: the hierarchical stage of one device batch runs on its set's own stream while the next batch's
+    // stage 1 runs on `st` (see S2Set)
+    static constexpr int MAX_S2_SETS = 8;
+    vcb::S2Set *s2_sets[MAX_S2_SETS] = {};
+    int s2_next = 0;
+    int coop_blocks = 0;              // occupancy of the cooperative spanning-forest kernel on this device
 #ifndef VCB_HOSTSIM
     cudaEvent_t events[16] = {};
 #endif
@@ -68,16 +87,21 @@ struct BatchResult {
     bool hier = false;
     u32 *pool = nullptr;              // concatenated Cluster.indices of all images (exact order), when materialised
     u8 *pixels = nullptr;             // retained copy of the input (Clusters.pixels, container.rs:8; take_image :34-40)
+    const u8 *ext_pixels = nullptr;   // device-resident runs: the caller's own buffer instead of a copy
     std::vector<u32> slot_base, nout, pool_base;
     std::vector<u64> indices_total, holes_total;
     u32 total_slots = 0;
     bool keep_key = false;
+    S2Set *pending = nullptr;         // stage 2 launched on this set, not yet finished (stage2_finish)
+    S2 s2args{};
     ~BatchResult();
 };
 
+inline int stage2_finish(vcb_ctx *c, BatchResult *res);
 inline BatchResult::~BatchResult() {
     if (!ctx) return;
     rt::set_device(ctx->device);
+    if (pending) stage2_finish(ctx, this);
     for (void *p : {(void *)labels, (void *)rec, (void *)outputs, (void *)d_slot_base, (void *)d_slot_img, (void *)pool,
                     (void *)pixels, (void *)labels1, (void *)mpar, (void *)outpos, (void *)childoff, (void *)holeoff, (void *)off1,
                     (void *)hpool, (void *)pool1})
@@ -258,9 +282,8 @@ inline int run_stage1(vcb_ctx *c, const Dims &d, const P &pol, u32 base, bool wa
         }
     }
     {
-        static int coop_blocks = 0;
-        if (!coop_blocks) coop_blocks = rt::max_coop_blocks((const void *)k_boruvka, K3_THREADS, 0, c->device);
-        int g = coop_blocks;
+        if (!c->coop_blocks) c->coop_blocks = rt::max_coop_blocks((const void *)k_boruvka, K3_THREADS, 0, c->device);
+        int g = c->coop_blocks;
         const int want = (int)((d.N / 4 + K3_THREADS - 1) / K3_THREADS);
         if (g > want) g = want < 1 ? 1 : want;
         rt::launch(st, "k_boruvka", rt::COOP, k_boruvka, dim3(g), dim3(K3_THREADS), 0, b);
@@ -413,32 +436,76 @@ inline int materialize_pool(vcb_ctx *c, const Dims &d, BatchResult *res, bool ke
 }
 
 // Stage 2 (builder.rs:379-539) on the records / labels produced by stage 1.  See stage2.cuh.
-inline int run_stage2(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg, bool has_key, BatchResult *res) {
-    rt::Stream &st = c->st;
-    const u32 total = res->total_slots;
-    if (total > c->cap_s2_slots) {
+inline S2Set *acquire_s2_set(vcb_ctx *c);
+inline int stage2_finish(vcb_ctx *c, BatchResult *res);
+
+inline int ensure_s2_set(vcb_ctx *c, S2Set *s, const Dims &d, u32 total) {
+    if (!s->ready) {
+        if (rt::stream_create(s->st) != 0 || rt::event_create(s->ev_in) != 0 || rt::event_create(s->ev_done) != 0) return VCB_ERR_CUDA;
+        s->ready = true;
+    }
+    if (total > s->cap_slots) {
         const size_t cap = (size_t)total + 64;
-        bool ok = grow(c->s2_fw, cap) & grow(c->s2_mnext, cap) & grow(c->s2_mtail, cap) & grow(c->s2_mark, cap) & grow(c->s2_tmin, cap) & grow(c->s2_bnd_off, cap + 1) & grow(c->s2_bcur, cap) &
-                  grow(c->s2_adj_off, cap + 1) & grow(c->s2_cursor, cap) & grow(c->s2_over, cap);
-        if (!ok) { c->cap_s2_slots = 0; return VCB_ERR_NOMEM; }
-        c->cap_s2_slots = total;
+        bool ok = grow(s->fw, cap) & grow(s->mnext, cap) & grow(s->mtail, cap) & grow(s->mark, cap) & grow(s->tmin, cap) & grow(s->bnd_off, cap + 1) &
+                  grow(s->bcur, cap) & grow(s->adj_off, cap + 1) & grow(s->cursor, cap) & grow(s->over, cap) & grow(s->live, cap) & grow(s->keys, cap);
+        if (!ok) { s->cap_slots = 0; return VCB_ERR_NOMEM; }
+        s->cap_slots = total;
     }
-    if ((size_t)d.N * 4 > c->cap_s2_adj) {
-        if (!grow(c->s2_adj, (size_t)d.N * 4 + 64) || !grow(c->s2_bnd_px, (size_t)d.N + 64)) { c->cap_s2_adj = 0; return VCB_ERR_NOMEM; }
-        c->cap_s2_adj = (size_t)d.N * 4;
+    if ((size_t)d.N * 4 > s->cap_adj) {
+        if (!grow(s->adj, (size_t)d.N * 4 + 64) || !grow(s->bnd_px, (size_t)d.N + 64)) { s->cap_adj = 0; return VCB_ERR_NOMEM; }
+        s->cap_adj = (size_t)d.N * 4;
     }
-    if (d.nimg > c->cap_s2_img) {
-        if (!grow(c->s2_ist, (size_t)d.nimg + 1)) { c->cap_s2_img = 0; return VCB_ERR_NOMEM; }
-        c->cap_s2_img = d.nimg;
+    if (d.nimg > s->cap_img) {
+        if (!grow(s->ist, (size_t)d.nimg + 1) || !grow(s->small, 4 * ((size_t)d.nimg + 4) + 32)) { s->cap_img = 0; return VCB_ERR_NOMEM; }
+        s->cap_img = d.nimg;
     }
-    res->mpar = (u32 *)rt::dev_malloc_async(st, (size_t)total * 4 + 4);
-    res->outpos = (u32 *)rt::dev_malloc_async(st, (size_t)total * 4 + 4);
-    res->childoff = (u32 *)rt::dev_malloc_async(st, (size_t)total * 4 + 4);
-    res->holeoff = (u32 *)rt::dev_malloc_async(st, (size_t)total * 4 + 4);
+    const size_t scan_items = std::max<size_t>(total, 1);
+    if (scan_items > s->cap_scan) {
+        if (!grow(s->chunksum, scan_items / 2048 + 1032)) { s->cap_scan = 0; return VCB_ERR_NOMEM; }
+        s->cap_scan = scan_items;
+    }
+    const size_t need = ((size_t)d.nimg + 4) * (sizeof(S2ImgState) + 16) + 4096;
+    if (need > s->h_pinned_cap) {
+        rt::host_free(s->h_pinned);
+        s->h_pinned = rt::host_malloc(need);
+        s->h_pinned_cap = s->h_pinned ? need : 0;
+        if (!s->h_pinned) return VCB_ERR_NOMEM;
+    }
+    return VCB_OK;
+}
+
+inline void free_s2_set(S2Set *s) {
+    if (!s) return;
+    for (void *p : {(void *)s->fw, (void *)s->mnext, (void *)s->mtail, (void *)s->mark, (void *)s->adj_off, (void *)s->cursor, (void *)s->adj,
+                    (void *)s->tmin, (void *)s->bnd_off, (void *)s->bcur, (void *)s->bnd_px, (void *)s->live, (void *)s->chunksum,
+                    (void *)s->small, (void *)s->over, (void *)s->keys, (void *)s->ist})
+        rt::dev_free(p);
+    rt::host_free(s->h_pinned);
+    if (s->ready) { rt::stream_destroy(s->st); rt::event_destroy(s->ev_in); rt::event_destroy(s->ev_done); }
+    delete s;
+}
+
+// Launches the hierarchical stage of `res` (whose stage 1 and records are queued on c->st).  With `async` the work goes to
+// the stream of a free workspace set and the call returns at once; stage2_finish completes the result.
+inline int stage2_launch(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg, bool has_key, BatchResult *res, bool async) {
+    const u32 total = res->total_slots;
+    const bool legacy = std::getenv("VCB_S2_LEGACY") != nullptr;           // per-epoch launches + global sorts (uses the ctx scratch)
+    if (legacy) async = false;
+    S2Set *set = acquire_s2_set(c);
+    if (!set) return VCB_ERR_NOMEM;
+    int e = ensure_s2_set(c, set, d, total);
+    if (e) return e;
+    res->mpar = (u32 *)rt::dev_malloc_async(c->st, (size_t)total * 4 + 4);
+    res->outpos = (u32 *)rt::dev_malloc_async(c->st, (size_t)total * 4 + 4);
+    res->childoff = (u32 *)rt::dev_malloc_async(c->st, (size_t)total * 4 + 4);
+    res->holeoff = (u32 *)rt::dev_malloc_async(c->st, (size_t)total * 4 + 4);
     res->labels1 = res->labels;
-    res->labels = (u32 *)rt::dev_malloc_async(st, (size_t)d.N * 4);
+    res->labels = (u32 *)rt::dev_malloc_async(c->st, (size_t)d.N * 4);
     if (!res->mpar || !res->outpos || !res->labels || !res->childoff || !res->holeoff) return VCB_ERR_NOMEM;
     res->hier = true;
+    // everything stage 2 reads was produced (or allocated) on c->st: the set's stream starts after it
+    rt::Stream &st = async ? set->st : c->st;
+    if (async) { rt::event_record(set->ev_in, c->st); rt::stream_wait(set->st, set->ev_in); }
 
     u32 max_slots = 1;
     for (u32 i = 0; i < d.nimg; ++i) max_slots = std::max(max_slots, res->slot_base[i + 1] - res->slot_base[i]);
@@ -457,11 +524,11 @@ inline int run_stage2(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg, b
 #endif
     a.l1 = res->labels1; a.rec = res->rec; a.slot_base = res->d_slot_base; a.slot_img = res->d_slot_img; a.total_slots = total;
     a.childoff = res->childoff; a.holeoff = res->holeoff;
-    a.fw = c->s2_fw; a.mpar = res->mpar; a.mnext = c->s2_mnext; a.mtail = c->s2_mtail; a.mark = c->s2_mark; a.tmin = c->s2_tmin; a.outpos = res->outpos;
-    a.bnd_off = c->s2_bnd_off; a.bcur = c->s2_bcur; a.bnd_px = c->s2_bnd_px;
-    a.adj_off = c->s2_adj_off; a.adj = c->s2_adj; a.cursor = c->s2_cursor; a.outputs = res->outputs; a.over = c->s2_over;
-    a.ist = c->s2_ist; a.keys = c->sk0; a.vals = c->sv0;
-    u32 *d_count = c->d_small + 3 * (d.nimg + 2) + 3;
+    a.fw = set->fw; a.mpar = res->mpar; a.mnext = set->mnext; a.mtail = set->mtail; a.mark = set->mark; a.tmin = set->tmin; a.outpos = res->outpos;
+    a.bnd_off = set->bnd_off; a.bcur = set->bcur; a.bnd_px = set->bnd_px;
+    a.adj_off = set->adj_off; a.adj = set->adj; a.cursor = set->cursor; a.outputs = res->outputs; a.over = set->over;
+    a.ist = set->ist; a.keys = legacy ? c->sk0 : set->keys; a.vals = c->sv0; a.live = set->live;
+    u32 *d_count = set->small + 3 * (d.nimg + 2) + 3;
     a.count = d_count;
     a.idx_bits = 1; while ((1u << a.idx_bits) < max_slots) ++a.idx_bits;
     a.area_bits = 1; while ((1ull << a.area_bits) <= (u64)d.n) ++a.area_bits;
@@ -471,53 +538,91 @@ inline int run_stage2(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg, b
     rt::launch(st, "k_s2_init_img", rt::SEQ, k_s2_init_img, dim3((d.nimg + 127) / 128), dim3(128), 0, a);
     rt::launch(st, "k_s2_init", rt::SEQ, k_s2_init, dim3(gs), dim3(256), 0, a);
     rt::launch(st, "k_rag_count", rt::SEQ, k_rag<false>, dim3(gp), dim3(256), 0, a);
-    prims::scan(st, "scan_deg", DegScan{a}, c->chunksum, total, c->sms * 8);
-    prims::scan(st, "scan_deg", BndScan{a}, c->chunksum, total, c->sms * 8);
+    prims::scan(st, "scan_deg", DegScan{a}, set->chunksum, total, c->sms * 8);
+    prims::scan(st, "scan_deg", BndScan{a}, set->chunksum, total, c->sms * 8);
     rt::launch(st, "k_rag_fill", rt::SEQ, k_rag<true>, dim3(gp), dim3(256), 0, a);
     int max_epoch = 0;
     while ((2ull << max_epoch) <= (u64)d.n) ++max_epoch;
-    for (int ep = 0; ep <= max_epoch; ++ep) {
-        rt::fill(st, d_count, 0, sizeof(u32));
-        rt::launch(st, "k_s2_collect", rt::THR, k_s2_collect, dim3(gs), dim3(256), 0, a, ep);
-        const int nbits = a.idx_bits + ep + (d.nimg > 1 ? img_bits : 0);      // within an epoch only `ep` bits of the area vary
-        const bool flipped = prims::radix_sort(st, c->sk0, c->sv0, c->sk1, c->sv1, d_count, total, nbits, c->rs_table, c->chunksum, c->sms * 8);
-        // few images: a thread-block cluster of fat CTAs per image (the leader replays the merges, the others help with the
-        // large perimeter scans); many images: one CTA per image, more CTAs per SM
+    // few images: fat CTAs (and, in the rect-scan perimeter mode, a thread-block cluster per image whose other CTAs help with
+    // the large perimeter scans); many images: one slim CTA per image, several per SM
 #ifdef VCB_HOSTSIM
-        const int s2_threads = 128;                                  // 4 warps: batch rounds of 4 candidates
-        const u32 G = (d.nimg == 1 && a.cfg.rect_perim) ? 2u : 1u;
+    const int s2_threads = 128;                                  // 4 warps: batch rounds of 4 candidates
+    const u32 G = (d.nimg == 1 && a.cfg.rect_perim) ? 2u : 1u;
 #else
-        const int s2_threads = d.nimg * 8 <= (u32)c->sms ? 1024 : d.nimg * 2 <= (u32)c->sms ? 512 : d.nimg <= (u32)c->sms ? 256 : 128;
-        u32 G = 1;
-        static const u32 maxg = std::getenv("VCB_S2_MAXG") ? (u32)std::atoi(std::getenv("VCB_S2_MAXG")) : 8u;
-        while (a.cfg.rect_perim && G < maxg && d.nimg * (G * 2) * 2 <= (u32)c->sms) G *= 2;   // helpers only serve the rect-scan perimeter
+    int s2_threads = d.nimg * 8 <= (u32)c->sms ? 1024 : d.nimg * 2 <= (u32)c->sms ? 512 : 256;
+    if (const char *ev = std::getenv("VCB_S2_THREADS")) s2_threads = std::max(32, std::min(1024, std::atoi(ev) / 32 * 32));
+    u32 G = 1;
+    static const u32 maxg = std::getenv("VCB_S2_MAXG") ? (u32)std::atoi(std::getenv("VCB_S2_MAXG")) : 8u;
+    while (a.cfg.rect_perim && G < maxg && d.nimg * (G * 2) * 2 <= (u32)c->sms) G *= 2;   // helpers only serve the rect-scan perimeter
 #endif
+    const size_t smem_fixed = ((offsetof(S2Shared, map) + (a.cfg.rect_perim ? S2_MAPBYTES : 0u) + 15u) & ~(size_t)15) + 16;
+    if (!legacy) {
+        // fused path: every epoch in one launch, keys sorted in shared memory (an epoch with more live roots than the shared
+        // key array holds is sorted in the image's global key range instead)
+        u32 key_cap = d.nimg * 2 <= (u32)c->sms ? 16384u : 2048u;
+        if (const char *ev = std::getenv("VCB_S2_KEYCAP")) key_cap = (u32)std::max(1, std::atoi(ev));
+        a.key_cap = key_cap;
+        const size_t smem = smem_fixed + (size_t)key_cap * 8;
         if (G > 1)
-            rt::launch_cluster(st, "k_s2_epoch", k_s2_epoch, dim3(d.nimg * G), dim3(s2_threads), sizeof(S2Shared) + 16, G, a,
-                               (const u64 *)(flipped ? c->sk1 : c->sk0), ep, G);
+            rt::launch_cluster(st, "k_s2_epoch", k_s2_run, dim3(d.nimg * G), dim3(s2_threads), smem, G, a, max_epoch, G);
         else
-            rt::launch(st, "k_s2_epoch", rt::THR, k_s2_epoch, dim3(d.nimg), dim3(s2_threads), sizeof(S2Shared) + 16, a,
-                       (const u64 *)(flipped ? c->sk1 : c->sk0), ep, G);
+            rt::launch(st, "k_s2_epoch", rt::THR, k_s2_run, dim3(d.nimg), dim3(s2_threads), smem, a, max_epoch, G);
+    } else {
+        for (int ep = 0; ep <= max_epoch; ++ep) {
+            rt::fill(st, d_count, 0, sizeof(u32));
+            rt::launch(st, "k_s2_collect", rt::THR, k_s2_collect, dim3(gs), dim3(256), 0, a, ep);
+            const int nbits = a.idx_bits + ep + (d.nimg > 1 ? img_bits : 0);      // within an epoch only `ep` bits of the area vary
+            const bool flipped = prims::radix_sort(st, c->sk0, c->sv0, c->sk1, c->sv1, d_count, total, nbits, c->rs_table, c->chunksum, c->sms * 8);
+            if (G > 1)
+                rt::launch_cluster(st, "k_s2_epoch", k_s2_epoch, dim3(d.nimg * G), dim3(s2_threads), smem_fixed, G, a,
+                                   (const u64 *)(flipped ? c->sk1 : c->sk0), ep, G);
+            else
+                rt::launch(st, "k_s2_epoch", rt::THR, k_s2_epoch, dim3(d.nimg), dim3(s2_threads), smem_fixed, a,
+                           (const u64 *)(flipped ? c->sk1 : c->sk0), ep, G);
+        }
     }
     rt::launch(st, "k_s2_labels", rt::SEQ, k_s2_labels, dim3(gp), dim3(256), 0, a, res->labels);
     // offsets of the per-slot lists after the merges
-    prims::scan(st, "scan_off", OffScan{res->rec, res->d_slot_base, res->d_slot_img, total, nullptr}, c->chunksum, total, c->sms * 8);
+    prims::scan(st, "scan_off", OffScan{res->rec, res->d_slot_base, res->d_slot_img, total, nullptr}, set->chunksum, total, c->sms * 8);
     rt::launch(st, "k_off_rebase", rt::SEQ, k_off_rebase, dim3(gs), dim3(REC_THREADS), 0, res->rec, res->d_slot_base, res->d_slot_img, total);
     rt::launch(st, "k_off_rebase0", rt::SEQ, k_off_rebase0, dim3((d.nimg + 127) / 128), dim3(128), 0, res->rec, res->d_slot_base, d.nimg);
-    u32 *d_first = c->d_small;
-    prims::scan(st, "scan_holes", HolesScan{res->rec, total}, c->chunksum, total, c->sms * 8);
+    u32 *d_first = set->small;
+    prims::scan(st, "scan_holes", HolesScan{res->rec, total}, set->chunksum, total, c->sms * 8);
     rt::launch(st, "k_holes_first", rt::SEQ, k_holes_first, dim3((d.nimg + 127) / 128), dim3(128), 0, (const vcb_cluster_rec *)res->rec, (const u32 *)res->d_slot_base, d.nimg, d_first);
     rt::launch(st, "k_holes_rebase", rt::SEQ, k_holes_rebase, dim3(gs), dim3(256), 0, res->rec, (const u32 *)res->d_slot_base, (const u32 *)res->d_slot_img, total, d_first);
-    S2ImgState *h = (S2ImgState *)c->h_pinned;
-    rt::copy_d2h(st, h, c->s2_ist, d.nimg * sizeof(S2ImgState));
+    rt::copy_d2h(st, set->h_pinned, set->ist, d.nimg * sizeof(S2ImgState));
+    if (async) rt::event_record(set->ev_done, set->st);
+    res->s2args = a;
+    res->pending = set;
+    set->busy = res;
+    if (!async) return stage2_finish(c, res);
+    return VCB_OK;
+}
+
+// Completes a result whose stage 2 was launched on a workspace set: waits for the set's stream, reads the output counts and
+// (when the ordered lists were requested) scatters the indices / holes pools.  c->st is ordered after the set's work.
+inline int stage2_finish(vcb_ctx *c, BatchResult *res) {
+    S2Set *set = res->pending;
+    if (!set) return VCB_OK;
+    res->pending = nullptr;
+    set->busy = nullptr;
+    const Dims d = res->d;
+    const bool on_set = set->st.s != nullptr && set->st.launches > 0 && !std::getenv("VCB_S2_LEGACY");
+    rt::Stream &st = c->st;
+    // the set's stream may hold the work: wait for it, then continue on c->st (ordered by the host-side wait)
+    if (set->ready && rt::stream_sync(set->st) != 0) { c->err = set->st.last_error_text; set->st.last_error = 0; return VCB_ERR_CUDA; }
+    if (set->st.last_error) { c->err = set->st.last_error_text; set->st.last_error = 0; return VCB_ERR_CUDA; }
+    (void)on_set;
     if (rt::stream_sync(st) != 0 || st.last_error) { c->err = st.last_error_text; st.last_error = 0; return VCB_ERR_CUDA; }
+    S2ImgState *h = (S2ImgState *)set->h_pinned;
     for (u32 i = 0; i < d.nimg; ++i) res->nout[i] = h[i].nout;
     if (std::getenv("VCB_S2_STATS"))
         std::fprintf(stderr, "[vcb] stage 2 image 0: merges %u, outputs %u, batch rounds %u (candidates %u, committed %u), single pops %u\n",
                      h[0].nmerge, h[0].nout, h[0].st_rounds, h[0].st_cands, h[0].st_committed, h[0].st_singles);
     if (res->pool1) {
         // ordered indices / holes pools from the stage-1 pool and the merge forest
-        u32 *d_ib = c->d_small, *d_hb = c->d_small + (d.nimg + 2), *d_p1b = c->d_small + 2 * (d.nimg + 2);
+        const S2 &a = res->s2args;
+        u32 *d_ib = set->small, *d_hb = set->small + (d.nimg + 2), *d_p1b = set->small + 2 * (d.nimg + 2);
         rt::launch(st, "k_pool_base", rt::SEQ, k_pool_base, dim3(1), dim3(32), 0, (const vcb_cluster_rec *)res->rec, (const u32 *)res->d_slot_base, d.nimg, d_ib);
         rt::launch(st, "k_hpool_base", rt::SEQ, k_hpool_base, dim3(1), dim3(32), 0, (const vcb_cluster_rec *)res->rec, (const u32 *)res->d_slot_base, d.nimg, d_hb);
         rt::copy_h2d(st, d_p1b, res->pool1_base.data(), (d.nimg + 1) * sizeof(u32));
@@ -532,8 +637,20 @@ inline int run_stage2(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg, b
         if (!res->pool || !res->hpool) return VCB_ERR_NOMEM;
         rt::launch(st, "k_s2_pool_scatter", rt::SEQ, k_s2_pool_scatter, dim3(grid_for(c, res->pool1_base[d.nimg], 256, 16)), dim3(256), 0, a,
                    (const u32 *)res->pool1, (const u32 *)d_p1b, (const u32 *)res->off1, (const u32 *)d_ib, (const u32 *)d_hb, res->pool, res->hpool);
+        if (rt::stream_sync(st) != 0 || st.last_error) { c->err = st.last_error_text; st.last_error = 0; return VCB_ERR_CUDA; }
     }
     return VCB_OK;
+}
+
+// next workspace set in round-robin order; a set still serving an earlier result is completed first
+inline S2Set *acquire_s2_set(vcb_ctx *c) {
+    const int nsets = std::max(1, std::min((int)vcb_ctx::MAX_S2_SETS, std::getenv("VCB_S2_SETS") ? std::atoi(std::getenv("VCB_S2_SETS")) : 4));
+    const int k = c->s2_next % nsets;
+    c->s2_next = (k + 1) % nsets;
+    if (!c->s2_sets[k]) c->s2_sets[k] = new (std::nothrow) S2Set();
+    S2Set *s = c->s2_sets[k];
+    if (s && s->busy) stage2_finish(c, s->busy);
+    return s;
 }
 
 }  // namespace vcb

@@ -172,6 +172,7 @@ inline void launch(Stream &st, const char *name, LaunchMode mode, void (*k)(KArg
         cudaError_t e = cudaLaunchCooperativeKernel((const void *)k, grid, block, ptrs, smem, st.s);
         if (e != cudaSuccess && !st.last_error) { st.last_error = (int)e; st.last_error_text = std::string(name) + ": " + cudaGetErrorString(e); }
     } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k<<<grid, block, smem, st.s>>>(KArgs(args)...);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess && !st.last_error) { st.last_error = (int)e; st.last_error_text = std::string(name) + ": " + cudaGetErrorString(e); }
@@ -200,6 +201,7 @@ inline void launch_cluster(Stream &st, const char *name, void (*k)(KArgs...), di
     attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     if (cluster > 8) cudaFuncSetAttribute((const void *)k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (smem > 48 * 1024) cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaError_t e = cudaLaunchKernelEx(&cfg, k, KArgs(args)...);
     if (e != cudaSuccess && !st.last_error) { st.last_error = (int)e; st.last_error_text = std::string(name) + ": " + cudaGetErrorString(e); }
     if (st.profiling) { cudaEventRecord(pe.e1, st.s); st.prof.push_back(pe); }

@@ -54,7 +54,14 @@ struct S2 {
     u64 *keys; u32 *vals;          // epoch sort input/output
     u32 *count;                    // number of keys collected this epoch
     int idx_bits, area_bits;
+    u32 *live;                     // fused kernel: per image, its live roots in index order (compacted as clusters merge)
+    u32 key_cap;                   // fused kernel: capacity of the shared-memory key array
 };
+
+// Where the pop keys of the current epoch come from: the globally sorted (image | area - 2^epoch | index) array of the
+// multi-launch path, or the CTA's own shared-memory array of ready-made (area << idx_bits | index) keys (fused kernel).
+struct S2Keys { const u64 *g; const u64 *s; u64 mask, add; };
+__device__ static __forceinline__ u64 s2_key(const S2Keys &k, u32 i) { return k.s ? k.s[i] : ((k.g[i] & k.mask) + k.add); }
 
 constexpr u32 FLAGBIT = 0x80000000u;
 constexpr u32 HOLLOWBIT = 0x40000000u;
@@ -189,6 +196,7 @@ __device__ static __forceinline__ i32 color_diff(u32 a, u32 b) {     // runner.r
     return dsum;
 }
 
+constexpr size_t S2_FUSED_SMEM_MAX = 200 * 1024;   // fused kernel: fixed part + key array must fit one SM's shared memory
 constexpr int S2_MAX_THREADS = 1024;   // block size is chosen at launch: 1024 for a few large images, 128 for big batches
 constexpr int S2_MEMCHUNK = 256;
 constexpr int S2_URGENT = 64;
@@ -213,7 +221,8 @@ struct S2Shared {
     u32 bnbr[S2_NB][S2_CAPN];
     u32 bmem[S2_NB][S2_CAPM];
     u32 nb, ncommit, mode, force_single, brounds, bdone, boff;
-    u8 map[S2_MAPBYTES];
+    u32 nlive, wsum[33];
+    alignas(16) u8 map[S2_MAPBYTES];   // last member: allocated only in the rect-scan perimeter mode
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -234,14 +243,12 @@ __device__ static __forceinline__ unsigned long long warp_min64(unsigned long lo
     return v;
 }
 
-__device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh, S2ImgState *ist, const u64 *keys, int epoch,
+__device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh, S2ImgState *ist, const S2Keys &keys, int epoch,
                                                       u32 img, u32 base, u64 *over) {
     const Dims d = a.d;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 W = (blockDim.x >> 5) < (u32)S2_NB ? (blockDim.x >> 5) : (u32)S2_NB;
-    const int kshift = a.idx_bits + epoch;
     const u64 idx_mask = (1ull << a.idx_bits) - 1ull;
-    const u32 area_base = 1u << epoch;
     // ---- F: warp 0 takes the next entries of the sorted segment that precede every pending urgent key
     if (warp == 0) {
         unsigned long long umin = ~0ull;
@@ -255,7 +262,7 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
         bool inrange = false, valid = false;
         u32 idx = 0, ar = 0;
         if (use && lane < W && lo + lane < hi) {
-            kb = (keys[lo + lane] & ((1ull << kshift) - 1ull)) + ((unsigned long long)area_base << a.idx_bits);
+            kb = s2_key(keys, lo + lane);
             inrange = kb < umin;
             if (inrange) {
                 idx = (u32)(kb & idx_mask); ar = (u32)(kb >> a.idx_bits);
@@ -632,51 +639,40 @@ __device__ static __forceinline__ void s2_perimeter_rows(const S2 &a, S2Shared *
     if (cntp) atomicAdd(&sh->perim, cntp);
 }
 
-__global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_epoch(S2 a, const u64 *keys, int epoch, u32 G) {
-    const u32 S2_THREADS = blockDim.x;
-    VCB_SMEM(S2Shared, sh);
-    const u32 img = blockIdx.x / G, crank = blockIdx.x % G, base = a.slot_base[img];   // G CTAs (one cluster) per image
-    const u32 nslots = a.slot_base[img + 1] - base;
+// helper CTAs of an image's thread-block cluster (rect-scan perimeter mode): they sleep in the cluster barrier and are
+// woken for a perimeter task or to quit
+__device__ static __forceinline__ void s2_helper_loop(const S2 &a, S2Shared *sh, S2ImgState *ist, u32 img, u32 base, u32 crank, u32 G) {
     const u32 tid = threadIdx.x;
-    S2ImgState *ist = a.ist + img;
-    const int kshift = a.idx_bits + epoch;                      // sorted keys: image | (area - 2^epoch) | index
+    while (true) {
+        VCB_CLUSTER_SYNC();
+        if (ldcg(&ist->task_quit)) break;
+        if (tid == 0) sh->perim = 0;
+        i32 rect[4];
+        for (int k2 = 0; k2 < 4; ++k2) rect[k2] = ldcg(&ist->task_rect[k2]);
+        const u32 tc = ldcg(&ist->task_c);
+        __syncthreads();
+        const u32 rh = (u32)(rect[3] - rect[1]);
+        s2_perimeter_rows(a, sh, img, base, tc, rect, (u32)((u64)rh * crank / G), (u32)((u64)rh * (crank + 1) / G));
+        __syncthreads();
+        if (tid == 0) { if (sh->perim) atomicAdd(&ist->perim_acc, sh->perim); __threadfence(); }
+        __syncthreads();
+        VCB_CLUSTER_SYNC();
+    }
+}
+__device__ static __forceinline__ void s2_release_helpers(S2ImgState *ist, u32 G) {
+    if (G > 1) {
+        if (threadIdx.x == 0) { stcg(&ist->task_quit, 1u); __threadfence(); }
+        __syncthreads();
+        VCB_CLUSTER_SYNC();
+    }
+}
+
+// All pops of one epoch of one image, in the reference's exact order.  sh->lo / sh->hi delimit the image's sorted keys.
+__device__ static __forceinline__ void s2_epoch_leader(const S2 &a, S2Shared *sh, S2ImgState *ist, const S2Keys &keys, int epoch,
+                                                       u32 img, u32 base, u64 *over, u32 G) {
+    const u32 S2_THREADS = blockDim.x;
+    const u32 tid = threadIdx.x;
     const u64 idx_mask = (1ull << a.idx_bits) - 1ull;
-    const u32 area_base = 1u << epoch;
-    u64 *over = a.over + base;
-
-    if (crank != 0) {
-        // helper CTA of the image's cluster: sleeps in the cluster barrier; woken for a perimeter task or to quit
-        while (true) {
-            VCB_CLUSTER_SYNC();
-            if (ldcg(&ist->task_quit)) break;
-            if (tid == 0) sh->perim = 0;
-            i32 rect[4];
-            for (int k2 = 0; k2 < 4; ++k2) rect[k2] = ldcg(&ist->task_rect[k2]);
-            const u32 tc = ldcg(&ist->task_c);
-            __syncthreads();
-            const u32 rh = (u32)(rect[3] - rect[1]);
-            s2_perimeter_rows(a, sh, img, base, tc, rect, (u32)((u64)rh * crank / G), (u32)((u64)rh * (crank + 1) / G));
-            __syncthreads();
-            if (tid == 0) { if (sh->perim) atomicAdd(&ist->perim_acc, sh->perim); __threadfence(); }
-            __syncthreads();
-            VCB_CLUSTER_SYNC();
-        }
-        return;
-    }
-
-    if (tid == 0) {
-        const u32 cnt = *a.count;
-        u32 lo = 0, hi = cnt;                       // first key of this image
-        while (lo < hi) { const u32 mid = (lo + hi) / 2; if ((u32)(keys[mid] >> kshift) < img) lo = mid + 1; else hi = mid; }
-        sh->lo = lo;
-        hi = cnt;
-        u32 l2 = lo;
-        while (l2 < hi) { const u32 mid = (l2 + hi) / 2; if ((u32)(keys[mid] >> kshift) <= img) l2 = mid + 1; else hi = mid; }
-        sh->hi = l2;
-        sh->nurg = 0; sh->force_single = 0; sh->mode = 0; sh->brounds = 0; sh->bdone = 0; sh->boff = 0;
-    }
-    __syncthreads();
-
     while (true) {
         if (a.cfg.batch_rounds && sh->boff == 0 && s2_batch_round(a, sh, ist, keys, epoch, img, base, over)) continue;
         if (tid == 0) {
@@ -684,7 +680,7 @@ __global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_epoch(S2 a, const u64 *ke
             u32 c = NONE, carea = 0;
             while (true) {
                 u64 kb = ~0ull; int src = -1; u32 which = 0;
-                if (sh->lo < sh->hi) { kb = (keys[sh->lo] & ((1ull << kshift) - 1ull)) + ((u64)area_base << a.idx_bits); src = 0; }
+                if (sh->lo < sh->hi) { kb = s2_key(keys, sh->lo); src = 0; }
                 for (u32 i = 0; i < sh->nurg; ++i) if (sh->urgent[i] < kb) { kb = sh->urgent[i]; src = 1; which = i; }
                 for (u32 i = 0; i < ist->nover; ++i) if (over[i] < kb) { kb = over[i]; src = 2; which = i; }
                 if (src < 0) break;
@@ -889,12 +885,122 @@ __global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_epoch(S2 a, const u64 *ke
         }
         __syncthreads();
     }
-    (void)nslots;
-    if (G > 1) {                                                      // release the helper CTAs
-        if (tid == 0) { stcg(&ist->task_quit, 1u); __threadfence(); }
-        __syncthreads();
-        VCB_CLUSTER_SYNC();
+}
+
+// multi-launch path: one launch per epoch over the globally sorted keys of all images (prims::radix_sort between launches)
+__global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_epoch(S2 a, const u64 *gkeys, int epoch, u32 G) {
+    VCB_SMEM(S2Shared, sh);
+    const u32 img = blockIdx.x / G, crank = blockIdx.x % G, base = a.slot_base[img];   // G CTAs (one cluster) per image
+    const u32 tid = threadIdx.x;
+    S2ImgState *ist = a.ist + img;
+    const int kshift = a.idx_bits + epoch;                      // sorted keys: image | (area - 2^epoch) | index
+    if (crank != 0) { s2_helper_loop(a, sh, ist, img, base, crank, G); return; }
+    if (tid == 0) {
+        const u32 cnt = *a.count;
+        u32 lo = 0, hi = cnt;                       // first key of this image
+        while (lo < hi) { const u32 mid = (lo + hi) / 2; if ((u32)(gkeys[mid] >> kshift) < img) lo = mid + 1; else hi = mid; }
+        sh->lo = lo;
+        hi = cnt;
+        u32 l2 = lo;
+        while (l2 < hi) { const u32 mid = (l2 + hi) / 2; if ((u32)(gkeys[mid] >> kshift) <= img) l2 = mid + 1; else hi = mid; }
+        sh->hi = l2;
+        sh->nurg = 0; sh->force_single = 0; sh->mode = 0; sh->brounds = 0; sh->bdone = 0; sh->boff = 0;
     }
+    __syncthreads();
+    const S2Keys keys{gkeys, nullptr, (1ull << kshift) - 1ull, (u64)(1u << epoch) << a.idx_bits};
+    s2_epoch_leader(a, sh, ist, keys, epoch, img, base, a.over + base, G);
+    s2_release_helpers(ist, G);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused path: ONE launch replays every epoch.  The CTA keeps the image's live roots as a compact list (index order); at the
+// start of an epoch it drops the absorbed ones, emits the pop keys of the roots whose area lies in [2^e, 2^(e+1)) into
+// shared memory and sorts them there (bitonic; index order makes epoch 0 sorted as collected).  No per-epoch host work,
+// no global sort: the hierarchical stage of a batch is one kernel, which lets several batches overlap on the device.
+__device__ static __forceinline__ u32 s2_collect_epoch(const S2 &a, S2Shared *sh, u64 *skeys, u32 base, u32 nslots, int ep, bool initial) {
+    const u32 T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = (T + 31) >> 5;
+    const u32 nin = initial ? nslots : sh->nlive;
+    u32 kept = 0, taken = 0;                                    // uniform running totals
+    for (u32 t0 = 0; t0 < nin; t0 += T) {
+        const u32 i = t0 + tid;
+        u32 s = NONE, area = 0;
+        bool keep = false, take = false;
+        if (i < nin) {
+            s = initial ? i : a.live[base + i];
+            if (ldcg(&a.fw[base + s]) == s) {
+                area = a.rec[base + s].indices_len;
+                keep = area != 0;
+                take = keep && (31 - __clz((int)area)) == ep;
+            }
+        }
+        const u32 mk = __ballot_sync(0xffffffffu, keep), mt = __ballot_sync(0xffffffffu, take);
+        if (lane == 0) sh->wsum[warp] = (u32)__popc(mk) | ((u32)__popc(mt) << 16);
+        __syncthreads();
+        u32 pk = 0, pt = 0, tk = 0, tt = 0;
+        for (u32 w = 0; w < nw; ++w) {
+            const u32 v = sh->wsum[w];
+            if (w < warp) { pk += v & 0xffffu; pt += v >> 16; }
+            tk += v & 0xffffu; tt += v >> 16;
+        }
+        // in place: the entries of this tile were read before the barrier, later tiles start at t0 + T >= kept + tk
+        if (keep) a.live[base + kept + pk + (u32)__popc(mk & ((1u << lane) - 1u))] = s;
+        if (take) skeys[taken + pt + (u32)__popc(mt & ((1u << lane) - 1u))] = ((u64)area << a.idx_bits) | s;
+        kept += tk; taken += tt;
+        __syncthreads();
+    }
+    if (tid == 0) sh->nlive = kept;
+    __syncthreads();
+    return taken;
+}
+// Bitonic sort, ascending, in the "normalised" form whose every compare-exchange moves the smaller key to the lower
+// index: keys beyond n behave as +infinity without being stored, so any n works in place (shared or global memory).
+__device__ static __forceinline__ void s2_sort_keys(u64 *k, u32 n) {
+    const u32 T = blockDim.x, tid = threadIdx.x;
+    u32 m = 1;
+    while (m < n) m <<= 1;
+    for (u32 size = 2; size <= m; size <<= 1) {
+        const u32 half = size >> 1;
+        for (u32 t = tid; t < (m >> 1); t += T) {
+            const u32 blk = t / half, off = t - blk * half;
+            const u32 i = blk * size + off, j = blk * size + size - 1u - off;
+            if (j < n) { const u64 x = k[i], y = k[j]; if (x > y) { k[i] = y; k[j] = x; } }
+        }
+        __syncthreads();
+        for (u32 stride = half >> 1; stride > 0; stride >>= 1) {
+            for (u32 t = tid; t < (m >> 1); t += T) {
+                const u32 i = ((t & ~(stride - 1u)) << 1) | (t & (stride - 1u)), j = i + stride;
+                if (j < n) { const u64 x = k[i], y = k[j]; if (x > y) { k[i] = y; k[j] = x; } }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_run(S2 a, int max_epoch, u32 G) {
+    VCB_SMEM(S2Shared, sh);
+    const u32 img = blockIdx.x / G, crank = blockIdx.x % G, base = a.slot_base[img];
+    const u32 nslots = a.slot_base[img + 1] - base;
+    const u32 tid = threadIdx.x;
+    S2ImgState *ist = a.ist + img;
+    if (crank != 0) { s2_helper_loop(a, sh, ist, img, base, crank, G); return; }
+    // the key array follows the fixed part of the shared block (and the byte map of the rect-scan perimeter mode)
+    u64 *skeys = reinterpret_cast<u64 *>(reinterpret_cast<u8 *>(sh) + ((offsetof(S2Shared, map) + (a.cfg.rect_perim ? S2_MAPBYTES : 0u) + 15u) & ~(size_t)15));
+    if (tid == 0) sh->nlive = nslots;
+    __syncthreads();
+    for (int ep = 0; ep <= max_epoch; ++ep) {
+        // the roots still alive bound the number of keys: shared memory when they fit, the image's global key range otherwise
+        u64 *kbuf = (ep == 0 ? nslots : sh->nlive) <= a.key_cap ? skeys : a.keys + base;
+        __syncthreads();
+        const u32 n = s2_collect_epoch(a, sh, kbuf, base, nslots, ep, ep == 0);
+        if (n == 0) continue;
+        if (ep > 0 && n > 1) s2_sort_keys(kbuf, n);              // epoch 0: every area is 1, collected in index order
+        if (tid == 0) { sh->lo = 0; sh->hi = n; sh->nurg = 0; sh->force_single = 0; sh->mode = 0; sh->brounds = 0; sh->bdone = 0; sh->boff = 0; }
+        __syncthreads();
+        const S2Keys keys{nullptr, kbuf, 0ull, 0ull};
+        s2_epoch_leader(a, sh, ist, keys, ep, img, base, a.over + base, G);
+        __syncthreads();
+    }
+    s2_release_helpers(ist, G);
 }
 
 // ------------------------------------------------------------------------------------------------- finalisation

@@ -84,8 +84,11 @@ int run_color_empty(vcb_ctx *c, const vcb_runner_config *cfg, u32 w, u32 h, size
     return check_stream(c);
 }
 
+// retain: keep a private copy of the input in the result (host inputs are staged in a buffer the next call reuses);
+// otherwise the result only remembers the caller's device pointer.  async_s2: the hierarchical stage is queued on a
+// workspace set's stream and the result must be completed with stage2_finish before it is handed out.
 int run_color(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w, u32 h, size_t nimg, bool want_pool,
-              bool retain, std::shared_ptr<BatchResult> &out_br, const DevSet *ds = nullptr) {
+              bool retain, std::shared_ptr<BatchResult> &out_br, const DevSet *ds = nullptr, bool async_s2 = false) {
     int e = validate_cfg(c, cfg);
     if (e) return e;
     if ((u64)w * h == 0) return run_color_empty(c, cfg, w, h, nimg, out_br);
@@ -107,7 +110,8 @@ int run_color(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w,
         br->pixels = (u8 *)rt::dev_malloc_async(c->st, (size_t)d.N * 4);
         if (!br->pixels) return fail(c, VCB_ERR_NOMEM, "device out of memory (image copy)");
         rt::copy_d2d(c->st, br->pixels, d_rgba, (size_t)d.N * 4);
-    }
+    } else
+        br->ext_pixels = d_rgba;
 
     ColorPolicy pol;
     pol.rgba = (const u32 *)d_rgba;
@@ -140,7 +144,7 @@ int run_color(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w,
             rt::launch(c->st, "k_save_off1", rt::SEQ, k_save_off1, dim3(grid_for(c, br->total_slots, 256, 16)), dim3(256), 0,
                        (const vcb_cluster_rec *)br->rec, br->total_slots, br->off1);
         }
-        e = run_stage2(c, d, cfg, pol.has_key != 0, br.get());
+        e = stage2_launch(c, d, cfg, pol.has_key != 0, br.get(), async_s2 && !ds);
         if (e) return fail(c, e, c->err.empty() ? "hierarchical stage failed" : c->err);
     }
     out_br = br;
@@ -151,28 +155,47 @@ int run_color(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w,
 // per-image stage-2 CTAs want >= 148 images in flight, so one chunk is sized to fill the SMs without exhausting HBM.
 constexpr u64 MAX_CHUNK_PX = 320ull << 20;
 
+// images per device batch of a hierarchical run over many images: small enough that the stage 2 of several batches overlaps
+// the stage 1 of the following ones (S2Set), large enough to amortise the fixed cost of the ~40 launches per batch
+size_t chunk_images(const vcb_runner_config *cfg, u64 n64, size_t nimg) {
+    size_t per = n64 ? (size_t)(MAX_CHUNK_PX / n64) : nimg;
+    if (per < 1) per = 1;
+    if (cfg->hierarchical != 0) {
+        if (const char *ev = std::getenv("VCB_CHUNK_IMAGES")) per = std::min(per, (size_t)std::max(1, std::atoi(ev)));
+        else if (nimg > 96) per = std::min<size_t>(per, 128);
+    }
+    return per;
+}
+
 int run_color_device(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w, u32 h, size_t nimg,
-                     vcb_clusters **out) {
+                     vcb_clusters **out, bool retain) {
     if (!out) return fail(c, VCB_ERR_INVALID_ARG, "null output");
     if (nimg == 0) return VCB_OK;
     for (size_t i = 0; i < nimg; ++i) out[i] = nullptr;         // on failure every entry is null: nothing for the caller to free
     const u64 n64 = (u64)w * h;
-    size_t per_chunk = n64 ? (size_t)(MAX_CHUNK_PX / n64) : nimg;
-    if (per_chunk < 1) per_chunk = 1;
-    for (size_t i0 = 0; i0 < nimg; i0 += per_chunk) {
+    const size_t per_chunk = chunk_images(cfg, n64, nimg);
+    std::vector<std::shared_ptr<BatchResult>> brs;
+    int e = VCB_OK;
+    for (size_t i0 = 0; i0 < nimg && !e; i0 += per_chunk) {
         const size_t cnt = nimg - i0 < per_chunk ? nimg - i0 : per_chunk;
         std::shared_ptr<BatchResult> br;
-        int e = run_color(c, cfg, d_rgba + i0 * n64 * 4, w, h, cnt, c->opt_materialize != 0, true, br);
-        if (e) {
-            for (size_t k = 0; k < nimg; ++k) { delete out[k]; out[k] = nullptr; }
-            return e;
-        }
-        for (size_t i = 0; i < cnt; ++i) {
+        e = run_color(c, cfg, d_rgba + i0 * n64 * 4, w, h, cnt, c->opt_materialize != 0, retain, br, nullptr, nimg > per_chunk);
+        if (!e) brs.push_back(br);
+    }
+    for (auto &br : brs) {                                      // complete the hierarchical stages still in flight
+        const int e2 = stage2_finish(c, br.get());
+        if (!e) e = e2;
+    }
+    if (e) return e;
+    size_t i0 = 0;
+    for (auto &br : brs) {
+        for (u32 i = 0; i < br->d.nimg; ++i) {
             vcb_clusters *hd = new (std::nothrow) vcb_clusters();
-            if (!hd) return fail(c, VCB_ERR_NOMEM, "host out of memory");
-            hd->br = br; hd->img = (u32)i;
+            if (!hd) { for (size_t k = 0; k < nimg; ++k) { delete out[k]; out[k] = nullptr; } return fail(c, VCB_ERR_NOMEM, "host out of memory"); }
+            hd->br = br; hd->img = i;
             out[i0 + i] = hd;
         }
+        i0 += br->d.nimg;
     }
     return VCB_OK;
 }
@@ -181,9 +204,10 @@ int run_color_device(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba,
 int ensure_pool(BatchResult *br) {
     if (br->pool || br->d.n == 0) return VCB_OK;
     vcb_ctx *c = br->ctx;
-    if (!br->pixels) return fail(c, VCB_ERR_INVALID_ARG, "result holds no image to rebuild the indices from");
+    const u8 *px = br->pixels ? br->pixels : br->ext_pixels;
+    if (!px) return fail(c, VCB_ERR_INVALID_ARG, "result holds no image to rebuild the indices from");
     std::shared_ptr<BatchResult> tmp;
-    int e = run_color(c, &br->cfg, br->pixels, br->d.w, br->d.h, br->d.nimg, true, false, tmp);
+    int e = run_color(c, &br->cfg, px, br->d.w, br->d.h, br->d.nimg, true, false, tmp);
     if (e) return e;
     std::swap(br->pool, tmp->pool);
     br->pool_base = tmp->pool_base;
@@ -253,8 +277,7 @@ void vcb_ctx_destroy(vcb_ctx *c) {
     rt::dev_free(b.cand); rt::dev_free(b.ea); rt::dev_free(b.eb); rt::dev_free(b.newlist); rt::dev_free(b.attr); rt::dev_free(b.labex); rt::dev_free(b.leaflist); rt::dev_free(b.meta); rt::dev_free(b.ctr);
     rt::dev_free(c->chunksum); rt::dev_free(c->rs_table); rt::dev_free(c->sk0); rt::dev_free(c->sk1);
     rt::dev_free(c->sv0); rt::dev_free(c->sv1); rt::dev_free(c->d_small); rt::dev_free(c->d_stage);
-    rt::dev_free(c->s2_fw); rt::dev_free(c->s2_mnext); rt::dev_free(c->s2_mtail); rt::dev_free(c->s2_mark); rt::dev_free(c->s2_adj_off);
-    rt::dev_free(c->s2_cursor); rt::dev_free(c->s2_adj); rt::dev_free(c->s2_tmin); rt::dev_free(c->s2_bnd_off); rt::dev_free(c->s2_bcur); rt::dev_free(c->s2_bnd_px); rt::dev_free(c->s2_over); rt::dev_free(c->s2_ist);
+    for (S2Set *&set : c->s2_sets) { if (set && set->ready) rt::stream_sync(set->st); free_s2_set(set); set = nullptr; }
     rt::dev_free(c->d_in[0]); rt::dev_free(c->d_in[1]);
     if (c->pipe_ready) { rt::stream_destroy(c->st_h2d); rt::stream_destroy(c->st_d2h); }
     for (rt::VmmArray *a : {&c->bw_flags, &c->bw_pc, &c->bw_la, &c->bw_ls, &c->bw_lr, &c->bw_ev, &c->bw_rgba}) rt::vmm_free(*a);
@@ -271,7 +294,8 @@ int vcb_ctx_device(const vcb_ctx *c) { return c ? c->device : -1; }
 int vcb_runner_run_device(vcb_ctx *c, const vcb_runner_config *cfg, const uint8_t *d_rgba, uint32_t width,
                           uint32_t height, size_t n, vcb_clusters **out) {
     if (!c) return VCB_ERR_INVALID_ARG;
-    return run_color_device(c, cfg, d_rgba, width, height, n, out);
+    // the caller owns d_rgba and keeps it alive while it uses take_image / the ordered lists of these handles
+    return run_color_device(c, cfg, d_rgba, width, height, n, out, false);
 }
 
 int vcb_runner_run(vcb_ctx *c, const vcb_runner_config *cfg, const uint8_t *rgba, uint32_t width, uint32_t height,
@@ -282,13 +306,13 @@ int vcb_runner_run(vcb_ctx *c, const vcb_runner_config *cfg, const uint8_t *rgba
     int e = validate_cfg(c, cfg);
     if (e) return e;
     const size_t bytes = (size_t)width * height * 4;
-    if (bytes == 0) return run_color_device(c, cfg, nullptr, width, height, 1, out);
+    if (bytes == 0) return run_color_device(c, cfg, nullptr, width, height, 1, out, true);
     if (!rgba) return fail(c, VCB_ERR_INVALID_ARG, "null image");
     rt::set_device(c->device);
     u8 *d = stage_input(c, bytes);
     if (!d) return fail(c, VCB_ERR_NOMEM, "device out of memory (input)");
     rt::copy_h2d(c->st, d, rgba, bytes);
-    return run_color_device(c, cfg, d, width, height, 1, out);
+    return run_color_device(c, cfg, d, width, height, 1, out, true);
 }
 
 int vcb_runner_run_batch_host(vcb_ctx *c, const vcb_runner_config *cfg, const uint8_t *const *rgba, uint32_t width,
@@ -328,16 +352,15 @@ int vcb_runner_run_batch_host(vcb_ctx *c, const vcb_runner_config *cfg, const ui
         rt::event_record(ev_in[k], c->st_h2d);
     };
     int rc = VCB_OK;
-    upload(0);
-    for (size_t k = 0; k < nchunks && rc == VCB_OK; ++k) {
+    // results of sub-batch k go back to the host once its hierarchical stage (queued on a workspace set's stream) is complete:
+    // that wait is taken after sub-batch k + 1 has been queued, so the device never idles on the host
+    auto download = [&](size_t k) -> int {
         const size_t i0 = k * per, cnt = std::min(per, n - i0);
-        if (k + 1 < nchunks) upload(k + 1);                     // the other input buffer: its last reader (chunk k-1) is finished
-        rt::stream_wait(c->st, ev_in[k]);
-        e = run_color(c, cfg, c->d_in[k & 1], width, height, cnt, false, false, keep[k]);
-        if (e) { rc = e; break; }
+        BatchResult *br = keep[k].get();
+        int e2 = stage2_finish(c, br);
+        if (e2) return e2;
         rt::event_record(ev_done[k], c->st);
         rt::stream_wait(c->st_d2h, ev_done[k]);
-        const BatchResult *br = keep[k].get();
         // the last record of every image carries the list totals: one small read for the whole sub-batch
         for (size_t i = 0; i < cnt; ++i) {
             vcb_host_result &r = results[i0 + i];
@@ -356,7 +379,18 @@ int vcb_runner_run_batch_host(vcb_ctx *c, const vcb_runner_config *cfg, const ui
                 else if (br->nout[i]) rt::copy_d2h(c->st_d2h, r.outputs, br->outputs + s0, (size_t)br->nout[i] * 4);
             }
         }
+        return VCB_OK;
+    };
+    upload(0);
+    for (size_t k = 0; k < nchunks && rc == VCB_OK; ++k) {
+        const size_t cnt = std::min(per, n - k * per);
+        if (k + 1 < nchunks) upload(k + 1);                     // the other input buffer: its last reader (chunk k-1) is finished
+        rt::stream_wait(c->st, ev_in[k]);
+        e = run_color(c, cfg, c->d_in[k & 1], width, height, cnt, false, false, keep[k], nullptr, true);
+        if (e) { rc = e; break; }
+        if (k > 0) { e = download(k - 1); if (e) { rc = e; break; } }
     }
+    if (rc == VCB_OK && nchunks > 0) rc = download(nchunks - 1);
     if (rt::stream_sync(c->st_d2h) != 0 || rt::stream_sync(c->st_h2d) != 0) rc = rc ? rc : VCB_ERR_CUDA;
     if (rc == VCB_OK) {
         for (size_t i = 0; i < n; ++i) {
@@ -471,7 +505,7 @@ int vcb_runner_run_batch(vcb_ctx *c, const vcb_runner_config *cfg, const uint8_t
                 rt::copy_h2d(c->st, d + (k - i) * bytes, rgba[k], bytes);
             }
         }
-        e = run_color_device(c, cfg, d, width[i], height[i], j - i, out + i);
+        e = run_color_device(c, cfg, d, width[i], height[i], j - i, out + i, true);
         if (e) { out[i] = nullptr; release_all(); return e; }
         i = j;
     }
@@ -539,8 +573,9 @@ int vcb_clusters_take_image(const vcb_clusters *h, uint8_t *rgba_out) {
     if (h->br->d.n == 0) return VCB_OK;
     if (!rgba_out) return VCB_ERR_INVALID_ARG;
     const BatchResult *br = h->br.get();
-    if (!br->pixels) return fail(br->ctx, VCB_ERR_INVALID_ARG, "result holds no image");
-    rt::copy_d2h(br->ctx->st, rgba_out, br->pixels + (size_t)h->img * br->d.n * 4, (size_t)br->d.n * 4);
+    const u8 *px = br->pixels ? br->pixels : br->ext_pixels;
+    if (!px) return fail(br->ctx, VCB_ERR_INVALID_ARG, "result holds no image");
+    rt::copy_d2h(br->ctx->st, rgba_out, px + (size_t)h->img * br->d.n * 4, (size_t)br->d.n * 4);
     return check_stream(br->ctx);
 }
 
@@ -576,9 +611,11 @@ int vcb_clusters_to_color_image(const vcb_clusters *h, uint8_t *rgba_out) {
         S2 a{};
         a.d = br->d; a.l1 = br->labels1; a.rec = br->rec; a.slot_base = br->d_slot_base; a.slot_img = br->d_slot_img;
         a.total_slots = br->total_slots; a.mpar = br->mpar; a.outpos = br->outpos;
-        u32 *slot_color = c->s2_cursor;      // scratch, total_slots entries
+        u32 *slot_color = (u32 *)rt::dev_malloc_async(c->st, (size_t)br->total_slots * 4 + 4);
+        if (!slot_color) return fail(c, VCB_ERR_NOMEM, "device out of memory");
         rt::launch(c->st, "k_s2_slot_color", rt::SEQ, k_s2_slot_color, dim3(grid_for(c, br->total_slots, 256, 16)), dim3(256), 0, a, slot_color);
         rt::launch(c->st, "k_s2_paint", rt::SEQ, k_s2_paint, dim3(grid_for(c, n, 256, 16)), dim3(256), 0, a, (const u32 *)slot_color, h->img, (u32 *)d);
+        rt::dev_free_async(c->st, slot_color);
     } else
     rt::launch(c->st, "k_color_image_flat", rt::SEQ, k_color_image_flat, dim3(grid_for(c, n, REC_THREADS, 16)), dim3(REC_THREADS), 0,
                n, (const u32 *)(br->labels + (size_t)h->img * n), (const vcb_cluster_rec *)(br->rec + br->slot_base[h->img]), (u32 *)d);

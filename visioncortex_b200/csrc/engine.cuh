@@ -33,7 +33,7 @@ struct vcb_ctx {
     rt::Stream st;
     std::string err;
     // workspace arena (grow-only, sized by the largest batch seen)
-    size_t capN = 0;
+    size_t capN = 0, capN_px = 0, cap_slots = 0;
     vcb::Bufs b{};
     u32 *chunksum = nullptr;          // scan scratch
     u32 *rs_table = nullptr;          // radix sort digit table
@@ -56,6 +56,7 @@ struct vcb_ctx {
     rt::VmmArray bw_flags, bw_pc, bw_la, bw_ls, bw_lr, bw_ev, bw_rgba;
     size_t bw_capN = 0;
     int bw_ndev = 0;
+    int bw_devs[8] = {};
     u32 bw_split = 0;
     // stage-2 workspace sets: the hierarchical stage of one device batch runs on its set's own stream while the next batch's
     // stage 1 runs on `st` (see S2Set)
@@ -63,6 +64,7 @@ struct vcb_ctx {
     vcb::S2Set *s2_sets[MAX_S2_SETS] = {};
     int s2_next = 0;
     int coop_blocks = 0;              // occupancy of the cooperative spanning-forest kernel on this device
+    bool s2_overlap = false;          // the current call overlaps stage 2 with the following device batches
 #ifndef VCB_HOSTSIM
     cudaEvent_t events[16] = {};
 #endif
@@ -122,21 +124,37 @@ template <class T> inline bool grow(T *&p, size_t n) {
     return p != nullptr;
 }
 
-inline int ensure_workspace(vcb_ctx *c, size_t N, size_t nimg) {
-    if (N > c->capN) {
+// banded: the per-pixel arrays that the row-band mode stripes over the devices (flags, pc, leaf and event records) come from
+// the striped allocation instead and are not allocated here
+inline int ensure_workspace(vcb_ctx *c, size_t N, size_t nimg, bool banded = false) {
+    if (!banded && N > c->capN_px) {
         const size_t cap = N + 64;
         bool ok = true;
         ok &= grow(c->b.flags, cap); ok &= grow(c->b.pc, cap); ok &= grow(c->b.la, cap); ok &= grow(c->b.ls, cap);
-        ok &= grow(c->b.lr, cap); ok &= grow(c->b.ev, cap); ok &= grow(c->b.cand, cap); ok &= grow(c->b.ea, cap); ok &= grow(c->b.eb, cap); ok &= grow(c->b.newlist, cap);
+        ok &= grow(c->b.lr, cap); ok &= grow(c->b.ev, cap);
+        if (!ok) { c->capN_px = 0; return VCB_ERR_NOMEM; }
+        c->capN_px = N;
+    }
+    if (N > c->capN) {
+        const size_t cap = N + 64;
+        bool ok = true;
+        ok &= grow(c->b.cand, cap); ok &= grow(c->b.ea, cap); ok &= grow(c->b.eb, cap); ok &= grow(c->b.newlist, cap);
         ok &= grow(c->b.attr, cap); ok &= grow(c->b.labex, cap); ok &= grow(c->b.leaflist, cap);
-        const size_t chunks = cap / 2048 + 4;
-        ok &= grow(c->chunksum, 256 * chunks / 2048 + chunks + 1024);
-        ok &= grow(c->rs_table, 256 * chunks + 16);
-        ok &= grow(c->sk0, cap + nimg + 16); ok &= grow(c->sk1, cap + nimg + 16);
-        ok &= grow(c->sv0, cap + nimg + 16); ok &= grow(c->sv1, cap + nimg + 16);
         if (!c->b.ctr) ok &= grow(c->b.ctr, 1);
         if (!ok) { c->capN = 0; return VCB_ERR_NOMEM; }
         c->capN = N;
+    }
+    // buffers indexed by slots as well as by pixels: a batch can own up to N + nimg slots (every pixel its own cluster plus the
+    // ZERO slot of every image), so they follow their own capacity -- many tiny images after one large image must regrow them
+    const size_t slots = N + nimg + 64;
+    if (slots > c->cap_slots) {
+        const size_t chunks = slots / 2048 + 4;
+        bool ok = grow(c->chunksum, 256 * chunks / 2048 + chunks + 1024);
+        ok &= grow(c->rs_table, 256 * chunks + 16);
+        ok &= grow(c->sk0, slots); ok &= grow(c->sk1, slots);
+        ok &= grow(c->sv0, slots); ok &= grow(c->sv1, slots);
+        if (!ok) { c->cap_slots = 0; return VCB_ERR_NOMEM; }
+        c->cap_slots = slots;
     }
     if (nimg > c->cap_img) {
         bool ok = grow(c->b.meta, nimg + 1);
@@ -199,17 +217,15 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 inline PFN_encodeTiled get_encode_tiled() {
-    static PFN_encodeTiled fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // initialised once, thread-safe (distinct contexts may be used from distinct threads)
+    static const PFN_encodeTiled fn = [] {
         void *p = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
-            fn = (PFN_encodeTiled)p;
-        else
-            cudaGetLastError();
-    }
+            return (PFN_encodeTiled)p;
+        cudaGetLastError();
+        return (PFN_encodeTiled) nullptr;
+    }();
     return fn;
 }
 template <> inline bool launch_edges_tma<ColorPolicy>(vcb_ctx *c, const Dims &d, const ColorPolicy &pol, const Bufs &b, u32 tile0, u32 tiles) {
@@ -284,6 +300,9 @@ inline int run_stage1(vcb_ctx *c, const Dims &d, const P &pol, u32 base, bool wa
     {
         if (!c->coop_blocks) c->coop_blocks = rt::max_coop_blocks((const void *)k_boruvka, K3_THREADS, 0, c->device);
         int g = c->coop_blocks;
+        // a cooperative grid must be resident as a whole: while the hierarchical stage of earlier device batches occupies part of
+        // every SM (S2Set), a full-occupancy grid would wait for those kernels to drain, so it is sized to fit beside them
+        if (c->s2_overlap && g > c->sms * 2) g = c->sms * 2;
         const int want = (int)((d.N / 4 + K3_THREADS - 1) / K3_THREADS);
         if (g > want) g = want < 1 ? 1 : want;
         rt::launch(st, "k_boruvka", rt::COOP, k_boruvka, dim3(g), dim3(K3_THREADS), 0, b);
@@ -436,7 +455,7 @@ inline int materialize_pool(vcb_ctx *c, const Dims &d, BatchResult *res, bool ke
 }
 
 // Stage 2 (builder.rs:379-539) on the records / labels produced by stage 1.  See stage2.cuh.
-inline S2Set *acquire_s2_set(vcb_ctx *c);
+inline S2Set *acquire_s2_set(vcb_ctx *c, bool async);
 inline int stage2_finish(vcb_ctx *c, BatchResult *res);
 
 inline int ensure_s2_set(vcb_ctx *c, S2Set *s, const Dims &d, u32 total) {
@@ -491,7 +510,7 @@ inline int stage2_launch(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg
     const u32 total = res->total_slots;
     const bool legacy = std::getenv("VCB_S2_LEGACY") != nullptr;           // per-epoch launches + global sorts (uses the ctx scratch)
     if (legacy) async = false;
-    S2Set *set = acquire_s2_set(c);
+    S2Set *set = acquire_s2_set(c, async);
     if (!set) return VCB_ERR_NOMEM;
     int e = ensure_s2_set(c, set, d, total);
     if (e) return e;
@@ -643,10 +662,10 @@ inline int stage2_finish(vcb_ctx *c, BatchResult *res) {
 }
 
 // next workspace set in round-robin order; a set still serving an earlier result is completed first
-inline S2Set *acquire_s2_set(vcb_ctx *c) {
+inline S2Set *acquire_s2_set(vcb_ctx *c, bool async) {
     const int nsets = std::max(1, std::min((int)vcb_ctx::MAX_S2_SETS, std::getenv("VCB_S2_SETS") ? std::atoi(std::getenv("VCB_S2_SETS")) : 4));
-    const int k = c->s2_next % nsets;
-    c->s2_next = (k + 1) % nsets;
+    int k = 0;                                                  // a run that does not overlap anything always takes set 0
+    if (async) { k = c->s2_next % nsets; c->s2_next = (k + 1) % nsets; }
     if (!c->s2_sets[k]) c->s2_sets[k] = new (std::nothrow) S2Set();
     S2Set *s = c->s2_sets[k];
     if (s && s->busy) stage2_finish(c, s->busy);

@@ -176,6 +176,7 @@ int run_color_device(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba,
     const size_t per_chunk = chunk_images(cfg, n64, nimg);
     std::vector<std::shared_ptr<BatchResult>> brs;
     int e = VCB_OK;
+    c->s2_overlap = cfg->hierarchical != 0 && nimg > per_chunk;
     for (size_t i0 = 0; i0 < nimg && !e; i0 += per_chunk) {
         const size_t cnt = nimg - i0 < per_chunk ? nimg - i0 : per_chunk;
         std::shared_ptr<BatchResult> br;
@@ -186,6 +187,7 @@ int run_color_device(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba,
         const int e2 = stage2_finish(c, br.get());
         if (!e) e = e2;
     }
+    c->s2_overlap = false;
     if (e) return e;
     size_t i0 = 0;
     for (auto &br : brs) {
@@ -223,6 +225,11 @@ u8 *stage_input(vcb_ctx *c, size_t bytes) {
         c->d_stage_cap = c->d_stage ? bytes : 0;
     }
     return c->d_stage;
+}
+
+template <class F> void for_each_stream(vcb_ctx *c, F f) {
+    f(c->st);
+    for (S2Set *set : c->s2_sets) if (set && set->ready) f(set->st);
 }
 
 }  // namespace
@@ -382,15 +389,17 @@ int vcb_runner_run_batch_host(vcb_ctx *c, const vcb_runner_config *cfg, const ui
         return VCB_OK;
     };
     upload(0);
+    c->s2_overlap = cfg->hierarchical != 0 && nchunks > 1;
     for (size_t k = 0; k < nchunks && rc == VCB_OK; ++k) {
         const size_t cnt = std::min(per, n - k * per);
         if (k + 1 < nchunks) upload(k + 1);                     // the other input buffer: its last reader (chunk k-1) is finished
         rt::stream_wait(c->st, ev_in[k]);
-        e = run_color(c, cfg, c->d_in[k & 1], width, height, cnt, false, false, keep[k], nullptr, true);
+        e = run_color(c, cfg, c->d_in[k & 1], width, height, cnt, false, false, keep[k], nullptr, nchunks > 1);
         if (e) { rc = e; break; }
         if (k > 0) { e = download(k - 1); if (e) { rc = e; break; } }
     }
     if (rc == VCB_OK && nchunks > 0) rc = download(nchunks - 1);
+    c->s2_overlap = false;
     if (rt::stream_sync(c->st_d2h) != 0 || rt::stream_sync(c->st_h2d) != 0) rc = rc ? rc : VCB_ERR_CUDA;
     if (rc == VCB_OK) {
         for (size_t i = 0; i < n; ++i) {
@@ -434,7 +443,10 @@ int vcb_runner_run_banded(vcb_ctx *const *ctxs, int nctx, const vcb_runner_confi
     const u32 N = (u32)n64;
     // striped workspace: device k owns pixels [k * split, (k + 1) * split); split is a multiple of the mapping granularity
     // for 1-byte elements, hence for every element size
-    if (N > c->bw_capN || nctx != c->bw_ndev) {
+    // (the pages are mapped on, and accessible from, one particular set of devices: a different set needs a new mapping)
+    bool same_devs = nctx == c->bw_ndev;
+    for (int k = 0; same_devs && k < nctx; ++k) same_devs = c->bw_devs[k] == devs[k];
+    if (N > c->bw_capN || !same_devs) {
         for (rt::VmmArray *a : {&c->bw_flags, &c->bw_pc, &c->bw_la, &c->bw_ls, &c->bw_lr, &c->bw_ev, &c->bw_rgba}) rt::vmm_free(*a);
         size_t gran = 1;
         for (int k = 0; k < nctx; ++k) gran = std::max(gran, rt::vmm_granularity(devs[k]));
@@ -450,8 +462,9 @@ int vcb_runner_run_banded(vcb_ctx *const *ctxs, int nctx, const vcb_runner_confi
         rc |= rt::vmm_alloc(c->bw_rgba, split, 4, nctx, devs, N);
         if (rc) { c->bw_capN = 0; return fail(c, VCB_ERR_NOMEM, "striped workspace allocation failed"); }
         c->bw_capN = N; c->bw_ndev = nctx; c->bw_split = (u32)split;
+        for (int k = 0; k < nctx; ++k) c->bw_devs[k] = devs[k];
     }
-    e = ensure_workspace(c, N, 1);
+    e = ensure_workspace(c, N, 1, true);                        // only the arrays that are not striped
     if (e) return fail(c, e, "device out of memory (workspace)");
     DevSet ds;
     ds.n = nctx; ds.split = c->bw_split;
@@ -726,32 +739,41 @@ int vcb_ctx_synchronize(vcb_ctx *c) {
     return check_stream(c);
 }
 
-uint64_t vcb_ctx_kernel_launches(const vcb_ctx *c) { return c ? c->st.launches : 0; }
+uint64_t vcb_ctx_kernel_launches(const vcb_ctx *c) {
+    if (!c) return 0;
+    uint64_t n = c->st.launches;
+    for (const S2Set *set : c->s2_sets) if (set) n += set->st.launches;      // the hierarchical stage runs on the sets' streams
+    return n;
+}
 
 int vcb_ctx_profile_reset(vcb_ctx *c, int enable) {
     if (!c) return VCB_ERR_INVALID_ARG;
-    rt::stream_sync(c->st);
+    for_each_stream(c, [&](rt::Stream &st) {
+        rt::stream_sync(st);
 #ifndef VCB_HOSTSIM
-    for (auto &p : c->st.prof) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+        for (auto &p : st.prof) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
 #endif
-    c->st.prof.clear();
-    c->st.profiling = enable != 0;
+        st.prof.clear();
+        st.profiling = enable != 0;
+    });
     return VCB_OK;
 }
 
 int vcb_ctx_profile_read(vcb_ctx *c, const char *kernel_name, double *total_ms, uint64_t *launches) {
     if (!c || !total_ms || !launches) return VCB_ERR_INVALID_ARG;
-    rt::stream_sync(c->st);
     double t = 0; uint64_t n = 0;
+    for_each_stream(c, [&](rt::Stream &st) {
+        rt::stream_sync(st);
 #ifndef VCB_HOSTSIM
-    for (auto &p : c->st.prof) {
-        if (kernel_name && kernel_name[0] && std::strcmp(kernel_name, p.name) != 0) continue;
-        float ms = 0;
-        if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) { t += ms; ++n; }
-    }
+        for (auto &p : st.prof) {
+            if (kernel_name && kernel_name[0] && std::strcmp(kernel_name, p.name) != 0) continue;
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) { t += ms; ++n; }
+        }
 #else
-    (void)kernel_name;
+        (void)kernel_name;
 #endif
+    });
     *total_ms = t; *launches = n;
     return VCB_OK;
 }

@@ -41,26 +41,26 @@ struct VmmApi {
     bool ok = false;
 };
 inline VmmApi &vmm_api() {
-    static VmmApi api;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // initialised once, thread-safe (distinct contexts may be used from distinct threads)
+    static VmmApi api = [] {
+        VmmApi a;
         auto get = [](const char *name, void **fn) {
             cudaDriverEntryPointQueryResult q;
             return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
         };
         bool ok = true;
-        ok &= get("cuMemGetAllocationGranularity", (void **)&api.getGranularity);
-        ok &= get("cuMemAddressReserve", (void **)&api.addressReserve);
-        ok &= get("cuMemCreate", (void **)&api.create);
-        ok &= get("cuMemMap", (void **)&api.map);
-        ok &= get("cuMemSetAccess", (void **)&api.setAccess);
-        ok &= get("cuMemUnmap", (void **)&api.unmap);
-        ok &= get("cuMemRelease", (void **)&api.release);
-        ok &= get("cuMemAddressFree", (void **)&api.addressFree);
+        ok &= get("cuMemGetAllocationGranularity", (void **)&a.getGranularity);
+        ok &= get("cuMemAddressReserve", (void **)&a.addressReserve);
+        ok &= get("cuMemCreate", (void **)&a.create);
+        ok &= get("cuMemMap", (void **)&a.map);
+        ok &= get("cuMemSetAccess", (void **)&a.setAccess);
+        ok &= get("cuMemUnmap", (void **)&a.unmap);
+        ok &= get("cuMemRelease", (void **)&a.release);
+        ok &= get("cuMemAddressFree", (void **)&a.addressFree);
         if (!ok) cudaGetLastError();
-        api.ok = ok;
-    }
+        a.ok = ok;
+        return a;
+    }();
     return api;
 }
 inline bool vmm_available() { return vmm_api().ok; }

@@ -123,3 +123,124 @@ def random_blocky(rng: np.random.Generator, width: int, height: int, ncolors: in
     out[..., :3] = img.astype(np.uint8)
     out[..., 3] = 255
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The same generators on a torch device (bench.py builds its inputs on the GPU: 512 distinct 1080p scenes or one
+# 16384 x 16384 image take seconds there and minutes in numpy).  torch has no uint64 arithmetic: the hash runs in
+# wrapping int64 with logical shifts and an unsigned modulo spelled out.  tests/test_synth.py checks bit equality
+# with the numpy generators above.
+def _t_lsr(x, k: int):
+    return (x >> k) & ((1 << (64 - k)) - 1)
+
+
+def _t_i64(v: int) -> int:
+    v &= 0xFFFFFFFFFFFFFFFF
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def _t_mix(x):
+    x = x + _t_i64(0x9E3779B97F4A7C15)
+    x = (x ^ _t_lsr(x, 30)) * _t_i64(0xBF58476D1CE4E5B9)
+    x = (x ^ _t_lsr(x, 27)) * _t_i64(0x94D049BB133111EB)
+    return x ^ _t_lsr(x, 31)
+
+
+def _t_h(seed: int, stream: int, i):
+    import torch
+
+    base = _t_mix(torch.tensor([_t_i64(seed ^ (stream << 56))], dtype=torch.int64, device=i.device))
+    return _t_mix(base + i.to(torch.int64))
+
+
+def _t_umod(x, m: int):
+    """x mod m for x read as an unsigned 64-bit value (m < 2^31)."""
+    lo = x & 0x7FFFFFFFFFFFFFFF
+    top = _t_lsr(x, 63)
+    return (lo % m + top * ((1 << 63) % m)) % m
+
+
+def _t_voronoi_ids(width: int, height: int, seed: int, cell: int, device):
+    import torch
+
+    gx = (width + cell - 1) // cell
+    gy = (height + cell - 1) // cell
+    ids = torch.arange(gx * gy, dtype=torch.int64, device=device)
+    cx, cy = ids % gx, ids // gx
+    sx = (cx * cell + _t_umod(_t_h(seed, 2, ids), cell)).to(torch.int32)
+    sy = (cy * cell + _t_umod(_t_h(seed, 3, ids), cell)).to(torch.int32)
+    out = torch.empty((height, width), dtype=torch.int32, device=device)
+    xs = torch.arange(width, dtype=torch.int32, device=device)[None, :]
+    pcx = xs // cell
+    band = max(1, min(height, (1 << 24) // max(1, width)))
+    big = 2 ** 31 - 1
+    for y0 in range(0, height, band):
+        y1 = min(height, y0 + band)
+        ys = torch.arange(y0, y1, dtype=torch.int32, device=device)[:, None]
+        pcy = ys // cell
+        best_d = torch.full((y1 - y0, width), big, dtype=torch.int32, device=device)
+        best_id = torch.zeros((y1 - y0, width), dtype=torch.int32, device=device)
+        for dy in (-1, 0, 1):
+            qy = pcy + dy
+            oky = (qy >= 0) & (qy < gy)
+            for dx in (-1, 0, 1):
+                qx = pcx + dx
+                ok = oky & ((qx >= 0) & (qx < gx))
+                qid = torch.where(ok, qy * gx + qx, torch.zeros_like(qx + qy)).to(torch.int32)
+                q64 = qid.to(torch.int64)
+                ddx = xs - sx[q64]
+                ddy = ys - sy[q64]
+                dist = torch.where(ok, ddx * ddx + ddy * ddy, torch.full_like(ddx, big))
+                better = (dist < best_d) | ((dist == best_d) & (qid < best_id))
+                best_d = torch.where(better, dist, best_d)
+                best_id = torch.where(better, qid, best_id)
+        out[y0:y1] = best_id
+    return out, gx * gy
+
+
+def g2_scene_torch(width: int, height: int, seed: int, device, cell: int = 48, amp: int = 3):
+    """g2_scene on a torch device: uint8 (h, w, 4) tensor."""
+    import torch
+
+    best_id, ncell = _t_voronoi_ids(width, height, seed, cell, device)
+    col24 = _t_h(seed, 4, torch.arange(ncell, dtype=torch.int64, device=device)) & 0xFFFFFF
+    ys = torch.arange(height, dtype=torch.int64, device=device)[:, None]
+    xs = torch.arange(width, dtype=torch.int64, device=device)[None, :]
+    shade = ((xs + 2 * ys) >> 5) & 15
+    pix = ys * width + xs
+    out = torch.empty((height, width, 4), dtype=torch.uint8, device=device)
+    cid = best_id.to(torch.int64)
+    for ch in range(3):
+        v = ((col24[cid] >> (8 * ch)) & 0xFF) + shade
+        if amp > 0:
+            v = v + _t_umod(_t_h(seed, 5, pix * 4 + ch), 2 * amp + 1) - amp
+        out[..., ch] = v.clamp(0, 255).to(torch.uint8)
+    out[..., 3] = 255
+    return out
+
+
+def g3_posterised_torch(width: int, height: int, seed: int, device, cell: int = 96, key=None):
+    """g3_posterised on a torch device: uint8 (h, w, 4) tensor."""
+    import torch
+
+    best_id, ncell = _t_voronoi_ids(width, height, seed, cell, device)
+    ids = torch.arange(ncell, dtype=torch.int64, device=device)
+    col24 = _t_h(seed, 4, ids) & 0xFFFFFF
+    out = torch.empty((height, width, 4), dtype=torch.uint8, device=device)
+    cid = best_id.to(torch.int64)
+    for ch in range(3):
+        q = (((col24 >> (8 * ch)) & 0xFF) >> 6) * 85
+        out[..., ch] = q[cid].to(torch.uint8)
+    out[..., 3] = 255
+    if key is not None:
+        keyed = _t_umod(_t_h(seed, 6, ids), 10) == 0
+        out[keyed[cid]] = torch.tensor(list(key), dtype=torch.uint8, device=device)
+    return out
+
+
+def g1_binary_torch(width: int, height: int, p: float, seed: int, device):
+    import torch
+
+    n = width * height
+    bits = _t_lsr(_t_h(seed, 1, torch.arange(n, dtype=torch.int64, device=device)), 32) < int(p * (1 << 32))
+    return bits.reshape(height, width)

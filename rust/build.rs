@@ -1,5 +1,7 @@
+// Links the CUDA product library.  VCB200_LIB_DIR = directory holding libvcb200.so (visioncortex_b200/csrc after `make`).
 fn main() {
-    // libvcb200.so is built by `make -C visioncortex_b200/csrc` (nvcc, sm_100a)
-    println!("cargo:rustc-link-search=native=../visioncortex_b200/csrc");
+    let dir = std::env::var("VCB200_LIB_DIR").unwrap_or_else(|_| "../visioncortex_b200/csrc".to_string());
+    println!("cargo:rustc-link-search=native={}", dir);
     println!("cargo:rustc-link-lib=dylib=vcb200");
+    println!("cargo:rerun-if-env-changed=VCB200_LIB_DIR");
 }

@@ -1,0 +1,97 @@
+"""Shared checks of the reference-API mirror (visioncortex_b200/api.py) against the independent Python restatement of the
+reference (oracle/vc_restate.py): used on the host simulator (CPU) and on the GPU."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import vc_restate as R  # noqa: E402
+from visioncortex_b200 import api  # noqa: E402
+
+
+def check_runner_api(ctx, img: np.ndarray, **kw):
+    """Runner::start() / tick() / progress() / result(), Clusters / ClustersView / Cluster queries."""
+    h, w = img.shape[:2]
+    cfg = api.RunnerConfig(**{k: (api.Color(*v) if k == "key_color" else v) for k, v in kw.items()})
+    ref = R.Builder(R.Config(**kw), [tuple(int(v) for v in p) for p in img.reshape(-1, 4)], w, h).run()
+
+    runner = api.Runner.new(cfg, api.ColorImage.from_array(img))
+    runner._ctx = ctx
+    ib = runner.start()
+    assert ib.progress() == 0
+    assert ib.tick() is False          # the whole computation
+    assert ib.progress() == 100
+    assert ib.tick() is True
+    view = ib.view()
+    clusters = ib.result()
+    assert ib.progress() == 0          # builder.rs:131-135: the builder was taken
+    assert clusters.output_len() == len(ref.clusters_output)
+    assert [int(v) for v in view.clusters_output] == ref.clusters_output
+    assert [int(v) for v in view.cluster_indices] == ref.cluster_indices
+    assert len(view.clusters) == len(ref.clusters)
+    for k, (got, want) in enumerate(zip(view.clusters, ref.clusters)):
+        assert [int(v) for v in got.indices] == want.indices, k
+        assert [int(v) for v in got.holes] == want.holes, k
+        assert (got.num_holes, got.depth, got.merged_into) == (want.num_holes, want.depth, want.merged_into)
+        assert (got.rect.left, got.rect.top, got.rect.right, got.rect.bottom) == want.rect.tup()
+        assert got.area() == want.area()
+    # queries on the output clusters
+    for idx, got in zip(view.clusters_output, view.iter()):
+        want = ref.clusters[int(idx)]
+        assert got is view.get_cluster(int(idx))
+        assert got.color().tuple() == want.sum.average() and got.residue_color().tuple() == want.residue_sum.average()
+        assert got.neighbours(view) == ref.neighbours_internal(want)
+        bits, bw, bh = R.to_image_with_hole(want, w, True)
+        im = got.to_image(view)
+        assert (im.width, im.height) == (bw, bh) and bytes(im.pixels.astype(np.uint8)) == bytes(bits)
+        assert got.perimeter(view) == R.image_boundary_count(bits, bw, bh)
+    if w * h:
+        assert view.get_cluster_at(0) == ref.cluster_indices[0]
+        assert view.get_cluster_at_point(api.PointI32(w - 1, h - 1)) == ref.cluster_indices[-1]
+        assert view.get_pixel(0, 0).tuple() == tuple(int(v) for v in img[0, 0])
+        assert view.get_pixel(-1, 0) is None and view.get_pixel(w, 0) is None and view.get_pixel_at_index(w * h) is None
+        want_img = np.array(ref.to_color_image(), dtype=np.uint8).reshape(h, w, 4)
+        assert np.array_equal(view.to_color_image().array(), want_img)
+        canvas = api.ColorImage.new_w_h(w, h)
+        for u in reversed(list(view.clusters_output)):
+            view.get_cluster(int(u)).render_to_color_image(view, canvas)
+        assert np.array_equal(canvas.array(), want_img)            # container.rs:104-116 spelled out on the host
+    # Runner::run() gives the same object shape; take_image hands the pixels back
+    again = api.Runner(cfg, api.ColorImage.from_array(img), ctx=ctx).run()
+    assert [int(v) for v in again.view().cluster_indices] == ref.cluster_indices
+    assert np.array_equal(again.take_image().array(), img)
+
+
+def check_builder_contract(ctx):
+    import pytest
+
+    img = np.zeros((3, 3, 4), dtype=np.uint8)
+    b = api.Runner(api.RunnerConfig(), api.ColorImage.from_array(img), ctx=ctx).builder()
+    for name in ("same", "diff", "deepen", "hollow"):
+        with pytest.raises(api.ClosureNotOffloadable):
+            getattr(b, name)(lambda *a: True)
+    assert b.diagonal(False).hierarchical(0).batch_size(100).key(api.Color()).keying_action(api.KeyingAction.Keep).run().output_len() >= 1
+    with pytest.raises(AssertionError):                            # assert!(is_same_color_a < 8), runner.rs:78
+        api.Runner(api.RunnerConfig(is_same_color_a=8), api.ColorImage.from_array(img), ctx=ctx).run()
+
+
+def check_binary_api(ctx):
+    # the reference's unit tests (clusters.rs:355-418) through the API mirror
+    img = api.BinaryImage.from_string("*--\n-*-\n--*")
+    cl = img.to_clusters(False, ctx=ctx)
+    assert len(cl) == 3 and [(c.points[0].x, c.points[0].y) for c in cl] == [(0, 0), (1, 1), (2, 2)]
+    assert (cl.clusters[2].rect.left, cl.clusters[2].rect.top, cl.clusters[2].rect.right, cl.clusters[2].rect.bottom) == (2, 2, 3, 3)
+    assert cl.clusters[1].to_binary_image().get_pixel(0, 0)
+    cl = img.to_clusters(True, ctx=ctx)
+    assert len(cl) == 1 and [(p.x, p.y) for p in cl.clusters[0].points] == [(0, 0), (1, 1), (2, 2)]
+    img = api.BinaryImage.new_w_h(4, 4)
+    for y in (1, 2):
+        for x in (1, 2):
+            img.set_pixel(x, y, True)
+    assert img.get_pixel(1, 1) and not img.get_pixel_safe(-1, 0) and not img.get_pixel_safe(4, 4)
+    cl = img.to_clusters(False, ctx=ctx)
+    assert len(cl) == 1 and (cl.rect.left, cl.rect.top, cl.rect.right, cl.rect.bottom) == (1, 1, 3, 3)
+    assert api.BinaryImage.new_w_h(0, 0).to_clusters(False, ctx=ctx).clusters == []

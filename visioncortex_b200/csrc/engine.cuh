@@ -18,7 +18,8 @@ struct S2Set {
     bool ready = false;
     size_t cap_slots = 0, cap_adj = 0, cap_img = 0, cap_scan = 0;
     u32 *fw = nullptr, *mnext = nullptr, *mtail = nullptr, *mark = nullptr, *adj_off = nullptr, *cursor = nullptr, *adj = nullptr,
-        *tmin = nullptr, *bnd_off = nullptr, *bcur = nullptr, *bnd_px = nullptr, *live = nullptr, *chunksum = nullptr, *small = nullptr;
+        *tmin = nullptr, *bnd_off = nullptr, *bcur = nullptr, *live = nullptr, *col = nullptr, *chunksum = nullptr, *small = nullptr;
+    uint4 *bnd_nb = nullptr;
     u64 *over = nullptr, *keys = nullptr;
     S2ImgState *ist = nullptr;
     void *h_pinned = nullptr;
@@ -466,12 +467,12 @@ inline int ensure_s2_set(vcb_ctx *c, S2Set *s, const Dims &d, u32 total) {
     if (total > s->cap_slots) {
         const size_t cap = (size_t)total + 64;
         bool ok = grow(s->fw, cap) & grow(s->mnext, cap) & grow(s->mtail, cap) & grow(s->mark, cap) & grow(s->tmin, cap) & grow(s->bnd_off, cap + 1) &
-                  grow(s->bcur, cap) & grow(s->adj_off, cap + 1) & grow(s->cursor, cap) & grow(s->over, cap) & grow(s->live, cap) & grow(s->keys, cap);
+                  grow(s->bcur, cap) & grow(s->adj_off, cap + 1) & grow(s->cursor, cap) & grow(s->over, cap) & grow(s->live, cap) & grow(s->keys, cap) & grow(s->col, cap);
         if (!ok) { s->cap_slots = 0; return VCB_ERR_NOMEM; }
         s->cap_slots = total;
     }
     if ((size_t)d.N * 4 > s->cap_adj) {
-        if (!grow(s->adj, (size_t)d.N * 4 + 64) || !grow(s->bnd_px, (size_t)d.N + 64)) { s->cap_adj = 0; return VCB_ERR_NOMEM; }
+        if (!grow(s->adj, (size_t)d.N * 4 + 64) || !grow(s->bnd_nb, (size_t)d.N + 64)) { s->cap_adj = 0; return VCB_ERR_NOMEM; }
         s->cap_adj = (size_t)d.N * 4;
     }
     if (d.nimg > s->cap_img) {
@@ -496,7 +497,7 @@ inline int ensure_s2_set(vcb_ctx *c, S2Set *s, const Dims &d, u32 total) {
 inline void free_s2_set(S2Set *s) {
     if (!s) return;
     for (void *p : {(void *)s->fw, (void *)s->mnext, (void *)s->mtail, (void *)s->mark, (void *)s->adj_off, (void *)s->cursor, (void *)s->adj,
-                    (void *)s->tmin, (void *)s->bnd_off, (void *)s->bcur, (void *)s->bnd_px, (void *)s->live, (void *)s->chunksum,
+                    (void *)s->tmin, (void *)s->bnd_off, (void *)s->bcur, (void *)s->bnd_nb, (void *)s->live, (void *)s->col, (void *)s->chunksum,
                     (void *)s->small, (void *)s->over, (void *)s->keys, (void *)s->ist})
         rt::dev_free(p);
     rt::host_free(s->h_pinned);
@@ -544,7 +545,7 @@ inline int stage2_launch(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg
     a.l1 = res->labels1; a.rec = res->rec; a.slot_base = res->d_slot_base; a.slot_img = res->d_slot_img; a.total_slots = total;
     a.childoff = res->childoff; a.holeoff = res->holeoff;
     a.fw = set->fw; a.mpar = res->mpar; a.mnext = set->mnext; a.mtail = set->mtail; a.mark = set->mark; a.tmin = set->tmin; a.outpos = res->outpos;
-    a.bnd_off = set->bnd_off; a.bcur = set->bcur; a.bnd_px = set->bnd_px;
+    a.bnd_off = set->bnd_off; a.bcur = set->bcur; a.bnd_nb = set->bnd_nb; a.col = set->col;
     a.adj_off = set->adj_off; a.adj = set->adj; a.cursor = set->cursor; a.outputs = res->outputs; a.over = set->over;
     a.ist = set->ist; a.keys = legacy ? c->sk0 : set->keys; a.vals = c->sv0; a.live = set->live;
     u32 *d_count = set->small + 3 * (d.nimg + 2) + 3;

@@ -47,7 +47,9 @@ struct S2 {
     u32 *adj_off;                  // total_slots + 1
     u32 *adj;                      // adjacency entries (image-local slot ids)
     u32 *cursor;                   // total_slots (fill cursors / degree counts)
-    u32 *bnd_off, *bnd_px, *bcur;  // per stage-1 slot: its boundary pixels (a neighbour with another label, or the image edge)
+    u32 *bnd_off, *bcur;           // per stage-1 slot: its boundary pixels (a neighbour with another label, or the image edge) ...
+    uint4 *bnd_nb;                 // ... each stored as the stage-1 labels of its four neighbours (NONE = outside the image)
+    u32 *col;                      // average colour (ColorSum::average) of every live root, kept current by the merges
     u32 *outputs;                  // total_slots: clusters_output per image at slot_base[img]
     u64 *over;                     // total_slots: per-image overflow of the urgent list at slot_base[img]
     S2ImgState *ist;               // nimg
@@ -86,11 +88,12 @@ template <bool FILL> __global__ void __launch_bounds__(256) k_rag(S2 a) {
         const u32 img = g / d.n, p = g - img * d.n, x = p % d.w, y = p / d.w;
         const u32 base = a.slot_base[img];
         const u32 la = a.l1[g];
-        {   // boundary pixel of its stage-1 slot: only these can ever be on the perimeter of a merged cluster
-            const bool bnd = x == 0 || y == 0 || x + 1 == d.w || y + 1 == d.h || a.l1[g - 1] != la || a.l1[g + 1] != la ||
-                             a.l1[g - d.w] != la || a.l1[g + d.w] != la;
-            if (bnd) {
-                if (FILL) a.bnd_px[a.bnd_off[base + la] + atomicAdd(&a.bcur[base + la], 1u)] = p;
+        {   // boundary pixel of its stage-1 slot: only these can ever be on the perimeter of a merged cluster.  What the
+            // perimeter test needs of such a pixel is the labels of its four neighbours (outside the image: NONE)
+            const u32 nl = x > 0 ? a.l1[g - 1] : NONE, nr = x + 1 < d.w ? a.l1[g + 1] : NONE;
+            const u32 nu = y > 0 ? a.l1[g - d.w] : NONE, nd = y + 1 < d.h ? a.l1[g + d.w] : NONE;
+            if (nl != la || nr != la || nu != la || nd != la) {
+                if (FILL) a.bnd_nb[a.bnd_off[base + la] + atomicAdd(&a.bcur[base + la], 1u)] = make_uint4(nl, nr, nu, nd);
                 else atomicAdd(&a.bcur[base + la], 1u);
             }
         }
@@ -137,13 +140,27 @@ struct DegScan {
     }
 };
 
+__device__ static __forceinline__ u32 avg_color(const u32 *sum) {   // ColorSum::average (color.rs:295-302), `as u8`
+    const u32 c = sum[4];
+    return ((sum[0] / c) & 255u) | (((sum[1] / c) & 255u) << 8) | (((sum[2] / c) & 255u) << 16) | (((sum[3] / c) & 255u) << 24);
+}
+__device__ static __forceinline__ i32 color_diff(u32 a, u32 b) {     // runner.rs:110-114
+    i32 dsum = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const i32 x = (i32)((a >> (8 * c)) & 255u) - (i32)((b >> (8 * c)) & 255u);
+        dsum += x < 0 ? -x : x;
+    }
+    return dsum;
+}
+
 __global__ void __launch_bounds__(256) k_s2_init(S2 a) {
     const u32 stride = gridDim.x * 256;
     for (u32 s = blockIdx.x * 256 + threadIdx.x; s < a.total_slots; s += stride) {
         a.fw[s] = s - a.slot_base[a.slot_img[s]]; a.mpar[s] = NONE; a.mnext[s] = NONE; a.mtail[s] = s - a.slot_base[a.slot_img[s]];
         a.mark[s] = 0; a.tmin[s] = NONE; a.outpos[s] = NONE; a.cursor[s] = 0; a.bcur[s] = 0;
         const u32 area = a.rec[s].indices_len;
-        if (area) atomicMax(&a.ist[a.slot_img[s]].maxarea, area);
+        if (area) { atomicMax(&a.ist[a.slot_img[s]].maxarea, area); a.col[s] = avg_color(a.rec[s].sum); }
     }
 }
 __global__ void k_s2_init_img(S2 a) {
@@ -180,20 +197,6 @@ __global__ void __launch_bounds__(256) k_s2_collect(S2 a, int epoch) {
             if (take) { pos += __popc(m & ((1u << lane) - 1u)); a.keys[pos] = key; a.vals[pos] = idx; }
         }
     }
-}
-
-__device__ static __forceinline__ u32 avg_color(const u32 *sum) {   // ColorSum::average (color.rs:295-302), `as u8`
-    const u32 c = sum[4];
-    return ((sum[0] / c) & 255u) | (((sum[1] / c) & 255u) << 8) | (((sum[2] / c) & 255u) << 16) | (((sum[3] / c) & 255u) << 24);
-}
-__device__ static __forceinline__ i32 color_diff(u32 a, u32 b) {     // runner.rs:110-114
-    i32 dsum = 0;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const i32 x = (i32)((a >> (8 * c)) & 255u) - (i32)((b >> (8 * c)) & 255u);
-        dsum += x < 0 ? -x : x;
-    }
-    return dsum;
 }
 
 constexpr size_t S2_FUSED_SMEM_MAX = 200 * 1024;   // fused kernel: fixed part + key array must fit one SM's shared memory
@@ -243,11 +246,32 @@ __device__ static __forceinline__ unsigned long long warp_min64(unsigned long lo
     return v;
 }
 
+// Number of boundary records k0, k0 + stride, ... below `end` whose pixel has a 4-neighbour outside cluster c (or outside
+// the image).  Two records per step; their eight forwarding-word loads are independent and issued together.
+__device__ static __forceinline__ u32 s2_count_boundary(const S2 &a, u32 base, u32 c, u32 k0, u32 end, u32 stride) {
+    u32 cnt = 0;
+    for (u32 k = k0; k < end; k += 2 * stride) {
+        const bool two = k + stride < end;
+        const uint4 q0 = a.bnd_nb[k];
+        const uint4 q1 = two ? a.bnd_nb[k + stride] : q0;
+        const u32 nb[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        u32 f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = nb[j] == NONE ? NONE : ldcg(&a.fw[base + nb[j]]);
+        if (f[0] != c || f[1] != c || f[2] != c || f[3] != c) cnt++;
+        if (two && (f[4] != c || f[5] != c || f[6] != c || f[7] != c)) cnt++;
+    }
+    return cnt;
+}
+
 __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh, S2ImgState *ist, const S2Keys &keys, int epoch,
                                                       u32 img, u32 base, u64 *over) {
     const Dims d = a.d;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 W = (blockDim.x >> 5) < (u32)S2_NB ? (blockDim.x >> 5) : (u32)S2_NB;
+    const u32 nwarps = blockDim.x >> 5;
+    // a warp evaluates the candidates q = warp, warp + nwarps, ... one after the other: a round always takes up to S2_NB
+    // candidates, whatever the block size
+    const u32 W = (u32)S2_NB;
     const u64 idx_mask = (1ull << a.idx_bits) - 1ull;
     // ---- F: warp 0 takes the next entries of the sorted segment that precede every pending urgent key
     if (warp == 0) {
@@ -289,34 +313,42 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
     if (sh->mode == 2) return true;
     const u32 nb = sh->nb;
     // ---- P: one warp per candidate: neighbours, arg-min, deepen / hollow, new area
-    if (warp < nb) {
-        const u32 c = sh->bc[warp], area = sh->barea[warp], stamp = sh->bstamp[warp];
+    for (u32 q = warp; q < nb; q += nwarps) {
+        const u32 c = sh->bc[q], area = sh->barea[q];
         u32 flags = 0;
         if (area > a.cfg.hierarchical) flags = BF_OUTONLY;
         else if (c == 0) flags = BF_SLOW;                            // clusters[0]: its merge turns label-0 pixels into neighbours
         else {
             bool slow = false;
+            // member slots of c (most candidates never absorbed anything: one load)
             if (lane == 0) {
                 u32 n = 0, m = c;
-                while (m != NONE && n < (u32)S2_CAPM) { sh->bmem[warp][n++] = m; m = a.mnext[base + m]; }
-                sh->bnmem[warp] = n;
-                if (m != NONE) sh->bnmem[warp] = 0xffffffffu;
+                while (m != NONE && n < (u32)S2_CAPM) { sh->bmem[q][n++] = m; m = ldcg(&a.mnext[base + m]); }
+                sh->bnmem[q] = n;
+                if (m != NONE) sh->bnmem[q] = 0xffffffffu;
             }
             __syncwarp();
-            const u32 nm = sh->bnmem[warp];
+            const u32 nm = sh->bnmem[q];
             if (nm == 0xffffffffu) slow = true;
             else {
-                const u32 mycolor = avg_color(a.rec[base + c].sum);
+                const u32 mycolor = ldcg(&a.col[base + c]);
+                // adjacency ranges and boundary ranges of all members at once (lane i = member i): one round trip
+                u32 e0 = 0, e1 = 0, b0 = 0, b1 = 0;
+                if (lane < nm) {
+                    const u32 sl = sh->bmem[q][lane];
+                    e0 = a.adj_off[base + sl]; e1 = a.adj_off[base + sl + 1];
+                    if (ldcg(&a.fw[base + sl]) == c) { b0 = a.bnd_off[base + sl]; b1 = a.bnd_off[base + sl + 1]; }   // hole members: no pixels of c
+                }
                 // distinct neighbour roots are collected in the candidate's own list (the global mark[] stamps cannot be
-                // shared by candidates that are scanned concurrently)
+                // shared by candidates that are scanned concurrently); no load depends on another inside this loop nest
+                // except adjacency entry -> forwarding word
                 u32 n = 0;                                           // warp-uniform
                 for (u32 i = 0; i < nm; ++i) {
-                    const u32 sl = sh->bmem[warp][i];
-                    const u32 e0 = a.adj_off[base + sl], e1 = a.adj_off[base + sl + 1];
-                    for (u32 eb = e0; eb < e1; eb += 32) {
+                    const u32 me0 = __shfl_sync(0xffffffffu, e0, (int)i), me1 = __shfl_sync(0xffffffffu, e1, (int)i);
+                    for (u32 eb = me0; eb < me1; eb += 32) {
                         const u32 e = eb + lane;
                         u32 o = NONE;
-                        if (e < e1) {
+                        if (e < me1) {
                             u32 fl;
                             o = s2_find(a.fw, base, a.adj[e], &fl);
                             if (o == c || o == 0) o = NONE;
@@ -325,14 +357,9 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
                         while (pending) {
                             const int src = __ffs((int)pending) - 1;
                             const u32 v = __shfl_sync(0xffffffffu, o, src);
-                            const bool found = __any_sync(0xffffffffu, lane < n && lane < (u32)S2_CAPN && sh->bnbr[warp][lane] == v);
+                            const bool found = __any_sync(0xffffffffu, lane < n && lane < (u32)S2_CAPN && sh->bnbr[q][lane] == v);
                             if (!found) {
-                                if ((int)lane == src) {
-                                    if (n < (u32)S2_CAPN) sh->bnbr[warp][n] = v;
-                                    const i32 df = color_diff(mycolor, avg_color(a.rec[base + v].sum));
-                                    const unsigned long long k = ((unsigned long long)((u32)df * 65535u + v) << 32) | v;
-                                    if (k < sh->bbest[warp]) sh->bbest[warp] = k;
-                                }
+                                if ((int)lane == src && n < (u32)S2_CAPN) sh->bnbr[q][n] = v;
                                 ++n;
                                 __syncwarp();
                             }
@@ -340,41 +367,34 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
                         }
                     }
                 }
-                if (lane == 0) sh->bndist[warp] = n;
-                __syncwarp();
-                const u32 nd = sh->bndist[warp];
+                const u32 nd = n;
                 if (nd > (u32)S2_CAPN) slow = true;
                 else if (nd == 0) flags = BF_ISOLATED;
                 else {
-                    const unsigned long long best = sh->bbest[warp];
+                    // arg-min of diff * 65535 + index (builder.rs:452-454) over the distinct neighbours: lane i = neighbour i
+                    unsigned long long kbest = ~0ull;
+                    if (lane < nd) {
+                        const u32 v = sh->bnbr[q][lane];
+                        const i32 df = color_diff(mycolor, ldcg(&a.col[base + v]));
+                        kbest = ((unsigned long long)((u32)df * 65535u + v) << 32) | v;
+                    }
+                    const unsigned long long best = warp_min64(kbest);
                     const u32 tg = (u32)best;
                     const i32 md = (i32)(((u32)(best >> 32) - tg) / 65535u);
                     bool deepen = false;
                     if (a.cfg.hier_max && a.cfg.good_min < (u64)area && (u64)area < a.cfg.good_max && md > a.cfg.deepen_diff) {
                         if (a.cfg.good_min == 0) deepen = true;
                         else {
-                            // perimeter from the members' boundary-pixel lists (see s2_perimeter_bnd), by this warp
-                            const u32 *l1 = a.l1 + (size_t)img * d.n;
-                            u32 items = 0;
-                            for (u32 i = 0; i < nm; ++i) {
-                                const u32 m = sh->bmem[warp][i];
-                                if (ldcg(&a.fw[base + m]) == c) items += a.bnd_off[base + m + 1] - a.bnd_off[base + m];
-                            }
+                            // perimeter from the members' boundary-pixel records (see s2_perimeter_bnd), by this warp
+                            u32 items = b1 - b0;
+#pragma unroll
+                            for (int o2 = 16; o2 > 0; o2 >>= 1) items += __shfl_xor_sync(0xffffffffu, items, o2);
                             if ((u64)items > S2_PERIM_WARP_MAX) slow = true;
                             else {
                                 u32 cnt = 0;
                                 for (u32 i = 0; i < nm; ++i) {
-                                    const u32 m = sh->bmem[warp][i];
-                                    if (ldcg(&a.fw[base + m]) != c) continue;
-                                    const u32 b0 = a.bnd_off[base + m], b1 = a.bnd_off[base + m + 1];
-                                    for (u32 k = b0 + lane; k < b1; k += 32) {
-                                        const u32 p = a.bnd_px[k];
-                                        const u32 x = p % d.w, y = p / d.w;
-                                        bool edge = x == 0 || y == 0 || x + 1 == d.w || y + 1 == d.h;
-                                        if (!edge) edge = !s2_in_cluster(a, l1, base, p - 1, c) || !s2_in_cluster(a, l1, base, p + 1, c) ||
-                                                          !s2_in_cluster(a, l1, base, p - d.w, c) || !s2_in_cluster(a, l1, base, p + d.w, c);
-                                        if (edge) cnt++;
-                                    }
+                                    const u32 mb0 = __shfl_sync(0xffffffffu, b0, (int)i), mb1 = __shfl_sync(0xffffffffu, b1, (int)i);
+                                    cnt += s2_count_boundary(a, base, c, mb0 + lane, mb1, 32u);
                                 }
 #pragma unroll
                                 for (int o2 = 16; o2 > 0; o2 >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o2);
@@ -385,31 +405,32 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
                     if (!slow) {
                         flags = BF_MERGE | (deepen ? BF_DEEPEN : 0u) | (((u64)nd <= a.cfg.hollow_neighbours) ? BF_HOLLOW : 0u);
                         if (lane == 0) {
-                            sh->btarget[warp] = tg;
-                            sh->bnewarea[warp] = a.rec[base + tg].indices_len + area;
-                            atomicMin(&a.tmin[base + tg], warp);
-                            atomicMin(&a.tmin[base + c], warp);
+                            sh->bndist[q] = nd;
+                            sh->btarget[q] = tg;
+                            sh->bnewarea[q] = a.rec[base + tg].indices_len + area;
+                            atomicMin(&a.tmin[base + tg], q);
+                            atomicMin(&a.tmin[base + c], q);
                         }
                     }
                 }
             }
             if (slow) flags = BF_SLOW;
         }
-        if (lane == 0) sh->bflags[warp] = flags;
+        if (lane == 0) sh->bflags[q] = flags;
     }
     __threadfence_block();
     __syncthreads();
     // ---- C: conflicts with earlier candidates of the batch
-    if (warp < nb) {
-        const u32 c = sh->bc[warp];
-        u32 f = sh->bflags[warp];
+    for (u32 q = warp; q < nb; q += nwarps) {
+        const u32 c = sh->bc[q];
+        u32 f = sh->bflags[q];
         bool conf = (f & BF_SLOW) != 0;                              // a slow candidate is handled alone by the single-pop path
-        if (lane == 0 && ldcg(&a.tmin[base + c]) < warp) conf = true;
+        if (lane == 0 && ldcg(&a.tmin[base + c]) < q) conf = true;
         if (f & BF_MERGE) {
-            const u32 nd = sh->bndist[warp];
-            for (u32 i = lane; i < nd; i += 32) if (ldcg(&a.tmin[base + sh->bnbr[warp][i]]) < warp) conf = true;
+            const u32 nd = sh->bndist[q];
+            for (u32 i = lane; i < nd; i += 32) if (ldcg(&a.tmin[base + sh->bnbr[q][i]]) < q) conf = true;
         }
-        if (__any_sync(0xffffffffu, conf) && lane == 0) sh->bflags[warp] = f | BF_CONFLICT;
+        if (__any_sync(0xffffffffu, conf) && lane == 0) sh->bflags[q] = f | BF_CONFLICT;
     }
     __syncthreads();
     // ---- D: warp 0 decides the committed prefix, output positions and the running maximum area
@@ -461,15 +482,15 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
     __syncthreads();
     // ---- E: commit the prefix in parallel (independent by construction), then clear the tmin marks
     const u32 J = sh->ncommit;
-    if (warp < nb) {
-        const u32 c = sh->bc[warp], f = sh->bflags[warp], area = sh->barea[warp];
-        if (warp < J) {
+    for (u32 q = warp; q < nb; q += nwarps) {
+        const u32 c = sh->bc[q], f = sh->bflags[q], area = sh->barea[q];
+        if (q < J) {
             u32 newfw = 0;
             if (lane == 0) {
-                const u32 pos = sh->bpos[warp];
+                const u32 pos = sh->bpos[q];
                 if (pos != NONE) { a.outputs[base + pos] = c; if (a.outpos[base + c] == NONE) a.outpos[base + c] = pos; }
                 if (f & BF_MERGE) {
-                    const u32 target = sh->btarget[warp];
+                    const u32 target = sh->btarget[q];
                     const bool deepen = (f & BF_DEEPEN) != 0, hollow = (f & BF_HOLLOW) != 0;
                     vcb_cluster_rec *rf = a.rec + base + c, *rt_ = a.rec + base + target;
                     if (!deepen) for (int k2 = 0; k2 < 5; ++k2) rt_->residue_sum[k2] += rf->residue_sum[k2];
@@ -484,6 +505,7 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
                             rt_->rect[3] = rt_->rect[3] > rf->rect[3] ? rt_->rect[3] : rf->rect[3];
                         }
                     }
+                    a.col[base + target] = avg_color(rt_->sum);
                     a.childoff[base + c] = rt_->indices_len;
                     a.holeoff[base + c] = rt_->holes_len;
                     rt_->indices_len += area;
@@ -511,13 +533,13 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
             }
             newfw = __shfl_sync(0xffffffffu, newfw, 0);
             if (f & BF_MERGE) {
-                const u32 nm = sh->bnmem[warp];
-                for (u32 i = lane; i < nm; i += 32) stcg(&a.fw[base + sh->bmem[warp][i]], newfw);
+                const u32 nm = sh->bnmem[q];
+                for (u32 i = lane; i < nm; i += 32) stcg(&a.fw[base + sh->bmem[q][i]], newfw);
             }
         }
         if (lane == 0) {
             stcg(&a.tmin[base + c], NONE);
-            if (f & BF_MERGE) stcg(&a.tmin[base + sh->btarget[warp]], NONE);
+            if (f & BF_MERGE) stcg(&a.tmin[base + sh->btarget[q]], NONE);
         }
     }
     __threadfence_block();
@@ -553,15 +575,24 @@ __device__ static __forceinline__ void s2_perimeter_bnd(const S2 &a, S2Shared *s
         if (tid == 0) { const u32 nm0 = sh->nmem; u32 acc = 0; for (u32 i = 0; i < nm0; ++i) { const u32 dg = sh->deg[i]; sh->deg[i] = acc; acc += dg; } sh->deg[nm0] = acc; }
         __syncthreads();
         const u32 nm = sh->nmem, nitems = sh->deg[nm];
-        for (u32 it = tid; it < nitems; it += T) {
-            u32 lo = 0, hi = nm;
-            while (hi - lo > 1) { const u32 mid = (lo + hi) / 2; if (sh->deg[mid] <= it) lo = mid; else hi = mid; }
-            const u32 p = a.bnd_px[sh->eoff[lo] + (it - sh->deg[lo])];
-            const u32 x = p % d.w, y = p / d.w;
-            bool edge = x == 0 || y == 0 || x + 1 == d.w || y + 1 == d.h;
-            if (!edge) edge = !s2_in_cluster(a, l1, base, p - 1, c) || !s2_in_cluster(a, l1, base, p + 1, c) ||
-                              !s2_in_cluster(a, l1, base, p - d.w, c) || !s2_in_cluster(a, l1, base, p + d.w, c);
-            if (edge) cntp++;
+        for (u32 it = tid; it < nitems; it += 2 * T) {
+            u32 kk[2]; bool ok[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const u32 t2 = it + u * T;
+                ok[u] = t2 < nitems;
+                u32 lo = 0, hi = nm;
+                if (ok[u]) while (hi - lo > 1) { const u32 mid = (lo + hi) / 2; if (sh->deg[mid] <= t2) lo = mid; else hi = mid; }
+                kk[u] = ok[u] ? sh->eoff[lo] + (t2 - sh->deg[lo]) : 0u;
+            }
+            const uint4 q0 = ok[0] ? a.bnd_nb[kk[0]] : make_uint4(NONE, NONE, NONE, NONE);
+            const uint4 q1 = ok[1] ? a.bnd_nb[kk[1]] : q0;
+            const u32 nb[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            u32 f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = nb[j] == NONE ? NONE : ldcg(&a.fw[base + nb[j]]);
+            if (ok[0] && (f[0] != c || f[1] != c || f[2] != c || f[3] != c)) cntp++;
+            if (ok[1] && (f[4] != c || f[5] != c || f[6] != c || f[7] != c)) cntp++;
         }
         __syncthreads();
         const bool last = sh->more == NONE;
@@ -695,7 +726,7 @@ __device__ static __forceinline__ void s2_epoch_leader(const S2 &a, S2Shared *sh
                 ist->st_singles += 1;
                 sh->best = ~0ull; sh->ndist = 0; sh->perim = 0;
                 sh->stamp = ++ist->stamp;
-                sh->mycolor = avg_color(a.rec[base + c].sum);
+                sh->mycolor = a.col[base + c];
                 sh->more = c; sh->nchunks = 0;
                 // fast path for a cluster that never absorbed anything (most pops): its member list is itself, so the
                 // adjacency range is loaded here and the gather / degree-prefix rounds are skipped
@@ -751,7 +782,7 @@ __device__ static __forceinline__ void s2_epoch_leader(const S2 &a, S2Shared *sh
                 const u32 o = s2_find(a.fw, base, a.adj[e], &fl);
                 if (o == c || o == 0) continue;                     // label 0 and self are not neighbours (cluster.rs:150)
                 if (atomicExch(&a.mark[base + o], stamp) != stamp) atomicAdd(&sh->ndist, 1u);
-                const i32 df = color_diff(mycolor, avg_color(a.rec[base + o].sum));
+                const i32 df = color_diff(mycolor, ldcg(&a.col[base + o]));
                 const unsigned long long k = ((unsigned long long)((u32)df * 65535u + o) << 32) | o;
                 atomicMin(&sh->best, k);
             }
@@ -831,6 +862,7 @@ __device__ static __forceinline__ void s2_epoch_leader(const S2 &a, S2Shared *sh
                     rt_->rect[3] = rt_->rect[3] > rf->rect[3] ? rt_->rect[3] : rf->rect[3];
                 }
             }
+            a.col[base + target] = avg_color(rt_->sum);
             a.childoff[base + c] = rt_->indices_len;                 // builder.rs:529: to.indices.append(from.indices)
             a.holeoff[base + c] = rt_->holes_len;
             rt_->indices_len += area;

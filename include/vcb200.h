@@ -186,7 +186,8 @@ uint64_t vcb_ctx_kernel_launches(const vcb_ctx *ctx);            /* kernels laun
 int  vcb_ctx_profile_reset(vcb_ctx *ctx, int enable);
 int  vcb_ctx_profile_read(vcb_ctx *ctx, const char *kernel_name, double *total_ms, uint64_t *launches);
 /* counters of the last stage-1 run on this context: out[0] = candidate events, out[1] = NEW events, out[2] = leaves after
- * the trivial-leaf contraction, out[3] = spanning-forest rounds, out[4] = error bits */
+ * the trivial-leaf contraction, out[3] = spanning-forest rounds, out[4] = error bits, out[5] = leaves resurrected through the
+ * stale cluster_upleft label (diagonal = true, builder.rs:301-305), out[6] = passes of the stage-1 pipeline (1 unless out[5] > 0) */
 int  vcb_ctx_last_counters(const vcb_ctx *ctx, uint32_t out[8]);
 /* CUDA events on the context's stream: record into slot 0..15, elapsed milliseconds between two recorded slots */
 int  vcb_ctx_event_record(vcb_ctx *ctx, int slot);

@@ -172,6 +172,7 @@ static inline unsigned __vsubus4(unsigned a, unsigned b) {
     for (int k = 0; k < 4; ++k) { int x = (a >> (8 * k)) & 255, y = (b >> (8 * k)) & 255; r |= (unsigned)(x > y ? x - y : 0) << (8 * k); }
     return r;
 }
+static inline long long clock64() { return 0; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }

@@ -73,19 +73,27 @@ def static_edges_binary(mask, diagonal):
     return J, M
 
 
-def run_model(J, M, w, h, base, check_stale_upleft):
-    """steps 2-9.  Returns dict(labels, num_slots, listing per slot, areas per slot)."""
+def run_model(J, M, w, h, base, check_stale_upleft, res=frozenset()):
+    """steps 2-9.  Returns dict(labels, num_slots, listing per slot, areas per slot).
+
+    `res` = pixels at which the reference's stale `cluster_upleft` read (builder.rs:301-305 vs :341-343) resurrects the
+    slot that has just lost the merge at the same pixel: such a pixel starts a provisional cluster of its own (like a NEW
+    pixel) that carries the dead label instead of a fresh one.  Whether a pixel is in that set depends on merge outcomes
+    before it, so the set is the fixpoint of `stale -> res` (run_model_fixpoint); the model reports the set it observes in
+    `stale_set`.  With check_stale_upleft and an inconsistent `res` the result is only meaningful as the next iterate."""
     n = w * h
     off = {UP: -w, LEFT: -1, UPLEFT: -w - 1}
+    res = frozenset(int(p) for p in res if J[int(p)] == UPLEFT)
     # step 2: provisional clusters = trees of the J forest (parent index < own index -> one forward pass == pointer jumping)
     pc = np.full(n, -1, dtype=np.int64)
     for i in range(n):
-        if J[i] == NEW:
+        if J[i] == NEW or i in res:
             pc[i] = i
         elif J[i] != NONE:
             pc[i] = pc[i + off[int(J[i])]]
-    new_pix = [i for i in range(n) if J[i] == NEW]
+    new_pix = [i for i in range(n) if J[i] == NEW or i in res]   # all leaves, ascending; resurrections are not NEW events
     K = len(new_pix)
+    is_new = [J[p] == NEW for p in new_pix]
     leaf_of = {p: k for k, p in enumerate(new_pix)}           # compaction of NEW flags (prefix scan)
     # step 4: candidate events, time-sorted by construction
     events = [(i, leaf_of[pc[i - 1]], leaf_of[pc[i - w]]) for i in range(n)
@@ -101,21 +109,23 @@ def run_model(J, M, w, h, base, check_stale_upleft):
 
     cur = list(range(K))                 # current tree node of each set (indexed by uf root)
     parent, birth, child_l, child_u = [-1] * K, [-1] * K, [-1] * K, [-1] * K
-    stale = []                           # (node, side) candidates for the stale-upleft quirk
+    stale = []                           # (node, side, pixel) candidates for the stale-upleft quirk
+    node_at = {}                         # event pixel -> tree node
     for (i, a, b) in events:
         ra, rb = find(a), find(b)
         if ra == rb:
             continue
         v = len(parent)
+        node_at[i] = v
         parent.append(-1); birth.append(i); child_l.append(cur[ra]); child_u.append(cur[rb])
         parent[cur[ra]] = v
         parent[cur[rb]] = v
         if check_stale_upleft and J[i] == UPLEFT:
             ru = find(leaf_of[pc[i - w - 1]])
             if ru == ra:
-                stale.append((v, 0))
+                stale.append((v, 0, i))
             elif ru == rb:
-                stale.append((v, 1))
+                stale.append((v, 1, i))
         uf[ra] = rb
         cur[rb] = v
     nn = len(parent)
@@ -139,32 +149,59 @@ def run_model(J, M, w, h, base, check_stale_upleft):
     left_wins = [False] * nn
     death_time = [None] * K
     death_left = [False] * K
+    loser_car = [-1] * nn
     for v in range(K, nn):
         l, u = child_l[v], child_u[v]
         if W[l] <= W[u]:                       # left loses, up's label survives
             carrier[v] = carrier[u]
+            loser_car[v] = carrier[l]
             death_time[carrier[l]] = birth[v]; death_left[carrier[l]] = True
         else:
             left_wins[v] = True
             carrier[v] = carrier[l]
+            loser_car[v] = carrier[u]
             death_time[carrier[u]] = birth[v]; death_left[carrier[u]] = False
-    for (v, side) in stale:
+    stale_set = set()
+    for (v, side, i) in stale:
         loser_side = 1 if left_wins[v] else 0
         if side == loser_side:
-            raise Unsupported("stale upleft label resurrects a dead slot")
-    # step 8: D flags and prefix-scan numbering
-    D = [False] * K
+            stale_set.add(i)
+    # a resurrected leaf carries the label of the leaf that lost at its own pixel; chains resolve to a NEW leaf (origin)
+    src = [-1] * K
     for k in range(K):
-        nxt = new_pix[k + 1] if k + 1 < K else None
-        if death_time[k] is not None and death_left[k] and (nxt is None or death_time[k] <= nxt):
-            D[k] = True
+        if not is_new[k]:
+            v = node_at.get(new_pix[k])
+            src[k] = loser_car[v] if v is not None else -1
+    origin = list(range(K))
+    for k in range(K):                         # sources are earlier leaves: one forward pass
+        if not is_new[k]:
+            origin[k] = origin[src[k]] if src[k] >= 0 else -1
+    # step 8: D flags and prefix-scan numbering (NEW events only)
+    news = [k for k in range(K) if is_new[k]]
+    nxt_new = {}
+    for j, k in enumerate(news):
+        nxt_new[k] = new_pix[news[j + 1]] if j + 1 < len(news) else None
+    D = [False] * K
+    fence = False
+    for k in range(K):
+        o = origin[k]
+        if o < 0 or death_time[k] is None or not death_left[k]:
+            continue
+        nx = nxt_new[o]
+        if nx is None or death_time[k] <= nx:
+            D[o] = True                            # builder.rs:315-317: the slot is handed to the next new cluster
+            if death_time[k] in stale_set:
+                fence = True                       # ... and resurrected at the same pixel: the next NEW overwrites it
     label = [0] * K
     run = base
-    for k in range(K):
+    for k in news:
         label[k] = run
         if not D[k]:
             run += 1
-    num_slots = run + (1 if (K > 0 and D[K - 1]) else 0)
+    for k in range(K):
+        if not is_new[k]:
+            label[k] = label[origin[k]] if origin[k] >= 0 else 0
+    num_slots = run + (1 if (news and D[news[-1]]) else 0)
     # root / final labels
     root = list(range(nn))
     for v in range(nn - 1, -1, -1):
@@ -191,4 +228,18 @@ def run_model(J, M, w, h, base, check_stale_upleft):
     order = sorted((p for p in range(n) if J[p] != NONE), key=lambda p: (labels[p], own_start[attr[p]], p))
     for p in order:
         listing.setdefault(int(labels[p]), []).append(p)
-    return dict(labels=labels, num_slots=max(num_slots, base), listing=listing, K=K)
+    return dict(labels=labels, num_slots=max(num_slots, base), listing=listing, K=K, stale_set=frozenset(stale_set), fence=fence)
+
+
+def run_model_fixpoint(J, M, w, h, base, max_iter=64):
+    """diagonal=true colour path: iterate `res <- stale_set(res)` to the (unique, by causality in time) fixpoint."""
+    res = frozenset()
+    for it in range(max_iter):
+        out = run_model(J, M, w, h, base, True, res)
+        if out["stale_set"] == res:
+            if out["fence"]:
+                raise Unsupported("a slot freed by builder.rs:315-317 is resurrected at the same pixel")
+            out["iterations"] = it + 1
+            return out
+        res = out["stale_set"]
+    raise Unsupported("no fixpoint")

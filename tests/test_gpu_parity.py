@@ -16,14 +16,25 @@ class Fenced(Exception):
 
 
 def run_gpu(gpu, img, cfg, **kw):
-    """Inputs whose result is order-dependent in the reference (unclean key colour) are
-    rejected with VCB_ERR_UNSUPPORTED instead of silently diverging; random tests skip them."""
+    """Two kinds of input are rejected with VCB_ERR_UNSUPPORTED instead of silently diverging, and random tests skip them:
+    an unclean key colour and, with diagonal = true, a slot that is freed and resurrected at the
+    same pixel (the reference then overwrites a live slot, builder.rs:347-348, and its labels disagree with its lists)."""
     try:
         return gpu.runner_run(img, cfg, **kw)
     except VcbError as e:
-        if e.status == 3 and ("not clean" in str(e) or "stale cluster_upleft" in str(e)):
-            raise Fenced()
+        if e.status == 3 and ("not clean" in str(e) or "resurrected at the same pixel" in str(e)):
+            raise Fenced(str(e))
         raise
+
+
+def near_threshold_noise(rng, w, h):
+    """colours scattered around one value by about the color_same threshold: the input family on which diagonal = true hits
+    the stale cluster_upleft read (builder.rs:301-305 vs :341-343) most often"""
+    amp = int(rng.integers(3, 14))
+    img = np.empty((h, w, 4), np.uint8)
+    img[..., :3] = np.clip(rng.integers(40, 200, size=3) + rng.integers(-amp, amp + 1, size=(h, w, 3)), 0, 255)
+    img[..., 3] = 255
+    return img
 
 
 def c2_config(w, h, **kw):
@@ -253,29 +264,62 @@ def test_c4_default_with_pools(gpu, oracle):
 
 
 def test_diagonal_colour(gpu, oracle):
-    """diagonal = true (BuilderConfig default, builder.rs:22-32).  Inputs on which the reference resurrects a dead slot through
-    the stale cluster_upleft read are detected on the device and fenced, never silently different."""
+    """diagonal = true (BuilderConfig default, builder.rs:22-32), including the inputs on which the reference resurrects a dead
+    slot through the stale cluster_upleft read: exact, not fenced."""
     rng = np.random.default_rng(71)
-    ok = fenced = 0
+    ok = 0
     for k in range(150):
         img, cfg = random_case(rng, max_side=40, keyed=(k % 4 == 3), hierarchical=[0, HM, 0][k % 3], diagonal=True)
         ref = oracle.runner_run(img, cfg, pools=True, color_image=True)
         try:
             got = run_gpu(gpu, img, cfg, pools=True, color_image=True)
-        except Fenced:
-            fenced += 1
+        except Fenced as e:
+            assert "not clean" in str(e) or k % 4 != 3, str(e)
             continue
         assert_same_clusters(got, ref, pools=True, ctx=f"diag case {k} {img.shape}")
         ok += 1
-    assert ok > 100, (ok, fenced)
+    assert ok >= 140, ok
     img = synth.g2_scene(1280, 720, seed=9)
     cfg = c2_config(1280, 720, diagonal=1)
     ref = oracle.runner_run(img, cfg, pools=False)
+    got = gpu.runner_run(img, cfg, pools=False)             # must not be fenced
+    assert_same_clusters(got, ref, pools=False, ctx="diag 720p")
+
+
+def test_diagonal_stale_upleft_resurrection(gpu, oracle):
+    """Inputs that do hit the stale cluster_upleft read: the pixel starts a provisional cluster that carries the dead label
+    (J_RES, ids.cuh), found as a fixpoint over whole-pipeline passes.  Checked: labels, every record, clusters_output, the
+    exact indices order, stage 2 on top and to_color_image; and that the path was really taken."""
+    rng = np.random.default_rng(72)
+    with_res = multi_pass = fenced = 0
+    for k in range(120):
+        side = [40, 100, 250][k % 3]
+        w, h = int(rng.integers(2, side + 1)), int(rng.integers(2, side + 1))
+        img = near_threshold_noise(rng, w, h)
+        cfg = make_config(hierarchical=[0, HM, 64][k % 3], diagonal=1, is_same_color_a=int(rng.choice([0, 1, 2, 3])),
+                          is_same_color_b=int(rng.choice([1, 2, 3, 6])), good_min_area=2, deepen_diff=8)
+        ref = oracle.runner_run(img, cfg, pools=True, color_image=True)
+        try:
+            got = run_gpu(gpu, img, cfg, pools=True, color_image=True)
+        except Fenced as e:
+            assert "resurrected at the same pixel" in str(e)
+            fenced += 1
+            continue
+        lc = gpu.last_counters()
+        with_res += lc["resurrected_leaves"] > 0
+        multi_pass += lc["stage1_passes"] > 2
+        assert_same_clusters(got, ref, pools=True, ctx=f"stale case {k} {img.shape}")
+    assert with_res >= 15 and fenced <= 12, (with_res, multi_pass, fenced)
+    # 720p of the same family: hundreds of resurrections, dependent ones included
+    img = near_threshold_noise(np.random.default_rng(73), 1280, 720)
+    cfg = make_config(hierarchical=0, diagonal=1, is_same_color_a=2, is_same_color_b=2)
+    ref = oracle.runner_run(img, cfg, pools=False)
     try:
         got = run_gpu(gpu, img, cfg, pools=False)
-        assert_same_clusters(got, ref, pools=False, ctx="diag 720p")
     except Fenced:
-        pass
+        pytest.skip("720p stale-upleft case hits the freed-slot overwrite")
+    assert gpu.last_counters()["resurrected_leaves"] > 0
+    assert_same_clusters(got, ref, pools=False, ctx="stale 720p")
 
 
 def test_c5_giant_image_single_gpu(gpu, oracle):

@@ -5,7 +5,7 @@ import sys
 
 import numpy as np
 
-from model_stage1 import Unsupported, run_model, static_edges_binary, static_edges_colour
+from model_stage1 import Unsupported, run_model, run_model_fixpoint, static_edges_binary, static_edges_colour
 from test_oracle_kat import _cfg
 
 
@@ -46,7 +46,7 @@ def check_colour_case(oracle, rng, diagonal=False, keyed=False):
                key_color=key, keying_action=action)
     try:
         J, M, kmask = static_edges_colour(img, diagonal, shift, thres, key, keyed)
-        mod = run_model(J, M, w, h, base=1, check_stale_upleft=diagonal)
+        mod = run_model_fixpoint(J, M, w, h, base=1) if diagonal else run_model(J, M, w, h, base=1, check_stale_upleft=False)
     except Unsupported:
         return False
     ref = oracle.runner_run(img, cfg)

@@ -59,6 +59,42 @@ def test_sim_empty_and_full(sim, oracle):
             assert_same_bin_clusters(sim.to_clusters(mask, diag), oracle.to_clusters(mask, diag))
 
 
+def test_sim_diagonal_stale_upleft(sim, oracle):
+    """diagonal = true inputs on which the reference's stale cluster_upleft read resurrects a dead slot (builder.rs:301-305 vs
+    :341-343): the executable id model (model_stage1.run_model_fixpoint) picks images that do hit it, the kernels must agree
+    with the oracle on them and must have taken the J_RES path."""
+    from model_stage1 import Unsupported, run_model_fixpoint, static_edges_colour
+    from visioncortex_b200.runtime import make_config
+
+    rng = np.random.default_rng(91)
+    done = 0
+    for k in range(2000):
+        w, h = int(rng.integers(6, 18)), int(rng.integers(6, 18))
+        amp = int(rng.integers(3, 14))
+        img = np.empty((h, w, 4), np.uint8)
+        img[..., :3] = np.clip(rng.integers(40, 200, size=3) + rng.integers(-amp, amp + 1, size=(h, w, 3)), 0, 255)
+        img[..., 3] = 255
+        shift, thres = int(rng.choice([0, 1, 2, 3])), int(rng.choice([1, 2, 3, 6]))
+        J, M, _ = static_edges_colour(img, True, shift, thres, (0, 0, 0, 0), False)
+        try:
+            mod = run_model_fixpoint(J, M, w, h, 1)
+        except Unsupported:
+            continue
+        if not mod["stale_set"]:
+            continue
+        cfg = make_config(hierarchical=[0, 0xFFFFFFFF][done % 2], diagonal=1, is_same_color_a=shift, is_same_color_b=thres,
+                          good_min_area=2, deepen_diff=8)
+        ref = oracle.runner_run(img, cfg, pools=True, color_image=True)
+        got = sim.runner_run(img, cfg, pools=True, color_image=True)
+        lc = sim.last_counters()
+        assert lc["resurrected_leaves"] == len(mod["stale_set"]) and lc["stage1_passes"] == mod["iterations"]
+        assert_same_clusters(got, ref, pools=True, ctx=f"stale case {k}")
+        done += 1
+        if done == 4:
+            break
+    assert done == 4
+
+
 def test_sim_unclean_key_is_fenced(sim):
     from visioncortex_b200.runtime import make_config
 

@@ -250,124 +250,139 @@ template <> inline bool launch_edges_tma<ColorPolicy>(vcb_ctx *c, const Dims &d,
 // Runs K1..K8 for `nimg` equally sized images resident on the device and builds the per-slot records.
 // base = 1 for the colour path (slot 0 = ZERO, builder.rs:44-45,189), 0 for the binary path.
 template <class P>
-inline int run_stage1(vcb_ctx *c, const Dims &d, const P &pol, u32 base, bool want_attr, int keep_key, BatchResult *res,
+inline int run_stage1(vcb_ctx *c, const Dims &d, const P &pol_in, u32 base, bool want_attr, int keep_key, BatchResult *res,
                       std::vector<ImgMeta> &meta_out, Counters &ctr_out, const DevSet *dsp = nullptr) {
     rt::Stream &st = c->st;
     Bufs b = c->b;
     DevSet one; one.n = 1; one.ctx[0] = c;
     const DevSet &ds = dsp ? *dsp : one;
     const bool multi = ds.n > 1;
-    const int g_img = (int)((d.nimg + 127) / 128);
-    rt::launch(st, "k_meta_init", rt::SEQ, k_meta_init, dim3(g_img), dim3(128), 0, d, b);
+    // colour path with diagonal = true: the pipeline is repeated until the set of resurrected pixels (J_RES, ids.cuh) is the
+    // one the pass itself observes.  Inputs without such pixels (every BASELINE configuration) take exactly one pass.
+    const bool res_mode = pol_in.fixpoint();
+    P pol = pol_in;
+    ImgMeta *hm = nullptr;
+    Counters *hc = nullptr;
+    int npass = 0;
+    for (int pass = 0;; ++pass) {
+        npass = pass + 1;
+        const int g_img = (int)((d.nimg + 127) / 128);
+        rt::launch(st, "k_meta_init", rt::SEQ, k_meta_init, dim3(g_img), dim3(128), 0, d, b);
 
-    const u32 tiles_x = (d.w + TW - 1) / TW, tiles_y = (d.h + TH - 1) / TH;
-    if (multi) { const int e = sync_devices(ds); if (e) return e; }
-    for (int k = 0; k < ds.n; ++k) {                      // K1: device k takes the tile rows that start in its band
-        vcb_ctx *ck = ds.ctx[k];
-        u32 t0 = multi ? (ds.row_begin(k, d) + TH - 1) / TH : 0, t1 = multi ? (ds.row_begin(k + 1, d) + TH - 1) / TH : tiles_y * d.nimg;
-        if (multi && t1 > tiles_y) t1 = tiles_y;
-        if (t1 <= t0) continue;
-        rt::set_device(ck->device);
-        const u32 tile0 = t0 * tiles_x, tiles = (t1 - t0) * tiles_x;
-        if (!launch_edges_tma(ck, d, pol, b, tile0, tiles))
-            rt::launch(ck->st, "k_edges_tile", rt::THR, k_edges_tile<P>, dim3(tiles), dim3(K1_THREADS), K1_SMEM, d, pol, b, tile0);
-    }
-    if (multi) { const int e = sync_devices(ds); if (e) return e; }
-    for (int k = 0; k < ds.n; ++k) {                      // K2
-        vcb_ctx *ck = ds.ctx[k];
-        const u32 p0 = multi ? ds.row_begin(k, d) * d.w : 0, p1 = multi ? ds.row_begin(k + 1, d) * d.w : d.N;
-        if (p1 <= p0) continue;
-        rt::set_device(ck->device);
-        if (d.w % 4 == 0)
-            rt::launch(ck->st, "k_flatten_events", rt::THR, k_flatten_events4, dim3(grid_for(ck, (p1 - p0) / 4, K2_THREADS, 16)), dim3(K2_THREADS), 0, d, b, p0 / 4, p1 / 4);
-        else
-            rt::launch(ck->st, "k_flatten_events", rt::THR, k_flatten_events, dim3(grid_for(ck, p1 - p0, K2_THREADS, 16)), dim3(K2_THREADS), 0, d, b, p0, p1);
-    }
-    if (multi) { const int e = sync_devices(ds); if (e) return e; }
-    {
-        static const bool plain = getenv("VCB_NO_FUSED_SCAN") != nullptr;
-        if (plain) {
-            prims::scan(st, "scan_new", NewScan{d, b}, c->chunksum, d.N, c->sms * 8);
-            prims::scan(st, "scan_new", LeafScan{d, b}, c->chunksum, d.N, c->sms * 8);
-        } else {
-            u64 *cs = reinterpret_cast<u64 *>(c->rs_table);           // free until the first sort
-            const u32 nchunks = (d.N + NL_CHUNK - 1) / NL_CHUNK;
-            const u32 grid = std::min<u32>(nchunks, (u32)c->sms * 8);
-            rt::launch(st, "scan_new", rt::THR, k_newleaf_sums, dim3(grid), dim3(NL_THREADS), 128, d, b, cs);
-            rt::launch(st, "scan_new", rt::THR, k_newleaf_chunks, dim3(1), dim3(NL_THREADS), 128, d, cs);
-            rt::launch(st, "scan_new", rt::THR, k_newleaf_apply, dim3(grid), dim3(NL_THREADS), 128, d, b, cs);
-        }
-    }
-    {
-        if (!c->coop_blocks) c->coop_blocks = rt::max_coop_blocks((const void *)k_boruvka, K3_THREADS, 0, c->device);
-        int g = c->coop_blocks;
-        // a cooperative grid must be resident as a whole: while the hierarchical stage of earlier device batches occupies part of
-        // every SM (S2Set), a full-occupancy grid would wait for those kernels to drain, so it is sized to fit beside them
-        if (c->s2_overlap && g > c->sms * 2) g = c->sms * 2;
-        const int want = (int)((d.N / 4 + K3_THREADS - 1) / K3_THREADS);
-        if (g > want) g = want < 1 ? 1 : want;
-        rt::launch(st, "k_boruvka", rt::COOP, k_boruvka, dim3(g), dim3(K3_THREADS), 0, b);
-    }
-    rt::launch(st, "k_chain_insert", rt::THR, k_chain_insert, dim3(grid_for(c, d.N / 2, K4_THREADS, 16)), dim3(K4_THREADS), 0, d, b);
-    {
-        // rows per segment: enough threads to fill the machine, as few restarts as possible
-        const u64 wpad = (d.w + 31) & ~31u;
-        const u64 target = (u64)c->sms * 2048 * (u64)ds.n;   // enough column walkers to fill every device
-        u32 nseg = (u32)((target + wpad * d.nimg - 1) / (wpad * d.nimg));
-        if (nseg < 1) nseg = 1;
-        if (nseg > d.h) nseg = d.h;
-        u32 rows = (d.h + nseg - 1) / nseg;
-        static const int env_rows = getenv("VCB_ATTR_ROWS") ? atoi(getenv("VCB_ATTR_ROWS")) : 0;
-        static const int env_per_sm = getenv("VCB_ATTR_PER_SM") ? atoi(getenv("VCB_ATTR_PER_SM")) : 16;
-        if (env_rows > 0 && (u32)env_rows < rows) rows = (u32)env_rows;
-        if (rows < 8 && d.h >= 8) rows = 8;
-        const u32 nseg_t = (d.h + rows - 1) / rows;
+        const u32 tiles_x = (d.w + TW - 1) / TW, tiles_y = (d.h + TH - 1) / TH;
         if (multi) { const int e = sync_devices(ds); if (e) return e; }
-        for (int k = 0; k < ds.n; ++k) {                  // K5: device k takes the row segments that start in its band
+        for (int k = 0; k < ds.n; ++k) {                      // K1: device k takes the tile rows that start in its band
             vcb_ctx *ck = ds.ctx[k];
-            u32 s0 = multi ? (ds.row_begin(k, d) + rows - 1) / rows : 0, s1 = multi ? (ds.row_begin(k + 1, d) + rows - 1) / rows : nseg_t * d.nimg;
-            if (multi && s1 > nseg_t) s1 = nseg_t;
-            if (s1 <= s0) continue;
+            u32 t0 = multi ? (ds.row_begin(k, d) + TH - 1) / TH : 0, t1 = multi ? (ds.row_begin(k + 1, d) + TH - 1) / TH : tiles_y * d.nimg;
+            if (multi && t1 > tiles_y) t1 = tiles_y;
+            if (t1 <= t0) continue;
             rt::set_device(ck->device);
-            const u64 t_lo = (u64)s0 * wpad, t_hi = (u64)s1 * wpad;
-            const int g = grid_for(ck, t_hi - t_lo, K5_THREADS, env_per_sm);
-            if (want_attr)
-                rt::launch(ck->st, "k_attribute", rt::THR, k_attribute<P, true>, dim3(g), dim3(K5_THREADS), 0, d, pol, b, rows, keep_key, t_lo, t_hi);
-            else
-                rt::launch(ck->st, "k_attribute", rt::THR, k_attribute<P, false>, dim3(g), dim3(K5_THREADS), 0, d, pol, b, rows, keep_key, t_lo, t_hi);
+            const u32 tile0 = t0 * tiles_x, tiles = (t1 - t0) * tiles_x;
+            if (!launch_edges_tma(ck, d, pol, b, tile0, tiles))
+                rt::launch(ck->st, "k_edges_tile", rt::THR, k_edges_tile<P>, dim3(tiles), dim3(K1_THREADS), K1_SMEM, d, pol, b, tile0);
         }
         if (multi) { const int e = sync_devices(ds); if (e) return e; }
-    }
-    rt::launch(st, "k_tournament", rt::THR, k_tournament, dim3(grid_for(c, d.N / 4, K6_THREADS, 16)), dim3(K6_THREADS), 0, d, b);
-    prims::scan(st, "scan_label", LabelScan{d, b}, c->chunksum, d.N, c->sms * 8);
-    rt::launch(st, "k_image_meta", rt::SEQ, k_image_meta, dim3(g_img), dim3(128), 0, d, b, base);
-    rt::launch(st, "k_leaf_final", rt::SEQ, k_leaf_final, dim3(grid_for(c, d.N / 4, K8_THREADS, 16)), dim3(K8_THREADS), 0, d, b, base);
-    if (res->labels) {
-        if (multi) { const int e = sync_devices(ds); if (e) return e; }
-        for (int k = 0; k < ds.n; ++k) {
+        for (int k = 0; k < ds.n; ++k) {                      // K2
             vcb_ctx *ck = ds.ctx[k];
             const u32 p0 = multi ? ds.row_begin(k, d) * d.w : 0, p1 = multi ? ds.row_begin(k + 1, d) * d.w : d.N;
             if (p1 <= p0) continue;
             rt::set_device(ck->device);
-            rt::launch(ck->st, "k_labels", rt::SEQ, k_labels, dim3(grid_for(ck, p1 - p0, K8_THREADS, 16)), dim3(K8_THREADS), 0, d, b, res->labels, p0, p1);
+            if (d.w % 4 == 0)
+                rt::launch(ck->st, "k_flatten_events", rt::THR, k_flatten_events4, dim3(grid_for(ck, (p1 - p0) / 4, K2_THREADS, 16)), dim3(K2_THREADS), 0, d, b, p0 / 4, p1 / 4);
+            else
+                rt::launch(ck->st, "k_flatten_events", rt::THR, k_flatten_events, dim3(grid_for(ck, p1 - p0, K2_THREADS, 16)), dim3(K2_THREADS), 0, d, b, p0, p1);
         }
         if (multi) { const int e = sync_devices(ds); if (e) return e; }
-    }
+        {
+            static const bool plain = getenv("VCB_NO_FUSED_SCAN") != nullptr;
+            if (plain) {
+                prims::scan(st, "scan_new", NewScan{d, b}, c->chunksum, d.N, c->sms * 8);
+                prims::scan(st, "scan_new", LeafScan{d, b}, c->chunksum, d.N, c->sms * 8);
+            } else {
+                u64 *cs = reinterpret_cast<u64 *>(c->rs_table);           // free until the first sort
+                const u32 nchunks = (d.N + NL_CHUNK - 1) / NL_CHUNK;
+                const u32 grid = std::min<u32>(nchunks, (u32)c->sms * 8);
+                rt::launch(st, "scan_new", rt::THR, k_newleaf_sums, dim3(grid), dim3(NL_THREADS), 128, d, b, cs);
+                rt::launch(st, "scan_new", rt::THR, k_newleaf_chunks, dim3(1), dim3(NL_THREADS), 128, d, cs);
+                rt::launch(st, "scan_new", rt::THR, k_newleaf_apply, dim3(grid), dim3(NL_THREADS), 128, d, b, cs);
+            }
+        }
+        {
+            if (!c->coop_blocks) c->coop_blocks = rt::max_coop_blocks((const void *)k_boruvka, K3_THREADS, 0, c->device);
+            int g = c->coop_blocks;
+            // a cooperative grid must be resident as a whole: while the hierarchical stage of earlier device batches occupies part of
+            // every SM (S2Set), a full-occupancy grid would wait for those kernels to drain, so it is sized to fit beside them
+            if (c->s2_overlap && g > c->sms * 2) g = c->sms * 2;
+            const int want = (int)((d.N / 4 + K3_THREADS - 1) / K3_THREADS);
+            if (g > want) g = want < 1 ? 1 : want;
+            rt::launch(st, "k_boruvka", rt::COOP, k_boruvka, dim3(g), dim3(K3_THREADS), 0, b);
+        }
+        rt::launch(st, "k_chain_insert", rt::THR, k_chain_insert, dim3(grid_for(c, d.N / 2, K4_THREADS, 16)), dim3(K4_THREADS), 0, d, b);
+        {
+            // rows per segment: enough threads to fill the machine, as few restarts as possible
+            const u64 wpad = (d.w + 31) & ~31u;
+            const u64 target = (u64)c->sms * 2048 * (u64)ds.n;   // enough column walkers to fill every device
+            u32 nseg = (u32)((target + wpad * d.nimg - 1) / (wpad * d.nimg));
+            if (nseg < 1) nseg = 1;
+            if (nseg > d.h) nseg = d.h;
+            u32 rows = (d.h + nseg - 1) / nseg;
+            static const int env_rows = getenv("VCB_ATTR_ROWS") ? atoi(getenv("VCB_ATTR_ROWS")) : 0;
+            static const int env_per_sm = getenv("VCB_ATTR_PER_SM") ? atoi(getenv("VCB_ATTR_PER_SM")) : 16;
+            if (env_rows > 0 && (u32)env_rows < rows) rows = (u32)env_rows;
+            if (rows < 8 && d.h >= 8) rows = 8;
+            const u32 nseg_t = (d.h + rows - 1) / rows;
+            if (multi) { const int e = sync_devices(ds); if (e) return e; }
+            for (int k = 0; k < ds.n; ++k) {                  // K5: device k takes the row segments that start in its band
+                vcb_ctx *ck = ds.ctx[k];
+                u32 s0 = multi ? (ds.row_begin(k, d) + rows - 1) / rows : 0, s1 = multi ? (ds.row_begin(k + 1, d) + rows - 1) / rows : nseg_t * d.nimg;
+                if (multi && s1 > nseg_t) s1 = nseg_t;
+                if (s1 <= s0) continue;
+                rt::set_device(ck->device);
+                const u64 t_lo = (u64)s0 * wpad, t_hi = (u64)s1 * wpad;
+                const int g = grid_for(ck, t_hi - t_lo, K5_THREADS, env_per_sm);
+                if (want_attr)
+                    rt::launch(ck->st, "k_attribute", rt::THR, k_attribute<P, true>, dim3(g), dim3(K5_THREADS), 0, d, pol, b, rows, keep_key, t_lo, t_hi);
+                else
+                    rt::launch(ck->st, "k_attribute", rt::THR, k_attribute<P, false>, dim3(g), dim3(K5_THREADS), 0, d, pol, b, rows, keep_key, t_lo, t_hi);
+            }
+            if (multi) { const int e = sync_devices(ds); if (e) return e; }
+        }
+        rt::launch(st, "k_tournament", rt::THR, k_tournament, dim3(grid_for(c, d.N / 4, K6_THREADS, 16)), dim3(K6_THREADS), 0, d, b);
+        if (res_mode) rt::launch(st, "k_res_resolve", rt::SEQ, k_res_resolve, dim3(grid_for(c, d.N / 8, 256, 8)), dim3(256), 0, d, b);
+        prims::scan(st, "scan_label", LabelScan{d, b, res_mode ? 1 : 0}, c->chunksum, d.N, c->sms * 8);
+        if (res_mode) rt::launch(st, "k_res_labels", rt::SEQ, k_res_labels, dim3(grid_for(c, d.N / 8, 256, 8)), dim3(256), 0, b);
+        rt::launch(st, "k_image_meta", rt::SEQ, k_image_meta, dim3(g_img), dim3(128), 0, d, b, base);
+        rt::launch(st, "k_leaf_final", rt::SEQ, k_leaf_final, dim3(grid_for(c, d.N / 4, K8_THREADS, 16)), dim3(K8_THREADS), 0, d, b, base);
+        if (res->labels) {
+            if (multi) { const int e = sync_devices(ds); if (e) return e; }
+            for (int k = 0; k < ds.n; ++k) {
+                vcb_ctx *ck = ds.ctx[k];
+                const u32 p0 = multi ? ds.row_begin(k, d) * d.w : 0, p1 = multi ? ds.row_begin(k + 1, d) * d.w : d.N;
+                if (p1 <= p0) continue;
+                rt::set_device(ck->device);
+                rt::launch(ck->st, "k_labels", rt::SEQ, k_labels, dim3(grid_for(ck, p1 - p0, K8_THREADS, 16)), dim3(K8_THREADS), 0, d, b, res->labels, p0, p1);
+            }
+            if (multi) { const int e = sync_devices(ds); if (e) return e; }
+        }
 
-    // one small read-back: per-image slot counts (sizes of the result) and the error flags
-    ImgMeta *hm = (ImgMeta *)c->h_pinned;
-    Counters *hc = (Counters *)((char *)c->h_pinned + (d.nimg + 1) * sizeof(ImgMeta));
-    rt::copy_d2h(st, hm, b.meta, d.nimg * sizeof(ImgMeta));
-    rt::copy_d2h(st, hc, b.ctr, sizeof(Counters));
-    if (rt::stream_sync(st) != 0 || st.last_error) {
-        c->err = st.last_error ? st.last_error_text : std::string("stream synchronize failed");
-        st.last_error = 0;
-        return VCB_ERR_CUDA;
+        // one small read-back: per-image slot counts (sizes of the result) and the error flags
+        hm = (ImgMeta *)c->h_pinned;
+        hc = (Counters *)((char *)c->h_pinned + (d.nimg + 1) * sizeof(ImgMeta));
+        rt::copy_d2h(st, hm, b.meta, d.nimg * sizeof(ImgMeta));
+        rt::copy_d2h(st, hc, b.ctr, sizeof(Counters));
+        if (rt::stream_sync(st) != 0 || st.last_error) {
+            c->err = st.last_error ? st.last_error_text : std::string("stream synchronize failed");
+            st.last_error = 0;
+            return VCB_ERR_CUDA;
+        }
+        if (!res_mode || hc->res_diff == 0) break;
+        if (pass >= 200) { c->err = "stale-upleft fixpoint did not converge"; return VCB_ERR_UNSUPPORTED; }
+        pol.set_use_res();
     }
     meta_out.assign(hm, hm + d.nimg);
     ctr_out = *hc;
     c->last_counters[0] = hc->ncand; c->last_counters[1] = hc->kt; c->last_counters[2] = hc->lt; c->last_counters[3] = hc->rounds;
-    c->last_counters[4] = hc->err;
+    c->last_counters[4] = hc->err; c->last_counters[5] = hc->nres; c->last_counters[6] = (u32)npass;
     return VCB_OK;
 }
 
@@ -537,6 +552,7 @@ inline int stage2_launch(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg
     a.cfg.hier_max = cfg->hierarchical == VCB_HIERARCHICAL_MAX;
     a.cfg.batch_rounds = std::getenv("VCB_S2_NOBATCH") ? 0 : 1;
     a.cfg.rect_perim = std::getenv("VCB_S2_RECT_PERIM") ? 1 : 0;
+    a.cfg.timing = std::getenv("VCB_S2_STATS") ? 1 : 0;
 #ifdef VCB_HOSTSIM
     a.cfg.help_min_px = 12;
 #else
@@ -639,6 +655,12 @@ inline int stage2_finish(vcb_ctx *c, BatchResult *res) {
     if (std::getenv("VCB_S2_STATS"))
         std::fprintf(stderr, "[vcb] stage 2 image 0: merges %u, outputs %u, batch rounds %u (candidates %u, committed %u), single pops %u\n",
                      h[0].nmerge, h[0].nout, h[0].st_rounds, h[0].st_cands, h[0].st_committed, h[0].st_singles);
+    if (std::getenv("VCB_S2_STATS")) {
+        static const char *names[14] = {"select", "nbr", "decide", "perim", "merge", "relabel", "bF", "bP", "bC", "bD", "bE", "collect", "sort", "out"};
+        std::fprintf(stderr, "[vcb] stage 2 image 0 kcycles:");
+        for (int k = 0; k < 13; ++k) std::fprintf(stderr, " %s %llu", names[k], h[0].tph[k] / 1000ull);
+        std::fprintf(stderr, "\n");
+    }
     if (res->pool1) {
         // ordered indices / holes pools from the stage-1 pool and the merge forest
         const S2 &a = res->s2args;

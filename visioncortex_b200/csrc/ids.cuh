@@ -20,8 +20,15 @@ namespace vcb {
 constexpr u32 NONE = 0xFFFFFFFFu;
 constexpr u32 TAG = 0x80000000u;   // node ids: leaf = TAG | pixel, event = pixel; also "dead" mark in the candidate list
 
-enum : u32 { J_NEW = 0, J_UP = 1, J_LEFT = 2, J_UPLEFT = 3, J_NONE = 4, J_RUP = 5, J_MASK = 7,
-             F_M = 8, F_CAND = 16, F_MSF = 32, F_FINAL = 64 };
+enum : u32 { J_NEW = 0, J_UP = 1, J_LEFT = 2, J_UPLEFT = 3, J_NONE = 4, J_RUP = 5, J_RES = 6, J_MASK = 7,
+             F_M = 8, F_CAND = 16, F_MSF = 32, F_FINAL = 64, F_STALE = 128 };
+// J_RES / F_STALE (colour path, diagonal = true): builder.rs:301-305 reads cluster_upleft BEFORE the merge step of the same
+// pixel, so an UPLEFT join whose up-left cluster has just lost that merge puts the pixel into the dead slot and brings it
+// back to life (builder.rs:341-343).  Such a pixel starts a provisional cluster of its own that
+// carries the dead label instead of a fresh one: join code J_RES.  Whether it happens depends on merge outcomes earlier in
+// the scan, so the set of these pixels is found as the fixpoint of "run the pipeline, F_STALE marks the pixels where the
+// stale side lost, the next pass turns exactly those into J_RES leaves" (run_stage1; the fixpoint is unique because a
+// pixel's outcome depends only on earlier pixels, and every pass fixes at least the earliest wrong one).
 constexpr u32 EV_LWIN = 0x100u;   // EvRec.arrive: bits 0-1 = side of the up-left cluster (stale check), bit 8 = left child won
 // F_FINAL: pc[] already holds the leaf after the tile kernel (its tile-local root is a NEW pixel); J_NONE on the colour path = keyed pixel
 
@@ -30,7 +37,8 @@ struct Dims { u32 w, h, n, nimg, N; };
 // one 32-byte sector per record; records are indexed by *pixel* (sparse): only NEW pixels own a leaf record and only
 // candidate-event pixels own an event record, and each is initialised by the kernel that creates it (no memsets).
 struct LeafA { u32 ufp, best0, best1, parL, cnt, death, label, flabel; };
-struct LeafS { u32 sum[4]; u32 npx; u32 pad[3]; };
+struct LeafS { u32 sum[4]; u32 npx; u32 pad[3]; };   // pad[0]: NEW leaf: slot freed by a later incarnation; J_RES leaf: the leaf whose label it carries
+                                                     // pad[1..2]: listing pair (listing.cuh)
 struct LeafR { i32 minx, maxx, miny, maxy; };
 struct EvRec { u32 parE, cnt, childU, arrive, a_wl, b_wu, carL, carU; };
 
@@ -47,12 +55,14 @@ struct ImgMeta {
 struct Counters {
     u32 ncand;             // candidate events
     u32 live[2];           // boruvka: any live edge this round
-    u32 err;               // bit 0: unclean key colour, bit 1: stale-upleft resurrection
+    u32 err;               // bit 0: unclean key colour, bit 2: a slot freed by builder.rs:315-317 is resurrected at the same pixel
     u32 kt;                // total leaves (all images)
     u32 rounds;            // boruvka rounds executed
     u32 lt;                // total real leaves (NEW events that were not contracted)
     u32 twork;             // k_tournament work counter
     u32 cwork;             // k_chain_insert work counter
+    u32 res_diff;          // pixels whose stale-upleft status differs from the J_RES set this pass ran with (0 = fixpoint)
+    u32 nres;              // J_RES leaves of this pass
 };
 
 struct Bufs {
@@ -66,6 +76,10 @@ struct ColorPolicy {
     const u32 *rgba;       // RGBA8 packed little-endian: r | g<<8 | b<<16 | a<<24 (image/format.rs:29-33)
     int shift, thres, diagonal, has_key;
     u32 key;
+    int use_res = 0;       // second and later passes of the stale-upleft fixpoint: flags[] still holds the previous pass
+    __device__ __forceinline__ bool resurrected(const u8 *flags, u32 g) const { return use_res && (flags[g] & F_STALE); }
+    bool fixpoint() const { return diagonal != 0; }
+    void set_use_res() { use_res = 1; }
 
     __device__ __forceinline__ u32 load(u32 g) const { return __ldg(rgba + g); }
     // color_same (color_clusters/runner.rs:116-129): alpha ignored.  The three channel tests run as one byte-wise SIMD
@@ -124,6 +138,10 @@ struct BinaryPolicy {
         return f | J_NEW;
     }
     __device__ __forceinline__ void stats(u32, u32 *s) const { s[0] = s[1] = s[2] = s[3] = 0; }
+    // immune: its upleft branch excludes v_up && v_left (clusters.rs:303-311), so an UPLEFT join never sits on a merge
+    __device__ __forceinline__ bool resurrected(const u8 *, u32) const { return false; }
+    bool fixpoint() const { return false; }
+    void set_use_res() {}
 };
 
 // --------------------------------------------------------------------------------------------------------------
@@ -218,6 +236,7 @@ template <class P> __device__ __forceinline__ void edges_tile_body(const Dims &d
             const u32 c = pix[(ly + 1) * PW + lx + XO], up = pix[ly * PW + lx + XO];
             const u32 left = pix[(ly + 1) * PW + lx + XO - 1], ul = pix[ly * PW + lx + XO - 1];
             f = pol.classify(c, up, left, ul, gy > 0, gx > 0, &err);
+            if ((f & J_MASK) == J_UPLEFT && lx < TW && pol.resurrected(b.flags, base + gy * d.w + gx)) f = (f & ~J_MASK) | J_RES;
         }
         fl[i] = (u8)f;
     }
@@ -270,15 +289,16 @@ template <class P> __device__ __forceinline__ void edges_tile_body(const Dims &d
             const int r = lp[i];
             const u32 jr = fl[(r / TW) * FW + r % TW] & J_MASK;
             const u32 gr = base + (y0 + r / TW) * d.w + x0 + r % TW;
-            root = jr == J_NEW ? gr : jr == J_UP ? gr - d.w : jr == J_LEFT ? gr - 1 : jr == J_UPLEFT ? gr - d.w - 1 : gr - d.w + 1;
-            if (jr == J_NEW) fin = F_FINAL;
+            const bool leaf = jr == J_NEW || jr == J_RES;
+            root = leaf ? gr : jr == J_UP ? gr - d.w : jr == J_LEFT ? gr - 1 : jr == J_UPLEFT ? gr - d.w - 1 : gr - d.w + 1;
+            if (leaf) fin = F_FINAL;
         }
         b.flags[g] = (u8)(f | fin);
         b.pc[g] = root;
-        if (j == J_NEW) {
+        if (j == J_NEW || j == J_RES) {
             LeafA a; a.ufp = g; a.best0 = NONE; a.best1 = NONE; a.parL = NONE; a.cnt = 1; a.death = NONE; a.label = 0; a.flabel = 0;
             b.la[g] = a;
-            LeafS s; pol.stats(pix[(ly + 1) * PW + lx + XO], s.sum); s.npx = 1; s.pad[0] = s.pad[1] = s.pad[2] = 0;
+            LeafS s; pol.stats(pix[(ly + 1) * PW + lx + XO], s.sum); s.npx = 1; s.pad[0] = j == J_RES ? NONE : 0u; s.pad[1] = s.pad[2] = 0;
             b.ls[g] = s;
             LeafR r; r.minx = r.maxx = (i32)gx; r.miny = r.maxy = (i32)gy;
             b.lr[g] = r;
@@ -676,10 +696,10 @@ __global__ void __launch_bounds__(K5_THREADS) k_attribute(Dims d, P pol, Bufs b,
                 if (upnode == NONE) { upnode = b.pc[p - d.w] | TAG; uppar = node_par_ro(b, upnode); }
                 climb2(b, upnode, uppar, p - 1);
                 stcg(&b.ev[p].childU, upnode);
-                if (j == J_UPLEFT) {
+                if (j == J_UPLEFT || j == J_RES) {
                     // builder.rs:301-305 reads cluster_upleft BEFORE the merge step: if the up-left pixel's cluster is one of
                     // the two merging sides and loses, the reference labels this pixel with the dead slot (SURVEY Appendix E
-                    // item 5).  Record which side it is on; k_tournament rejects the input if that side loses.
+                    // item 5).  Record which side it is on; k_tournament marks the pixel F_STALE if that side loses.
                     u32 ul = gl_n, ulp = gl_p;
                     if (lane == 0 || ul == NONE) { ul = b.pc[p - d.w - 1] | TAG; ulp = node_par_ro(b, ul); }
                     climb2(b, ul, ulp, p - 1);
@@ -690,7 +710,7 @@ __global__ void __launch_bounds__(K5_THREADS) k_attribute(Dims d, P pol, Bufs b,
             }
             bool resolved = true;
             if (valid && j != J_NONE) {
-                if (j == J_NEW) { g = p | TAG; gpar = __ldg(&b.la[p].parL); prefetch_event(b, gpar); }
+                if (j == J_NEW || j == J_RES) { g = p | TAG; gpar = __ldg(&b.la[p].parL); prefetch_event(b, gpar); }
                 else if (j == J_LEFT && lane > 0) resolved = false;          // wait for the lane to the left
                 else {
                     if (j == J_UP && upnode != NONE) { g = upnode; gpar = uppar; }
@@ -716,7 +736,7 @@ __global__ void __launch_bounds__(K5_THREADS) k_attribute(Dims d, P pol, Bufs b,
                     }
                 } else {
                     if (WRITE_ATTR) b.attr[p] = g;
-                    if (j != J_NEW) {
+                    if (j != J_NEW && j != J_RES) {
                         if (g == run_node) run_cnt++;
                         else {
                             if (run_cnt) atomicAdd((run_node & TAG) ? &b.la[run_node & ~TAG].cnt : &b.ev[run_node].cnt, run_cnt);
@@ -774,7 +794,7 @@ __device__ static __forceinline__ u64 nl_count(u64 w) {
 #pragma unroll
     for (int k = 0; k < NL_ITEMS; ++k) {
         const u32 j = (u32)(w >> (8 * k)) & J_MASK;
-        s += (j == J_NEW ? 0x100000001ull : 0ull) + (j == J_RUP ? 1ull : 0ull);   // low half: NEW events, high half: leaves
+        s += (j == J_NEW ? 0x100000001ull : 0ull) + (j == J_RUP ? 1ull : 0ull) + (j == J_RES ? 0x100000000ull : 0ull);   // low half: NEW events, high half: leaves
     }
     return s;
 }
@@ -828,6 +848,7 @@ __global__ void __launch_bounds__(NL_THREADS, 6) k_newleaf_apply(Dims d, Bufs b,
                     const u32 j = (u32)(w[q] >> (8 * k)) & J_MASK;
                     if (j == J_NEW) { b.newlist[xn++] = i; b.leaflist[xl++] = i; }
                     else if (j == J_RUP) b.newlist[xn++] = i | TAG;
+                    else if (j == J_RES) b.leaflist[xl++] = i;
                     if (i == d.N - 1) { b.ctr->kt = xn; b.ctr->lt = xl; }
                 }
             }
@@ -839,7 +860,7 @@ __global__ void __launch_bounds__(NL_THREADS, 6) k_newleaf_apply(Dims d, Bufs b,
 struct LeafScan {
     Dims d; Bufs b;
     __device__ u32 count() const { return d.N; }
-    __device__ u32 value(u32 i) const { return (b.flags[i] & J_MASK) == J_NEW ? 1u : 0u; }
+    __device__ u32 value(u32 i) const { const u32 j = b.flags[i] & J_MASK; return (j == J_NEW || j == J_RES) ? 1u : 0u; }
     __device__ void emit(u32 i, u32 ex, u32 v) const {
         if (v) b.leaflist[ex] = i;
         if (i == d.N - 1) b.ctr->lt = ex + v;
@@ -862,16 +883,25 @@ __device__ static __forceinline__ void tournament_step(const Bufs &b, TWalk &w, 
     const u32 Wo = (u32)other, co = (u32)(other >> 32);
     const u32 WL = up ? Wo : w.W, WU = up ? w.W : Wo;
     const u32 cL = up ? co : w.car, cU = up ? w.car : co;
-    u32 lwin = 0;
+    u32 lwin = 0, dead = NONE;
     if (WL <= WU) {                                       // left loses: its label dies as the left side (builder.rs:313-318)
         stcg(&b.la[cL].death, w.v | TAG);
         w.car = cU;
-        if (stale == 1) atomicOr(&b.ctr->err, 2u);
+        if (stale == 1) dead = cL;
     } else {
         stcg(&b.la[cU].death, w.v);
         w.car = cL;
         lwin = EV_LWIN;
-        if (stale == 2) atomicOr(&b.ctr->err, 2u);
+        if (stale == 2) dead = cU;
+    }
+    if (dead != NONE) {
+        // the pixel of this event joins its up-left cluster through a label read before the merge (builder.rs:301-305): it
+        // resurrects the slot that has just died.  This pass either already runs with the pixel as a J_RES leaf (record the
+        // leaf whose label it carries) or has to be repeated with it
+        const u32 f = b.flags[w.v];
+        b.flags[w.v] = (u8)(f | F_STALE);
+        if ((f & J_MASK) == J_RES) stcg(&b.ls[w.v].pad[0], dead);
+        else atomicAdd(&b.ctr->res_diff, 1u);
     }
     stcg(&e->arrive, stale | lwin);
     stcg(&e->a_wl, WL); stcg(&e->b_wu, WU);               // both child areas, for the listing pass
@@ -965,10 +995,12 @@ __global__ void __launch_bounds__(K6_THREADS) k_tournament(Dims d, Bufs b) {
 // the freed slot is handed to the next new cluster).  label = base + #{earlier leaves of the image not in D}.
 struct LabelScan {
     Dims d; Bufs b;
+    int res_mode;                                         // J_RES leaves exist: a later incarnation of the label may have freed the slot
     __device__ u32 count() const { return ldcg(&b.ctr->kt); }
     __device__ u32 value(u32 k) const {
         const u32 e = b.newlist[k];
         if (e & TAG) return 0u;                           // contracted NEW event: in D by construction
+        if (res_mode && b.ls[e].pad[0]) return 0u;        // k_res_resolve
         const u32 death = b.la[e].death;
         if (death == NONE || !(death & TAG)) return 1u;
         const u32 kt = ldcg(&b.ctr->kt);
@@ -989,6 +1021,51 @@ struct LabelScan {
         if (k == b.meta[img].leaf_begin) b.meta[img].notd_base = ex;
     }
 };
+
+// J_RES leaves (see the enum above).  A resurrected leaf r carries the label of the leaf that lost at r's own pixel; chains of
+// resurrections end at the NEW leaf o that was handed the slot.  The slot is handed on to the next new cluster
+// (builder.rs:315-317) when ANY incarnation of the label dies as the left side before the next NEW event after o, because
+// the label is then still the most recently allocated one: that is recorded on o for the numbering scan.  If the
+// incarnation that dies this way is resurrected at the very same pixel, the next NEW event overwrites a live slot
+// (builder.rs:347-348) and its pixels are orphaned: err bit 2, such inputs go to the sequential replay.
+__device__ static __forceinline__ u32 next_new_after(const Dims &d, const Bufs &b, u32 o) {
+    const u32 kt = ldcg(&b.ctr->kt);
+    u32 lo = 0, hi = kt;                                  // newlist is ascending in pixel id (contracted entries carry TAG)
+    while (hi - lo > 1) { const u32 mid = (lo + hi) / 2; if ((b.newlist[mid] & ~TAG) <= o) lo = mid; else hi = mid; }
+    if (lo + 1 >= kt) return NONE;
+    const u32 nxt = b.newlist[lo + 1] & ~TAG;
+    return nxt / d.n != o / d.n ? NONE : nxt;
+}
+__global__ void __launch_bounds__(256) k_res_resolve(Dims d, Bufs b) {
+    const u32 lt = ldcg(&b.ctr->lt);
+    const u32 stride = gridDim.x * 256;
+    for (u32 k = blockIdx.x * 256 + threadIdx.x; k < lt; k += stride) {
+        const u32 r = b.leaflist[k];
+        const u32 f = b.flags[r];
+        if ((f & J_MASK) != J_RES) continue;
+        atomicAdd(&b.ctr->nres, 1u);
+        if (!(f & F_STALE)) { atomicAdd(&b.ctr->res_diff, 1u); b.la[r].label = NONE; continue; }   // not resurrected after all
+        const u32 src = ldcg(&b.ls[r].pad[0]);
+        u32 o = src;
+        while (o != NONE && (b.flags[o] & J_MASK) == J_RES) o = ldcg(&b.ls[o].pad[0]);
+        b.la[r].label = o;                                // origin; replaced by its label after the numbering scan
+        if (o == NONE) continue;
+        const u32 nxt = next_new_after(d, b, o);
+        const u32 death = b.la[r].death;
+        if (death != NONE && (death & TAG) && (death & ~TAG) <= nxt) stcg(&b.ls[o].pad[0], 1u);
+        if (b.la[src].death == (r | TAG) && r <= nxt) atomicOr(&b.ctr->err, 4u);
+    }
+}
+__global__ void __launch_bounds__(256) k_res_labels(Bufs b) {
+    const u32 lt = ldcg(&b.ctr->lt);
+    const u32 stride = gridDim.x * 256;
+    for (u32 k = blockIdx.x * 256 + threadIdx.x; k < lt; k += stride) {
+        const u32 r = b.leaflist[k];
+        if ((b.flags[r] & J_MASK) != J_RES) continue;
+        const u32 o = b.la[r].label;
+        b.la[r].label = o == NONE ? 0u : b.la[o].label;
+    }
+}
 
 // per image: slot count: base + #(leaves not in D) + [last leaf in D]
 __global__ void k_image_meta(Dims d, Bufs b, u32 base) {

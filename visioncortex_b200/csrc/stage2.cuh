@@ -21,6 +21,7 @@ struct S2Cfg {
     u64 help_min_px;   // rects at least this large are counted by the whole thread-block cluster
     int batch_rounds;  // parallel batch rounds on (default) / off
     int rect_perim;    // 1: perimeter by scanning the bounding rect (cluster helpers); 0: by the boundary-pixel lists
+    int timing;        // VCB_S2_STATS: thread 0 accumulates the cycles spent in each phase of a pop / batch round (S2ImgState.tph)
 };
 
 struct S2ImgState {
@@ -28,6 +29,7 @@ struct S2ImgState {
     u32 nmerge, task_c, task_quit, perim_acc;
     i32 task_rect[4];
     u32 st_rounds, st_committed, st_cands, st_singles;   // statistics of the batch rounds / single pops
+    unsigned long long tph[16];                          // cycles per phase (S2Cfg.timing)
 };
 
 struct S2 {
@@ -64,6 +66,10 @@ struct S2 {
 // multi-launch path, or the CTA's own shared-memory array of ready-made (area << idx_bits | index) keys (fused kernel).
 struct S2Keys { const u64 *g; const u64 *s; u64 mask, add; };
 __device__ static __forceinline__ u64 s2_key(const S2Keys &k, u32 i) { return k.s ? k.s[i] : ((k.g[i] & k.mask) + k.add); }
+
+// phase timing (thread 0, after a barrier): the cycles since the previous tick are added to phase k
+enum { TP_SELECT = 0, TP_NBR, TP_DECIDE, TP_PERIM, TP_MERGE, TP_RELABEL, TP_BF, TP_BP, TP_BC, TP_BD, TP_BE, TP_COLLECT, TP_SORT, TP_OUT };
+#define S2_TICK(k) do { if (a.cfg.timing && threadIdx.x == 0) { const unsigned long long t_ = clock64(); sh->tph[k] += t_ - sh->tlast; sh->tlast = t_; } } while (0)
 
 constexpr u32 FLAGBIT = 0x80000000u;
 constexpr u32 HOLLOWBIT = 0x40000000u;
@@ -225,6 +231,7 @@ struct S2Shared {
     u32 bmem[S2_NB][S2_CAPM];
     u32 nb, ncommit, mode, force_single, brounds, bdone, boff;
     u32 nlive, wsum[33];
+    unsigned long long tph[16], tlast;
     alignas(16) u8 map[S2_MAPBYTES];   // last member: allocated only in the rect-scan perimeter mode
 };
 
@@ -309,6 +316,7 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
         } else if (lane == 0) { sh->mode = 0; sh->force_single = 0; }
     }
     __syncthreads();
+    S2_TICK(TP_BF);
     if (sh->mode == 0) return false;
     if (sh->mode == 2) return true;
     const u32 nb = sh->nb;
@@ -420,6 +428,7 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
     }
     __threadfence_block();
     __syncthreads();
+    S2_TICK(TP_BP);
     // ---- C: conflicts with earlier candidates of the batch
     for (u32 q = warp; q < nb; q += nwarps) {
         const u32 c = sh->bc[q];
@@ -433,6 +442,7 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
         if (__any_sync(0xffffffffu, conf) && lane == 0) sh->bflags[q] = f | BF_CONFLICT;
     }
     __syncthreads();
+    S2_TICK(TP_BC);
     // ---- D: warp 0 decides the committed prefix, output positions and the running maximum area
     if (warp == 0) {
         const bool in = lane < nb;
@@ -480,6 +490,7 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
         }
     }
     __syncthreads();
+    S2_TICK(TP_BD);
     // ---- E: commit the prefix in parallel (independent by construction), then clear the tmin marks
     const u32 J = sh->ncommit;
     for (u32 q = warp; q < nb; q += nwarps) {
@@ -544,6 +555,7 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
     }
     __threadfence_block();
     __syncthreads();
+    S2_TICK(TP_BE);
     return true;
 }
 
@@ -739,6 +751,7 @@ __device__ static __forceinline__ void s2_epoch_leader(const S2 &a, S2Shared *sh
             }
         }
         __syncthreads();
+        S2_TICK(TP_SELECT);
         const u32 c = sh->cur;
         if (c == NONE) break;
         const u32 area = sh->area;
@@ -791,6 +804,7 @@ __device__ static __forceinline__ void s2_epoch_leader(const S2 &a, S2Shared *sh
             __syncthreads();                                          // thread 0 rewrites sh->more in the next round
             if (last) break;
         }
+        S2_TICK(TP_NBR);
         const u32 ndist = sh->ndist;
         if (ndist == 0) {                                             // builder.rs:444-450
             if (tid == 0 && (area == ist->maxarea || a.cfg.can_discard)) {
@@ -814,6 +828,7 @@ __device__ static __forceinline__ void s2_epoch_leader(const S2 &a, S2Shared *sh
             sh->rect[0] = rc->rect[0]; sh->rect[1] = rc->rect[1]; sh->rect[2] = rc->rect[2]; sh->rect[3] = rc->rect[3];
         }
         __syncthreads();
+        S2_TICK(TP_DECIDE);
         const u32 target = sh->target;
         bool deepen = sh->deepen != 0;
         if (sh->want_perim) {
@@ -840,6 +855,7 @@ __device__ static __forceinline__ void s2_epoch_leader(const S2 &a, S2Shared *sh
                 __syncthreads();
             }
             deepen = (u64)sh->perim < (u64)area;
+            S2_TICK(TP_PERIM);
         }
         const bool hollow = (u64)ndist <= a.cfg.hollow_neighbours;
         if (tid == 0) {
@@ -889,6 +905,7 @@ __device__ static __forceinline__ void s2_epoch_leader(const S2 &a, S2Shared *sh
             if (sh->nchunks > 1) sh->more = c;                        // the member list no longer fits sh->mem: walk it again
         }
         __syncthreads();
+        S2_TICK(TP_MERGE);
         // relabel: every member slot of c now resolves to the target (builder.rs:527-529)
         {
             const u32 nf = sh->newfw;
@@ -916,6 +933,7 @@ __device__ static __forceinline__ void s2_epoch_leader(const S2 &a, S2Shared *sh
             }
         }
         __syncthreads();
+        S2_TICK(TP_RELABEL);
     }
 }
 
@@ -1017,21 +1035,24 @@ __global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_run(S2 a, int max_epoch, 
     if (crank != 0) { s2_helper_loop(a, sh, ist, img, base, crank, G); return; }
     // the key array follows the fixed part of the shared block (and the byte map of the rect-scan perimeter mode)
     u64 *skeys = reinterpret_cast<u64 *>(reinterpret_cast<u8 *>(sh) + ((offsetof(S2Shared, map) + (a.cfg.rect_perim ? S2_MAPBYTES : 0u) + 15u) & ~(size_t)15));
-    if (tid == 0) sh->nlive = nslots;
+    if (tid == 0) { sh->nlive = nslots; for (int k = 0; k < 16; ++k) sh->tph[k] = 0; sh->tlast = clock64(); }
     __syncthreads();
     for (int ep = 0; ep <= max_epoch; ++ep) {
         // the roots still alive bound the number of keys: shared memory when they fit, the image's global key range otherwise
         u64 *kbuf = (ep == 0 ? nslots : sh->nlive) <= a.key_cap ? skeys : a.keys + base;
         __syncthreads();
         const u32 n = s2_collect_epoch(a, sh, kbuf, base, nslots, ep, ep == 0);
+        S2_TICK(TP_COLLECT);
         if (n == 0) continue;
         if (ep > 0 && n > 1) s2_sort_keys(kbuf, n);              // epoch 0: every area is 1, collected in index order
+        S2_TICK(TP_SORT);
         if (tid == 0) { sh->lo = 0; sh->hi = n; sh->nurg = 0; sh->force_single = 0; sh->mode = 0; sh->brounds = 0; sh->bdone = 0; sh->boff = 0; }
         __syncthreads();
         const S2Keys keys{nullptr, kbuf, 0ull, 0ull};
         s2_epoch_leader(a, sh, ist, keys, ep, img, base, a.over + base, G);
         __syncthreads();
     }
+    if (a.cfg.timing && tid == 0) for (int k = 0; k < 16; ++k) ist->tph[k] = sh->tph[k];
     s2_release_helpers(ist, G);
 }
 

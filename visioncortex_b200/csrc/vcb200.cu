@@ -127,7 +127,7 @@ int run_color(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w,
     e = run_stage1(c, d, pol, 1u, want_pool, keep ? 1 : 0, br.get(), meta, ctr, ds);
     if (e) return e;
     if (ctr.err & 1u) return fail(c, VCB_ERR_UNSUPPORTED, "key colour is not clean: a non-key pixel is color_same to the key (order-dependent in the reference)");
-    if (ctr.err & 2u) return fail(c, VCB_ERR_UNSUPPORTED, "diagonal=true: a stale cluster_upleft label resurrects a dead slot in the reference (builder.rs:301-305,341-343); this input is fenced");
+    if (ctr.err & 4u) return fail(c, VCB_ERR_UNSUPPORTED, "diagonal=true: a slot freed by builder.rs:315-317 is resurrected at the same pixel through the stale cluster_upleft label (builder.rs:301-305,341-343) and then overwritten (builder.rs:347-348)");
     e = build_records(c, d, meta, br.get(), cfg->hierarchical == 0, keep);
     if (e) return e;
     if (want_pool) {

@@ -242,7 +242,9 @@ template <> inline bool launch_edges_tma<ColorPolicy>(vcb_ctx *c, const Dims &d,
     if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)pol.rgba, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return false;
-    rt::launch(c->st, "k_edges_tile", rt::THR, k_edges_tile_tma<ColorPolicy>, dim3(tiles), dim3(K1_THREADS), K1_SMEM, d, pol, b, tmap, tile0);
+    static const bool old_k1 = std::getenv("VCB_K1_TILE") != nullptr;      // the pointer-jumping tile kernel, for comparison
+    if (old_k1) rt::launch(c->st, "k_edges_tile", rt::THR, k_edges_tile_tma<ColorPolicy>, dim3(tiles), dim3(K1_THREADS), K1_SMEM, d, pol, b, tmap, tile0);
+    else rt::launch(c->st, "k_edges_tile", rt::THR, k_edges_rows_tma<ColorPolicy>, dim3((tiles + RW_WARPS - 1) / RW_WARPS), dim3(RW_THREADS), RW_SMEM, d, pol, b, tmap, tile0, tiles);
     return true;
 }
 #endif
@@ -278,8 +280,16 @@ inline int run_stage1(vcb_ctx *c, const Dims &d, const P &pol_in, u32 base, bool
             if (t1 <= t0) continue;
             rt::set_device(ck->device);
             const u32 tile0 = t0 * tiles_x, tiles = (t1 - t0) * tiles_x;
-            if (!launch_edges_tma(ck, d, pol, b, tile0, tiles))
-                rt::launch(ck->st, "k_edges_tile", rt::THR, k_edges_tile<P>, dim3(tiles), dim3(K1_THREADS), K1_SMEM, d, pol, b, tile0);
+            if (!launch_edges_tma(ck, d, pol, b, tile0, tiles)) {
+                bool done = false;
+                if constexpr (P::row_sweep) {
+                    if (d.w % 4 == 0 && !std::getenv("VCB_K1_TILE")) {
+                        rt::launch(ck->st, "k_edges_tile", rt::THR, k_edges_rows<P>, dim3((tiles + RW_WARPS - 1) / RW_WARPS), dim3(RW_THREADS), RW_SMEM, d, pol, b, tile0, tiles);
+                        done = true;
+                    }
+                }
+                if (!done) rt::launch(ck->st, "k_edges_tile", rt::THR, k_edges_tile<P>, dim3(tiles), dim3(K1_THREADS), K1_SMEM, d, pol, b, tile0);
+            }
         }
         if (multi) { const int e = sync_devices(ds); if (e) return e; }
         for (int k = 0; k < ds.n; ++k) {                      // K2
@@ -553,6 +563,8 @@ inline int stage2_launch(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg
     a.cfg.batch_rounds = std::getenv("VCB_S2_NOBATCH") ? 0 : 1;
     a.cfg.rect_perim = std::getenv("VCB_S2_RECT_PERIM") ? 1 : 0;
     a.cfg.timing = std::getenv("VCB_S2_STATS") ? 1 : 0;
+    a.cfg.prefetch = std::getenv("VCB_S2_PREFETCH") ? std::atoi(std::getenv("VCB_S2_PREFETCH")) : 0;
+    a.cfg.boff_min = std::getenv("VCB_S2_BOFF") ? (u32)std::atoi(std::getenv("VCB_S2_BOFF")) : 6u;
 #ifdef VCB_HOSTSIM
     a.cfg.help_min_px = 12;
 #else
@@ -597,8 +609,24 @@ inline int stage2_launch(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg
         // key array holds is sorted in the image's global key range instead)
         u32 key_cap = d.nimg * 2 <= (u32)c->sms ? 16384u : 2048u;
         if (const char *ev = std::getenv("VCB_S2_KEYCAP")) key_cap = (u32)std::max(1, std::atoi(ev));
+        else key_cap = std::min(key_cap, (max_slots + 63u) & ~63u);          // an epoch never holds more keys than the image has slots
         a.key_cap = key_cap;
-        const size_t smem = smem_fixed + (size_t)key_cap * 8;
+        // per-slot state in shared memory (k_s2_run): as many of (fw, col, mnext + mtail) as fit for the largest image.  While
+        // other device batches overlap this kernel, part of every SM's shared memory is left to their stage-1 kernels
+        size_t budget = (c->s2_overlap ? 0u : 216u) * 1024u;               // overlapped batches: measured slower (stage-1 kernels starve for shared memory)
+        if (const char *ev = std::getenv("VCB_S2_SMEM_KB")) budget = (size_t)std::max(0, std::atoi(ev)) * 1024u;
+        const size_t used = smem_fixed + (size_t)key_cap * 8;
+        const size_t avail = budget > used ? budget - used : 0;
+        const u32 cap = (max_slots + 31u) & ~31u;
+        a.state_cap = cap; a.state_mask = 0;
+        if (G == 1) {
+            if ((size_t)cap * 16 <= avail) a.state_mask = 7;
+            else if ((size_t)cap * 8 <= avail) a.state_mask = 3;
+            else if ((size_t)cap * 4 <= avail) a.state_mask = 1;
+            else if (avail >= 4096 * 4) { a.state_cap = (u32)(avail / 4) & ~31u; a.state_mask = 1; }   // the smaller images of the batch
+        }
+        const size_t state_bytes = (size_t)a.state_cap * 4 * ((a.state_mask & 1) + ((a.state_mask >> 1) & 1) + ((a.state_mask >> 2) & 1) * 2);
+        const size_t smem = used + state_bytes;
         if (G > 1)
             rt::launch_cluster(st, "k_s2_epoch", k_s2_run, dim3(d.nimg * G), dim3(s2_threads), smem, G, a, max_epoch, G);
         else
@@ -656,9 +684,9 @@ inline int stage2_finish(vcb_ctx *c, BatchResult *res) {
         std::fprintf(stderr, "[vcb] stage 2 image 0: merges %u, outputs %u, batch rounds %u (candidates %u, committed %u), single pops %u\n",
                      h[0].nmerge, h[0].nout, h[0].st_rounds, h[0].st_cands, h[0].st_committed, h[0].st_singles);
     if (std::getenv("VCB_S2_STATS")) {
-        static const char *names[14] = {"select", "nbr", "decide", "perim", "merge", "relabel", "bF", "bP", "bC", "bD", "bE", "collect", "sort", "out"};
+        static const char *names[16] = {"select", "nbr", "decide", "perim", "merge", "relabel", "bF", "bP", "bC", "bD", "bE", "collect", "sort", "gather", "deg", "bP2"};
         std::fprintf(stderr, "[vcb] stage 2 image 0 kcycles:");
-        for (int k = 0; k < 13; ++k) std::fprintf(stderr, " %s %llu", names[k], h[0].tph[k] / 1000ull);
+        for (int k = 0; k < 16; ++k) std::fprintf(stderr, " %s %llu", names[k], h[0].tph[k] / 1000ull);
         std::fprintf(stderr, "\n");
     }
     if (res->pool1) {

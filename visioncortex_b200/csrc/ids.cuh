@@ -80,14 +80,33 @@ struct ColorPolicy {
     __device__ __forceinline__ bool resurrected(const u8 *flags, u32 g) const { return use_res && (flags[g] & F_STALE); }
     bool fixpoint() const { return diagonal != 0; }
     void set_use_res() { use_res = 1; }
+    static constexpr bool row_sweep = true;               // k_edges_rows (32-bit pixels, two per lane)
 
     __device__ __forceinline__ u32 load(u32 g) const { return __ldg(rgba + g); }
     // color_same (color_clusters/runner.rs:116-129): alpha ignored.  The three channel tests run as one byte-wise SIMD
     // absolute difference: m4 keeps the shifted r, g, b bytes (alpha cleared), t4 holds the threshold in every byte.
     u32 m4, t4;
+    // The row-sweep kernel tests color_same on channels spread to 10-bit fields (r | g << 10 | b << 20): with
+    //   PG(a) = P(a) | 512 per field   and   Q(b) = t per field - P(b)
+    // the sum PG(a) + Q(b) holds 512 + a - b + t in every field (257 .. 1022: no field borrows from its neighbour), and
+    // |a - b| <= t  <=>  512 <= field <= 512 + 2t  <=>  bit 9 set and (low nine bits + 511 - 2t) leaves bit 9 clear.
+    // Five integer instructions per test instead of the emulated saturating byte subtraction of same().
+    u32 t3, k3;
+    static constexpr u32 F3 = 0x00100401u, G3 = 0x200u * F3, L3 = 0x1ffu * F3;
     __host__ __device__ void prepare() {
         m4 = 0x00010101u * (u32)(255 >> shift);
-        t4 = 0x00010101u * (u32)(thres > 255 ? 255 : (thres < 0 ? 0 : thres));
+        const u32 t = (u32)(thres > 255 ? 255 : (thres < 0 ? 0 : thres));
+        t4 = 0x00010101u * t;
+        t3 = F3 * t; k3 = F3 * (511u - 2u * t);
+    }
+    __device__ __forceinline__ u32 pack3(u32 c) const {
+        const u32 v = (c >> shift) & m4;
+        return (v & 0xffu) | ((v & 0xff00u) << 2) | ((v & 0xff0000u) << 4);
+    }
+    __device__ __forceinline__ bool same3(u32 pg_a, u32 q_b) const {   // pg_a = pack3(a) | G3, q_b = t3 - pack3(b); thres >= 0
+        const u32 x = pg_a + q_b;
+        const u32 w = (x & L3) + k3;
+        return ((w | ~x) & G3) == 0u;
     }
     __device__ __forceinline__ bool same(u32 a, u32 b) const {
         if (thres < 0) return false;                      // |x - y| > thres always
@@ -142,6 +161,7 @@ struct BinaryPolicy {
     __device__ __forceinline__ bool resurrected(const u8 *, u32) const { return false; }
     bool fixpoint() const { return false; }
     void set_use_res() {}
+    static constexpr bool row_sweep = false;
 };
 
 // --------------------------------------------------------------------------------------------------------------
@@ -306,6 +326,203 @@ template <class P> __device__ __forceinline__ void edges_tile_body(const Dims &d
     }
     if (err) atomicOr(&b.ctr->err, err);
 }
+
+// --------------------------------------------------------------------------------------------------------------
+// K1, row-sweep form (colour images whose width is a multiple of 4): one WARP per TW x TH tile, no block-wide barrier.
+// The warp's 72 x 33 pixel box (tile + halo) is staged in shared memory by its own TMA bulk tensor copy; the lanes then
+// walk down the rows, lane l owning the columns 2l and 2l + 1.  Everything a pixel needs from its neighbourhood is in
+// registers: the row above is the lane's previous iteration, the pixels to the left / right belong to the neighbouring
+// lanes (one shuffle).  The tile-local J forest is resolved on the way down instead of by pointer jumping afterwards:
+//   * UP / UPLEFT / RUP joins take the root the row above already carries (own register or a neighbour's);
+//   * a run of LEFT joins takes the root of the run's head, found with two ballots: the chain walks left through the
+//     lanes whose both pixels are LEFT joins, so the head sits in the nearest lane to the left that is not all-LEFT.
+// A root is either a NEW (or resurrected) pixel of the tile -- final, F_FINAL -- or the id of the pixel outside the tile
+// that the chain leaves through, exactly what k_edges_tile writes; K2 finishes those.  Per pixel this is about a sixth of
+// the instructions of the pointer-jumping kernel, which was issue-bound (82 % SM throughput).
+constexpr int RW_WARPS = 4, RW_THREADS = RW_WARPS * 32;
+constexpr size_t RW_BOX_PITCH = (K1_PIX_BYTES + 127) & ~(size_t)127;
+constexpr size_t RW_SMEM = RW_WARPS * RW_BOX_PITCH + RW_WARPS * 8 + 16;
+static_assert(TW == 64, "two pixels per lane");
+
+template <class P> __device__ __forceinline__ void edges_rows_body(const Dims &d, const P &pol, const Bufs &b, const u32 *pix, u32 img,
+                                                                    u32 x0, u32 y0) {
+    const u32 FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const u32 base = img * d.n;
+    const u32 gx0 = x0 + 2u * (u32)lane;                 // the lane's pixels: (gx0, gy) and (gx0 + 1, gy); w is even: both or none
+    const bool act = gx0 < d.w;
+    const bool vl0 = gx0 > 0;
+    const bool can = pol.thres >= 0;                     // a negative threshold: nothing is the same colour
+    const bool diag = pol.diagonal != 0, hk = pol.has_key != 0;
+    const bool halo_r = lane == 31 && x0 + TW < d.w;     // this lane also evaluates the merge flag of the column right of the tile
+    u32 err = 0;
+    // row above: pixels (gx0, gy - 1), (gx0 + 1, gy - 1), (gx0 - 1, gy - 1) as raw values (key tests) and as Q words;
+    // box row 0 is the halo (zero-filled above the image: masked out by vu)
+    u32 u0, u1, ul0, qu0, qu1, qul0;
+    {
+        const uint2 t = *reinterpret_cast<const uint2 *>(pix + 2 * lane + XO);
+        u0 = t.x; u1 = t.y;
+        ul0 = __shfl_up_sync(FULL, u1, 1);
+        if (lane == 0) ul0 = pix[XO - 1];
+        qu0 = pol.t3 - pol.pack3(u0); qu1 = pol.t3 - pol.pack3(u1); qul0 = pol.t3 - pol.pack3(ul0);
+    }
+    // roots carried by the row above: pixel id | TAG when final (a leaf of this tile), plain id of an outside pixel otherwise
+    u32 pv0 = NONE, pv1 = NONE;
+    const u32 rows = d.h - y0 < (u32)TH ? d.h - y0 : (u32)TH;
+    for (u32 ly = 0; ly < rows; ++ly) {
+        const u32 gy = y0 + ly;
+        const u32 *row = pix + (ly + 1) * PW;
+        const uint2 t = *reinterpret_cast<const uint2 *>(row + 2 * lane + XO);
+        const u32 c0 = t.x, c1 = t.y;
+        u32 l0 = __shfl_up_sync(FULL, c1, 1);
+        if (lane == 0) l0 = row[XO - 1];
+        const u32 p0 = pol.pack3(c0), p1 = pol.pack3(c1), pl0 = pol.pack3(l0);
+        const u32 g_0 = p0 | P::G3, g_1 = p1 | P::G3, g_l0 = pl0 | P::G3;
+        const u32 q_0 = pol.t3 - p0, ql0 = pol.t3 - pl0;
+        // everything below is written with non-short-circuit operators and select chains: the compiler turns `&&` / nested
+        // `?:` over these predicates into divergent branches, which cost far more than evaluating both sides
+        const bool vu = (gy > 0) & can, v0 = vu & vl0, vl = vl0 & can;
+        // color_same of (c, up), (c, left), (c, upleft), (left, up) for both pixels (runner.rs:116-129), validity folded in
+        bool s_cu0 = vu & pol.same3(g_0, qu0), s_cl0 = vl & pol.same3(g_0, ql0), s_cul0 = v0 & pol.same3(g_0, qul0), s_lu0 = v0 & pol.same3(g_l0, qu0);
+        bool s_cu1 = vu & pol.same3(g_1, qu1), s_cl1 = can & pol.same3(g_1, q_0), s_cul1 = vu & pol.same3(g_1, qu0), s_lu1 = vu & pol.same3(g_0, qu1);
+        bool kc0 = false, kc1 = false;
+        if (hk) {
+            // builder.rs:330-334 and the clean-key rule of ColorPolicy::classify: keyed pixels are never joined
+            const u32 key = pol.key;
+            kc0 = c0 == key; kc1 = c1 == key;
+            const bool ku0 = u0 == key, ku1 = u1 == key, kl0 = l0 == key, kul0 = ul0 == key;
+            const u32 qk = pol.t3 - pol.pack3(key);
+            if (act & can & ((!kc0 & pol.same3(g_0, qk)) | (!kc1 & pol.same3(g_1, qk)))) err |= 1u;
+            s_cu0 &= !ku0; s_cl0 &= !kl0; s_cul0 &= !kul0; s_lu0 &= !ku0 & !kl0;
+            s_cu1 &= !ku1; s_cl1 &= !kc0; s_cul1 &= !ku0; s_lu1 &= !ku1 & !kc0;
+        }
+        const bool m0 = s_lu0 & (diag | (s_cl0 & s_cu0)), m1 = s_lu1 & (diag | (s_cl1 & s_cu1));
+        u32 j0 = J_NEW, j1 = J_NEW;
+        j0 = (diag & s_cul0) ? (u32)J_UPLEFT : j0; j0 = (s_cl0 & s_cul0) ? (u32)J_LEFT : j0; j0 = (s_cu0 & s_cul0) ? (u32)J_UP : j0;
+        j1 = (diag & s_cul1) ? (u32)J_UPLEFT : j1; j1 = (s_cl1 & s_cul1) ? (u32)J_LEFT : j1; j1 = (s_cu1 & s_cul1) ? (u32)J_UP : j1;
+        j0 = (kc0 | !act) ? (u32)J_NONE : j0; j1 = (kc1 | !act) ? (u32)J_NONE : j1;
+        // merge flag of the pixel to the right of pixel 1 (trivial-leaf contraction): the next lane's pixel 0, or the halo column
+        bool mr = __shfl_down_sync(FULL, (int)(act & m0), 1) != 0;
+        mr &= lane != 31;
+        if (halo_r) {
+            const u32 hc = row[XO + TW], hu = row[XO + TW - PW];
+            const u32 gh = pol.pack3(hc) | P::G3, qhu = pol.t3 - pol.pack3(hu);
+            bool s_lu = vu & pol.same3(g_1, qhu);
+            const bool s_cl = can & pol.same3(gh, pol.t3 - p1), s_cu = vu & pol.same3(gh, qhu);
+            if (hk) s_lu &= (hu != pol.key) & !kc1;
+            mr = s_lu & (diag | (s_cl & s_cu));
+        }
+        const u32 g0 = base + gy * d.w + gx0;
+        if (diag & act & pol.use_res) {
+            if (j0 == J_UPLEFT && pol.resurrected(b.flags, g0)) j0 = J_RES;
+            if (j1 == J_UPLEFT && pol.resurrected(b.flags, g0 + 1)) j1 = J_RES;
+        }
+        j0 = ((j0 == J_NEW) & m1) ? (u32)J_RUP : j0;
+        j1 = ((j1 == J_NEW) & mr) ? (u32)J_RUP : j1;
+        const u32 pvL = __shfl_up_sync(FULL, pv1, 1);        // root of (gx0 - 1, gy - 1)
+        const u32 pvR = __shfl_down_sync(FULL, pv0, 1);      // root of (gx0 + 2, gy - 1)
+        const bool top = ly == 0;
+        const u32 gup = g0 - d.w;
+        // root candidates of the three upward joins (outside the tile: the id of the pixel joined), then one select chain
+        const u32 a_up0 = top ? gup : pv0, a_ul0 = (top | (lane == 0)) ? gup - 1 : pvL, a_ru0 = top ? gup + 1 : pv1;
+        const u32 a_up1 = top ? gup + 1 : pv1, a_ul1 = top ? gup : pv0, a_ru1 = (top | (lane == 31)) ? gup + 2 : pvR;
+        u32 r0 = g0 | TAG, r1 = (g0 + 1) | TAG;
+        r0 = j0 == J_UP ? a_up0 : r0; r0 = j0 == J_UPLEFT ? a_ul0 : r0; r0 = j0 == J_RUP ? a_ru0 : r0;
+        r1 = j1 == J_UP ? a_up1 : r1; r1 = j1 == J_UPLEFT ? a_ul1 : r1; r1 = j1 == J_RUP ? a_ru1 : r1;
+        // LEFT joins: the chain from pixel 0 goes to pixel 1 of the lane to the left and on through all-LEFT lanes
+        const u32 mA = __ballot_sync(FULL, j0 == J_LEFT), mB = __ballot_sync(FULL, j1 == J_LEFT);
+        const u32 open = ~(mA & mB) & ((1u << lane) - 1u);  // lanes to the left where the chain stops
+        const int hl = open ? 31 - __clz((int)open) : 0;
+        const u32 h0 = __shfl_sync(FULL, r0, hl), h1 = __shfl_sync(FULL, r1, hl);
+        u32 head = ((mB >> hl) & 1u) ? h0 : h1;             // the head is pixel 1 of that lane unless that is itself a LEFT join
+        head = open ? head : g0 - 2u * (u32)lane - 1u;      // no such lane: the chain leaves the tile through its left edge
+        r0 = j0 == J_LEFT ? head : r0;
+        r1 = j1 == J_LEFT ? r0 : r1;
+        if (act) {
+            const u32 f0 = j0 | (m0 ? (u32)F_M : 0u) | (((j0 != J_NONE) & ((r0 & TAG) != 0u)) ? (u32)F_FINAL : 0u);
+            const u32 f1 = j1 | (m1 ? (u32)F_M : 0u) | (((j1 != J_NONE) & ((r1 & TAG) != 0u)) ? (u32)F_FINAL : 0u);
+            *reinterpret_cast<u16 *>(b.flags + g0) = (u16)(f0 | (f1 << 8));
+            *reinterpret_cast<uint2 *>(b.pc + g0) = make_uint2(j0 == J_NONE ? NONE : (r0 & ~TAG), j1 == J_NONE ? NONE : (r1 & ~TAG));
+            const bool n0 = (j0 == J_NEW) | (j0 == J_RES), n1 = (j1 == J_NEW) | (j1 == J_RES);
+            if (n0 | n1) {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (!(k ? n1 : n0)) continue;
+                    const u32 g = g0 + k, c = k ? c1 : c0;
+                    uint4 *pa = reinterpret_cast<uint4 *>(b.la + g), *ps = reinterpret_cast<uint4 *>(b.ls + g);
+                    pa[0] = make_uint4(g, NONE, NONE, NONE);         // ufp, best0, best1, parL
+                    pa[1] = make_uint4(1u, NONE, 0u, 0u);            // cnt, death, label, flabel
+                    ps[0] = make_uint4(c & 255u, (c >> 8) & 255u, (c >> 16) & 255u, c >> 24);     // ColorPolicy::stats
+                    ps[1] = make_uint4(1u, (k ? j1 : j0) == J_RES ? NONE : 0u, 0u, 0u);           // npx, pad[0..2]
+                    *reinterpret_cast<uint4 *>(b.lr + g) = make_uint4(gx0 + k, gx0 + k, gy, gy);      // minx, maxx, miny, maxy
+                }
+            }
+        }
+        ul0 = l0; u0 = c0; u1 = c1; qul0 = ql0; qu0 = q_0; qu1 = pol.t3 - p1; pv0 = r0; pv1 = r1;
+    }
+    if (err) atomicOr(&b.ctr->err, err);
+}
+
+// staging by plain loads (host simulator, and when the tensor map cannot be encoded)
+template <class P> __global__ void __launch_bounds__(RW_THREADS) k_edges_rows(Dims d, P pol, Bufs b, u32 tile0, u32 ntiles) {
+    VCB_SMEM(unsigned char, sm);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 t = blockIdx.x * RW_WARPS + warp;
+    if (t >= ntiles) return;
+    const u32 tiles_x = (d.w + TW - 1) / TW, tiles_y = (d.h + TH - 1) / TH;
+    const u32 tile = t + tile0;
+    const u32 img = tile / (tiles_x * tiles_y), tr = tile % (tiles_x * tiles_y);
+    const u32 x0 = (tr % tiles_x) * TW, y0 = (tr / tiles_x) * TH;
+    u32 *pix = reinterpret_cast<u32 *>(sm + warp * RW_BOX_PITCH);
+    const u32 base = img * d.n;
+    for (int idx = lane; idx < (TH + 1) * PW; idx += 32) {
+        const int ly = idx / PW, lx = idx % PW;
+        const i64 gy = (i64)y0 - 1 + ly, gx = (i64)x0 - XO + lx;
+        u32 v = 0;
+        if (gy >= 0 && gx >= 0 && gy < d.h && gx < d.w) v = pol.load(base + (u32)gy * d.w + (u32)gx);
+        pix[idx] = v;
+    }
+    __syncwarp();
+    edges_rows_body(d, pol, b, pix, img, x0, y0);
+}
+
+#ifndef VCB_HOSTSIM
+template <class P> __global__ void __launch_bounds__(RW_THREADS)
+k_edges_rows_tma(Dims d, P pol, Bufs b, const __grid_constant__ CUtensorMap tmap, u32 tile0, u32 ntiles) {
+    VCB_SMEM(unsigned char, sm);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 t = blockIdx.x * RW_WARPS + warp;
+    if (t >= ntiles) return;                              // whole warps leave: nothing below synchronises the block
+    const u32 tiles_x = (d.w + TW - 1) / TW, tiles_y = (d.h + TH - 1) / TH;
+    const u32 tile = t + tile0;
+    const u32 img = tile / (tiles_x * tiles_y), tr = tile % (tiles_x * tiles_y);
+    const u32 x0 = (tr % tiles_x) * TW, y0 = (tr / tiles_x) * TH;
+    u32 *pix = reinterpret_cast<u32 *>(sm + warp * RW_BOX_PITCH);
+    const u32 bar = smem_addr(sm + RW_WARPS * RW_BOX_PITCH + warp * 8);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((u32)K1_PIX_BYTES) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(smem_addr(pix)), "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"((int)x0 - XO), "r"((int)y0 - 1),
+            "r"((int)img), "r"(bar)
+            : "memory");
+    }
+    __syncwarp();
+    {
+        u32 done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                : "=r"(done)
+                : "r"(bar)
+                : "memory");
+        }
+    }
+    edges_rows_body(d, pol, b, pix, img, x0, y0);
+}
+#endif
 
 // --------------------------------------------------------------------------------------------------------------
 // K2: one thread per pixel.  pc[] -> provisional-cluster root (leaf id); candidate events.

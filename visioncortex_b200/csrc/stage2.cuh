@@ -21,6 +21,8 @@ struct S2Cfg {
     u64 help_min_px;   // rects at least this large are counted by the whole thread-block cluster
     int batch_rounds;  // parallel batch rounds on (default) / off
     int rect_perim;    // 1: perimeter by scanning the bounding rect (cluster helpers); 0: by the boundary-pixel lists
+    int prefetch;      // warm L2 with the image's records / adjacency / boundary lists when the fused kernel starts
+    u32 boff_min;      // batch rounds are given up for the rest of an epoch when they commit fewer pops per round than this
     int timing;        // VCB_S2_STATS: thread 0 accumulates the cycles spent in each phase of a pop / batch round (S2ImgState.tph)
 };
 
@@ -60,6 +62,7 @@ struct S2 {
     int idx_bits, area_bits;
     u32 *live;                     // fused kernel: per image, its live roots in index order (compacted as clusters merge)
     u32 key_cap;                   // fused kernel: capacity of the shared-memory key array
+    u32 state_cap, state_mask;     // fused kernel: slots per shared-memory state array; bit 0 fw, bit 1 col, bit 2 mnext + mtail
 };
 
 // Where the pop keys of the current epoch come from: the globally sorted (image | area - 2^epoch | index) array of the
@@ -68,8 +71,14 @@ struct S2Keys { const u64 *g; const u64 *s; u64 mask, add; };
 __device__ static __forceinline__ u64 s2_key(const S2Keys &k, u32 i) { return k.s ? k.s[i] : ((k.g[i] & k.mask) + k.add); }
 
 // phase timing (thread 0, after a barrier): the cycles since the previous tick are added to phase k
-enum { TP_SELECT = 0, TP_NBR, TP_DECIDE, TP_PERIM, TP_MERGE, TP_RELABEL, TP_BF, TP_BP, TP_BC, TP_BD, TP_BE, TP_COLLECT, TP_SORT, TP_OUT };
+enum { TP_SELECT = 0, TP_NBR, TP_DECIDE, TP_PERIM, TP_MERGE, TP_RELABEL, TP_BF, TP_BP, TP_BC, TP_BD, TP_BE, TP_COLLECT, TP_SORT, TP_GATHER, TP_DEG, TP_BP2 };
 #define S2_TICK(k) do { if (a.cfg.timing && threadIdx.x == 0) { const unsigned long long t_ = clock64(); sh->tph[k] += t_ - sh->tlast; sh->tlast = t_; } } while (0)
+
+// Per-slot state of the image being replayed (forwarding words, colours, member links) lives in the CTA's shared memory
+// when it fits (k_s2_run) and in global memory otherwise; both are reached through these accessors.  Writers and readers
+// of a word are always separated by a barrier (or are the same warp), so plain volatile accesses are enough.
+template <class T> __device__ static __forceinline__ T ldv(const T *p) { return *reinterpret_cast<const volatile T *>(p); }
+template <class T> __device__ static __forceinline__ void stv(T *p, T v) { *reinterpret_cast<volatile T *>(p) = v; }
 
 constexpr u32 FLAGBIT = 0x80000000u;
 constexpr u32 HOLLOWBIT = 0x40000000u;
@@ -79,7 +88,7 @@ constexpr u32 MPAR_MASK = 0x3fffffffu;
 // members of the absorbed cluster (the counterpart of the reference's relabel loop, builder.rs:527-529), so resolving a
 // stage-1 label is one load.  Bit 31 = "the hop into the root was a hollow deepen merge" (the pixel is in root.holes).
 __device__ static __forceinline__ u32 s2_find(const u32 *fw, u32 base, u32 s, u32 *flag) {
-    const u32 v = ldcg(&fw[base + s]);
+    const u32 v = ldv(&fw[base + s]);
     *flag = v >> 31;
     return v & ~FLAGBIT;
 }
@@ -213,8 +222,7 @@ constexpr u32 S2_MAPBYTES = 28672;
 constexpr int S2_NB = 32;                 // candidates per batch round (one warp each)
 constexpr int S2_CAPN = 32;               // neighbour roots kept per candidate
 constexpr int S2_CAPM = 32;               // member slots kept per candidate
-constexpr u64 S2_PERIM_WARP_MAX = 2048;   // rects up to this size are counted by the candidate's own warp
-enum : u32 { BF_SLOW = 1, BF_OUTONLY = 2, BF_ISOLATED = 4, BF_DEEPEN = 8, BF_HOLLOW = 16, BF_CONFLICT = 32, BF_MERGE = 64 };
+enum : u32 { BF_SLOW = 1, BF_OUTONLY = 2, BF_ISOLATED = 4, BF_DEEPEN = 8, BF_HOLLOW = 16, BF_CONFLICT = 32, BF_MERGE = 64, BF_NEEDP = 128 };
 
 struct S2Shared {
     unsigned long long best;
@@ -229,9 +237,12 @@ struct S2Shared {
     u32 bc[S2_NB], barea[S2_NB], btarget[S2_NB], bndist[S2_NB], bflags[S2_NB], bnewarea[S2_NB], bpos[S2_NB], bseg[S2_NB], bstamp[S2_NB], bnmem[S2_NB];
     u32 bnbr[S2_NB][S2_CAPN];
     u32 bmem[S2_NB][S2_CAPM];
+    u32 bb0[S2_NB][S2_CAPM], bpre[S2_NB][S2_CAPM + 1];   // perimeter work of a round: first boundary record / running count per member
+    u32 bperim[S2_NB], bpoff[S2_NB + 1];
     u32 nb, ncommit, mode, force_single, brounds, bdone, boff;
     u32 nlive, wsum[33];
     unsigned long long tph[16], tlast;
+    S2ImgState ist_l;                  // the image's counters while the fused kernel runs (written back at the end)
     alignas(16) u8 map[S2_MAPBYTES];   // last member: allocated only in the rect-scan perimeter mode
 };
 
@@ -245,30 +256,12 @@ struct S2Shared {
 // earlier in the batch, so the global (area, index) pop order is never violated.  Everything else of a pop (outputs in
 // candidate order, the running maximum area of builder.rs:446, list offsets) is a prefix scan over the batch.
 __device__ static __forceinline__ bool s2_in_cluster(const S2 &a, const u32 *l1, u32 base, u32 q, u32 c) {
-    return ldcg(&a.fw[base + __ldg(&l1[q])]) == c;
+    return ldv(&a.fw[base + __ldg(&l1[q])]) == c;
 }
 __device__ static __forceinline__ unsigned long long warp_min64(unsigned long long v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
     return v;
-}
-
-// Number of boundary records k0, k0 + stride, ... below `end` whose pixel has a 4-neighbour outside cluster c (or outside
-// the image).  Two records per step; their eight forwarding-word loads are independent and issued together.
-__device__ static __forceinline__ u32 s2_count_boundary(const S2 &a, u32 base, u32 c, u32 k0, u32 end, u32 stride) {
-    u32 cnt = 0;
-    for (u32 k = k0; k < end; k += 2 * stride) {
-        const bool two = k + stride < end;
-        const uint4 q0 = a.bnd_nb[k];
-        const uint4 q1 = two ? a.bnd_nb[k + stride] : q0;
-        const u32 nb[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-        u32 f[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = nb[j] == NONE ? NONE : ldcg(&a.fw[base + nb[j]]);
-        if (f[0] != c || f[1] != c || f[2] != c || f[3] != c) cnt++;
-        if (two && (f[4] != c || f[5] != c || f[6] != c || f[7] != c)) cnt++;
-    }
-    return cnt;
 }
 
 __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh, S2ImgState *ist, const S2Keys &keys, int epoch,
@@ -309,7 +302,7 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
                 const u32 slot = (u32)__popc(vmask & ((1u << lane) - 1u));
                 sh->bc[slot] = idx; sh->barea[slot] = ar; sh->bseg[slot] = lo + lane; sh->bkey[slot] = kb;
                 sh->bstamp[slot] = ist->stamp + 1 + slot; sh->bflags[slot] = 0; sh->bbest[slot] = ~0ull; sh->bndist[slot] = 0;
-                sh->btarget[slot] = NONE; sh->bnewarea[slot] = 0; sh->bnmem[slot] = 0;
+                sh->btarget[slot] = NONE; sh->bnewarea[slot] = 0; sh->bnmem[slot] = 0; sh->bperim[slot] = 0;
             }
             __syncwarp();
             if (lane == 0) { ist->stamp += nb; sh->lo = lo + npre; sh->nb = nb; sh->mode = nb ? 1u : 2u; }
@@ -331,7 +324,7 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
             // member slots of c (most candidates never absorbed anything: one load)
             if (lane == 0) {
                 u32 n = 0, m = c;
-                while (m != NONE && n < (u32)S2_CAPM) { sh->bmem[q][n++] = m; m = ldcg(&a.mnext[base + m]); }
+                while (m != NONE && n < (u32)S2_CAPM) { sh->bmem[q][n++] = m; m = ldv(&a.mnext[base + m]); }
                 sh->bnmem[q] = n;
                 if (m != NONE) sh->bnmem[q] = 0xffffffffu;
             }
@@ -339,13 +332,13 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
             const u32 nm = sh->bnmem[q];
             if (nm == 0xffffffffu) slow = true;
             else {
-                const u32 mycolor = ldcg(&a.col[base + c]);
+                const u32 mycolor = ldv(&a.col[base + c]);
                 // adjacency ranges and boundary ranges of all members at once (lane i = member i): one round trip
                 u32 e0 = 0, e1 = 0, b0 = 0, b1 = 0;
                 if (lane < nm) {
                     const u32 sl = sh->bmem[q][lane];
                     e0 = a.adj_off[base + sl]; e1 = a.adj_off[base + sl + 1];
-                    if (ldcg(&a.fw[base + sl]) == c) { b0 = a.bnd_off[base + sl]; b1 = a.bnd_off[base + sl + 1]; }   // hole members: no pixels of c
+                    if (ldv(&a.fw[base + sl]) == c) { b0 = a.bnd_off[base + sl]; b1 = a.bnd_off[base + sl + 1]; }   // hole members: no pixels of c
                 }
                 // distinct neighbour roots are collected in the candidate's own list (the global mark[] stamps cannot be
                 // shared by candidates that are scanned concurrently); no load depends on another inside this loop nest
@@ -383,41 +376,35 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
                     unsigned long long kbest = ~0ull;
                     if (lane < nd) {
                         const u32 v = sh->bnbr[q][lane];
-                        const i32 df = color_diff(mycolor, ldcg(&a.col[base + v]));
+                        const i32 df = color_diff(mycolor, ldv(&a.col[base + v]));
                         kbest = ((unsigned long long)((u32)df * 65535u + v) << 32) | v;
                     }
                     const unsigned long long best = warp_min64(kbest);
                     const u32 tg = (u32)best;
                     const i32 md = (i32)(((u32)(best >> 32) - tg) / 65535u);
-                    bool deepen = false;
+                    bool deepen = false, needp = false;
                     if (a.cfg.hier_max && a.cfg.good_min < (u64)area && (u64)area < a.cfg.good_max && md > a.cfg.deepen_diff) {
                         if (a.cfg.good_min == 0) deepen = true;
                         else {
-                            // perimeter from the members' boundary-pixel records (see s2_perimeter_bnd), by this warp
-                            u32 items = b1 - b0;
+                            // the perimeter (patch_good, runner.rs:131-146) is counted from the members' boundary-pixel records
+                            // by the whole block after this phase: one flat work list over all candidates of the round, so that a
+                            // long boundary does not hold up the round on a single warp
+                            const u32 len = b1 - b0;
+                            u32 inc = len;
 #pragma unroll
-                            for (int o2 = 16; o2 > 0; o2 >>= 1) items += __shfl_xor_sync(0xffffffffu, items, o2);
-                            if ((u64)items > S2_PERIM_WARP_MAX) slow = true;
-                            else {
-                                u32 cnt = 0;
-                                for (u32 i = 0; i < nm; ++i) {
-                                    const u32 mb0 = __shfl_sync(0xffffffffu, b0, (int)i), mb1 = __shfl_sync(0xffffffffu, b1, (int)i);
-                                    cnt += s2_count_boundary(a, base, c, mb0 + lane, mb1, 32u);
-                                }
-#pragma unroll
-                                for (int o2 = 16; o2 > 0; o2 >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o2);
-                                deepen = (u64)cnt < (u64)area;
-                            }
+                            for (int o2 = 1; o2 < 32; o2 <<= 1) { const u32 t2 = __shfl_up_sync(0xffffffffu, inc, o2); if ((int)lane >= o2) inc += t2; }
+                            sh->bb0[q][lane] = b0;
+                            sh->bpre[q][lane] = inc - len;
+                            if (lane == 31) sh->bpre[q][32] = inc;
+                            needp = true;
                         }
                     }
                     if (!slow) {
-                        flags = BF_MERGE | (deepen ? BF_DEEPEN : 0u) | (((u64)nd <= a.cfg.hollow_neighbours) ? BF_HOLLOW : 0u);
+                        flags = BF_MERGE | (deepen ? BF_DEEPEN : 0u) | (needp ? BF_NEEDP : 0u) | (((u64)nd <= a.cfg.hollow_neighbours) ? BF_HOLLOW : 0u);
                         if (lane == 0) {
                             sh->bndist[q] = nd;
                             sh->btarget[q] = tg;
                             sh->bnewarea[q] = a.rec[base + tg].indices_len + area;
-                            atomicMin(&a.tmin[base + tg], q);
-                            atomicMin(&a.tmin[base + c], q);
                         }
                     }
                 }
@@ -429,15 +416,51 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
     __threadfence_block();
     __syncthreads();
     S2_TICK(TP_BP);
-    // ---- C: conflicts with earlier candidates of the batch
+    // ---- P2: perimeters of the candidates that need one, block-wide over the flat list of their boundary records
+    if (warp == 0) {
+        const u32 v = (lane < nb && (sh->bflags[lane] & BF_NEEDP)) ? sh->bpre[lane][32] : 0u;
+        u32 inc = v;
+#pragma unroll
+        for (int o2 = 1; o2 < 32; o2 <<= 1) { const u32 t2 = __shfl_up_sync(0xffffffffu, inc, o2); if ((int)lane >= o2) inc += t2; }
+        sh->bpoff[lane] = inc - v;
+        if (lane == 31) sh->bpoff[32] = inc;
+    }
+    __syncthreads();
+    {
+        const u32 total = sh->bpoff[32];
+        if (total) {
+            for (u32 it = tid; it < total; it += blockDim.x) {
+                u32 lo = 0, hi = 32;                                 // candidate: last q with bpoff[q] <= it
+                while (hi - lo > 1) { const u32 mid = (lo + hi) / 2; if (sh->bpoff[mid] <= it) lo = mid; else hi = mid; }
+                const u32 q = lo, loc = it - sh->bpoff[q];
+                lo = 0; hi = 32;                                     // member: last i with bpre[q][i] <= loc
+                while (hi - lo > 1) { const u32 mid = (lo + hi) / 2; if (sh->bpre[q][mid] <= loc) lo = mid; else hi = mid; }
+                const uint4 nbq = a.bnd_nb[sh->bb0[q][lo] + (loc - sh->bpre[q][lo])];
+                const u32 c = sh->bc[q];
+                const u32 f0 = nbq.x == NONE ? NONE : ldv(&a.fw[base + nbq.x]), f1 = nbq.y == NONE ? NONE : ldv(&a.fw[base + nbq.y]);
+                const u32 f2 = nbq.z == NONE ? NONE : ldv(&a.fw[base + nbq.z]), f3 = nbq.w == NONE ? NONE : ldv(&a.fw[base + nbq.w]);
+                if (f0 != c || f1 != c || f2 != c || f3 != c) atomicAdd(&sh->bperim[q], 1u);
+            }
+            __syncthreads();
+            if (tid < nb && (sh->bflags[tid] & BF_NEEDP) && (u64)sh->bperim[tid] < (u64)sh->barea[tid]) sh->bflags[tid] |= BF_DEEPEN;
+            __syncthreads();
+        }
+    }
+    S2_TICK(TP_BP2);
+    // ---- C: conflicts with earlier candidates of the batch.  Candidate i modifies its own slot and its target; candidate q
+    // reads its own slot and its neighbour roots: lane k holds one of the slots q reads and compares it with the (at most
+    // 31) earlier merging candidates, all in shared memory
     for (u32 q = warp; q < nb; q += nwarps) {
         const u32 c = sh->bc[q];
-        u32 f = sh->bflags[q];
+        const u32 f = sh->bflags[q];
         bool conf = (f & BF_SLOW) != 0;                              // a slow candidate is handled alone by the single-pop path
-        if (lane == 0 && ldcg(&a.tmin[base + c]) < q) conf = true;
-        if (f & BF_MERGE) {
-            const u32 nd = sh->bndist[q];
-            for (u32 i = lane; i < nd; i += 32) if (ldcg(&a.tmin[base + sh->bnbr[q][i]]) < q) conf = true;
+        const u32 nd = (f & BF_MERGE) ? sh->bndist[q] : 0u;
+        for (u32 k0 = 0; k0 <= nd; k0 += 32) {
+            const u32 k = k0 + lane;
+            if (k > nd) continue;
+            const u32 rd = k == nd ? c : sh->bnbr[q][k];
+            for (u32 i = 0; i < q; ++i)
+                if ((sh->bflags[i] & BF_MERGE) && (sh->bc[i] == rd || sh->btarget[i] == rd)) conf = true;
         }
         if (__any_sync(0xffffffffu, conf) && lane == 0) sh->bflags[q] = f | BF_CONFLICT;
     }
@@ -486,7 +509,7 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
             // commits one or two pops and costs more than the single-pop path; give up for the rest of the epoch
             sh->brounds += 1; sh->bdone += J;
             ist->st_rounds += 1; ist->st_committed += J; ist->st_cands += nb;
-            if (sh->brounds >= 6 && sh->bdone < 6 * sh->brounds) sh->boff = 1;
+            if (sh->brounds >= 6 && sh->bdone < a.cfg.boff_min * sh->brounds) sh->boff = 1;
         }
     }
     __syncthreads();
@@ -545,12 +568,8 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
             newfw = __shfl_sync(0xffffffffu, newfw, 0);
             if (f & BF_MERGE) {
                 const u32 nm = sh->bnmem[q];
-                for (u32 i = lane; i < nm; i += 32) stcg(&a.fw[base + sh->bmem[q][i]], newfw);
+                for (u32 i = lane; i < nm; i += 32) stv(&a.fw[base + sh->bmem[q][i]], newfw);
             }
-        }
-        if (lane == 0) {
-            stcg(&a.tmin[base + c], NONE);
-            if (f & BF_MERGE) stcg(&a.tmin[base + sh->btarget[q]], NONE);
         }
     }
     __threadfence_block();
@@ -579,7 +598,7 @@ __device__ static __forceinline__ void s2_perimeter_bnd(const S2 &a, S2Shared *s
         __syncthreads();
         for (u32 i = tid; i < sh->nmem; i += T) {
             const u32 m = sh->mem[i];
-            const bool in = ldcg(&a.fw[base + m]) == c;              // root is c and the slot is not one of its holes
+            const bool in = ldv(&a.fw[base + m]) == c;              // root is c and the slot is not one of its holes
             sh->eoff[i] = a.bnd_off[base + m];
             sh->deg[i] = in ? a.bnd_off[base + m + 1] - a.bnd_off[base + m] : 0u;
         }
@@ -602,7 +621,7 @@ __device__ static __forceinline__ void s2_perimeter_bnd(const S2 &a, S2Shared *s
             const u32 nb[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
             u32 f[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = nb[j] == NONE ? NONE : ldcg(&a.fw[base + nb[j]]);
+            for (int j = 0; j < 8; ++j) f[j] = nb[j] == NONE ? NONE : ldv(&a.fw[base + nb[j]]);
             if (ok[0] && (f[0] != c || f[1] != c || f[2] != c || f[3] != c)) cntp++;
             if (ok[1] && (f[4] != c || f[5] != c || f[6] != c || f[7] != c)) cntp++;
         }
@@ -665,7 +684,7 @@ __device__ static __forceinline__ void s2_perimeter_rows(const S2 &a, S2Shared *
             }
             u32 fwv[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) fwv[u] = ok[u] ? ldcg(&a.fw[base + lab[u]]) : 0xffffffffu;
+            for (int u = 0; u < 4; ++u) fwv[u] = ok[u] ? ldv(&a.fw[base + lab[u]]) : 0xffffffffu;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const u32 q = q0 + u * S2_THREADS;
@@ -775,6 +794,7 @@ __device__ static __forceinline__ void s2_epoch_leader(const S2 &a, S2Shared *sh
                     sh->nmem = n; sh->more = m; sh->nchunks++;
                 }
                 __syncthreads();
+                S2_TICK(TP_GATHER);
                 // edge-parallel: prefix of the member degrees in shared memory, then one (member, edge) item per thread step
                 for (u32 i = tid; i < sh->nmem; i += S2_THREADS) {
                     const u32 s = sh->mem[i];
@@ -784,6 +804,7 @@ __device__ static __forceinline__ void s2_epoch_leader(const S2 &a, S2Shared *sh
                 __syncthreads();
                 if (tid == 0) { const u32 nm0 = sh->nmem; u32 acc = 0; for (u32 i = 0; i < nm0; ++i) { const u32 dg = sh->deg[i]; sh->deg[i] = acc; acc += dg; } sh->deg[nm0] = acc; }
                 __syncthreads();
+                S2_TICK(TP_DEG);
             }
             const u32 nm = sh->nmem;
             const u32 nitems = sh->deg[nm];
@@ -795,7 +816,7 @@ __device__ static __forceinline__ void s2_epoch_leader(const S2 &a, S2Shared *sh
                 const u32 o = s2_find(a.fw, base, a.adj[e], &fl);
                 if (o == c || o == 0) continue;                     // label 0 and self are not neighbours (cluster.rs:150)
                 if (atomicExch(&a.mark[base + o], stamp) != stamp) atomicAdd(&sh->ndist, 1u);
-                const i32 df = color_diff(mycolor, ldcg(&a.col[base + o]));
+                const i32 df = color_diff(mycolor, ldv(&a.col[base + o]));
                 const unsigned long long k = ((unsigned long long)((u32)df * 65535u + o) << 32) | o;
                 atomicMin(&sh->best, k);
             }
@@ -911,7 +932,7 @@ __device__ static __forceinline__ void s2_epoch_leader(const S2 &a, S2Shared *sh
             const u32 nf = sh->newfw;
             if (sh->nchunks <= 1) {
                 const u32 nm = sh->nmem;
-                for (u32 i = tid; i < nm; i += S2_THREADS) stcg(&a.fw[base + sh->mem[i]], nf);
+                for (u32 i = tid; i < nm; i += S2_THREADS) stv(&a.fw[base + sh->mem[i]], nf);
             } else {
                 // c's list is c -> ... -> old tail; it was appended to the target's list, so stop at the old tail of c
                 const u32 stop = a.mtail[base + target];              // == old tail of c
@@ -924,7 +945,7 @@ __device__ static __forceinline__ void s2_epoch_leader(const S2 &a, S2Shared *sh
                     }
                     __syncthreads();
                     const u32 nm = sh->nmem;
-                    for (u32 i = tid; i < nm; i += S2_THREADS) stcg(&a.fw[base + sh->mem[i]], nf);
+                    for (u32 i = tid; i < nm; i += S2_THREADS) stv(&a.fw[base + sh->mem[i]], nf);
                     __syncthreads();
                     const bool last = sh->more == NONE;
                     __syncthreads();
@@ -977,7 +998,7 @@ __device__ static __forceinline__ u32 s2_collect_epoch(const S2 &a, S2Shared *sh
         bool keep = false, take = false;
         if (i < nin) {
             s = initial ? i : a.live[base + i];
-            if (ldcg(&a.fw[base + s]) == s) {
+            if (ldv(&a.fw[base + s]) == s) {
                 area = a.rec[base + s].indices_len;
                 keep = area != 0;
                 take = keep && (31 - __clz((int)area)) == ep;
@@ -1026,15 +1047,51 @@ __device__ static __forceinline__ void s2_sort_keys(u64 *k, u32 n) {
     }
 }
 
-__global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_run(S2 a, int max_epoch, u32 G) {
+__global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_run(S2 a_in, int max_epoch, u32 G) {
     VCB_SMEM(S2Shared, sh);
+    S2 a = a_in;
     const u32 img = blockIdx.x / G, crank = blockIdx.x % G, base = a.slot_base[img];
     const u32 nslots = a.slot_base[img + 1] - base;
-    const u32 tid = threadIdx.x;
-    S2ImgState *ist = a.ist + img;
-    if (crank != 0) { s2_helper_loop(a, sh, ist, img, base, crank, G); return; }
-    // the key array follows the fixed part of the shared block (and the byte map of the rect-scan perimeter mode)
+    const u32 tid = threadIdx.x, T = blockDim.x;
+    S2ImgState *gist = a.ist + img;
+    if (crank != 0) { s2_helper_loop(a, sh, gist, img, base, crank, G); return; }
+    // the key array follows the fixed part of the shared block (and the byte map of the rect-scan perimeter mode), the state
+    // arrays follow the keys
     u64 *skeys = reinterpret_cast<u64 *>(reinterpret_cast<u8 *>(sh) + ((offsetof(S2Shared, map) + (a.cfg.rect_perim ? S2_MAPBYTES : 0u) + 15u) & ~(size_t)15));
+    u32 *sstate = reinterpret_cast<u32 *>(skeys + a.key_cap);
+    // State in shared memory: the replay is a chain of dependent lookups (adjacency entry -> forwarding word -> colour, member
+    // -> next member), so the words it chases are kept next to the SM.  Helper CTAs of a cluster (rect-scan mode) read the
+    // forwarding words too, so that mode keeps everything in global memory.
+    const u32 smask = (G == 1 && nslots <= a.state_cap) ? a.state_mask : 0u;
+    u32 *gfw = a.fw;
+    if (smask & 1u) { u32 *p = sstate; sstate += a.state_cap; for (u32 s = tid; s < nslots; s += T) p[s] = a.fw[base + s]; a.fw = p - base; }
+    if (smask & 2u) { u32 *p = sstate; sstate += a.state_cap; for (u32 s = tid; s < nslots; s += T) p[s] = a.col[base + s]; a.col = p - base; }
+    if (smask & 4u) {
+        u32 *p = sstate; sstate += a.state_cap; for (u32 s = tid; s < nslots; s += T) p[s] = a.mnext[base + s]; a.mnext = p - base;
+        u32 *q = sstate; sstate += a.state_cap; for (u32 s = tid; s < nslots; s += T) q[s] = a.mtail[base + s]; a.mtail = q - base;
+    }
+#ifndef VCB_HOSTSIM
+    if (a.cfg.prefetch) {
+        // one pass over everything the replay will chase: the first touch of a record is then an L2 hit, not a DRAM miss
+        auto pf = [&](const void *p0, size_t bytes) {
+            const char *p = reinterpret_cast<const char *>(p0);
+            for (size_t o = (size_t)tid * 128; o < bytes; o += (size_t)T * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+        };
+        pf(a.rec + base, (size_t)nslots * sizeof(vcb_cluster_rec));
+        pf(a.adj_off + base, (size_t)(nslots + 1) * 4);
+        pf(a.bnd_off + base, (size_t)(nslots + 1) * 4);
+        const u32 e0 = a.adj_off[base], e1 = a.adj_off[base + nslots];
+        pf(a.adj + e0, (size_t)(e1 - e0) * 4);
+        if (a.cfg.prefetch > 1) { const u32 b0 = a.bnd_off[base], b1 = a.bnd_off[base + nslots]; pf(a.bnd_nb + b0, (size_t)(b1 - b0) * 16); }
+        pf(a.mark + base, (size_t)nslots * 4);
+        if (!(smask & 1u)) pf(a.fw + base, (size_t)nslots * 4);
+        if (!(smask & 2u)) pf(a.col + base, (size_t)nslots * 4);
+        if (!(smask & 4u)) { pf(a.mnext + base, (size_t)nslots * 4); pf(a.mtail + base, (size_t)nslots * 4); }
+    }
+#endif
+    // the image's counters stay in shared memory while the kernel runs (helper CTAs exchange tasks through the global copy)
+    S2ImgState *ist = gist;
+    if (G == 1) { if (tid == 0) sh->ist_l = *gist; ist = &sh->ist_l; }
     if (tid == 0) { sh->nlive = nslots; for (int k = 0; k < 16; ++k) sh->tph[k] = 0; sh->tlast = clock64(); }
     __syncthreads();
     for (int ep = 0; ep <= max_epoch; ++ep) {
@@ -1052,8 +1109,12 @@ __global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_run(S2 a, int max_epoch, 
         s2_epoch_leader(a, sh, ist, keys, ep, img, base, a.over + base, G);
         __syncthreads();
     }
-    if (a.cfg.timing && tid == 0) for (int k = 0; k < 16; ++k) ist->tph[k] = sh->tph[k];
-    s2_release_helpers(ist, G);
+    if (smask & 1u) for (u32 s = tid; s < nslots; s += T) gfw[base + s] = a.fw[base + s];   // k_s2_labels, to_color_image read it
+    if (tid == 0) {
+        if (a.cfg.timing) for (int k = 0; k < 16; ++k) ist->tph[k] = sh->tph[k];
+        if (G == 1) *gist = sh->ist_l;
+    }
+    s2_release_helpers(gist, G);
 }
 
 // ------------------------------------------------------------------------------------------------- finalisation

@@ -481,6 +481,7 @@ inline int materialize_pool(vcb_ctx *c, const Dims &d, BatchResult *res, bool ke
 }
 
 // Stage 2 (builder.rs:379-539) on the records / labels produced by stage 1.  See stage2.cuh.
+inline int s2_set_count();
 inline S2Set *acquire_s2_set(vcb_ctx *c, bool async);
 inline int stage2_finish(vcb_ctx *c, BatchResult *res);
 
@@ -713,8 +714,12 @@ inline int stage2_finish(vcb_ctx *c, BatchResult *res) {
 }
 
 // next workspace set in round-robin order; a set still serving an earlier result is completed first
+inline int s2_set_count() {
+    static const int n = std::max(1, std::min((int)vcb_ctx::MAX_S2_SETS, std::getenv("VCB_S2_SETS") ? std::atoi(std::getenv("VCB_S2_SETS")) : 4));
+    return n;
+}
 inline S2Set *acquire_s2_set(vcb_ctx *c, bool async) {
-    const int nsets = std::max(1, std::min((int)vcb_ctx::MAX_S2_SETS, std::getenv("VCB_S2_SETS") ? std::atoi(std::getenv("VCB_S2_SETS")) : 4));
+    const int nsets = s2_set_count();
     int k = 0;                                                  // a run that does not overlap anything always takes set 0
     if (async) { k = c->s2_next % nsets; c->s2_next = (k + 1) % nsets; }
     if (!c->s2_sets[k]) c->s2_sets[k] = new (std::nothrow) S2Set();

@@ -239,6 +239,15 @@ struct S2Shared {
     u32 bmem[S2_NB][S2_CAPM];
     u32 bb0[S2_NB][S2_CAPM], bpre[S2_NB][S2_CAPM + 1];   // perimeter work of a round: first boundary record / running count per member
     u32 bperim[S2_NB], bpoff[S2_NB + 1];
+    u32 bcolor[S2_NB];                 // colour of the candidate when the round started
+    u32 frec[S2_NB][24];               // the candidate's own record (vcb_cluster_rec as 24 words) when the round started
+    u32 prec[S2_NB][24];               // the record of the target chosen on the state the round started from
+    u32 trec[S2_NB][24], tslot[S2_NB]; // records of the targets modified in this round (written back when the round ends)
+    u32 rtmp[32];
+    u32 bncol[S2_NB][S2_CAPN];         // colours of the candidate's neighbour roots when the round started
+    u32 mcs[S2_NB], mts[S2_NB];        // merges committed in this round, in order: absorbed root -> target
+    u32 tcol[S2_NB], tmtail[S2_NB];    // per cached target: current colour, current tail of its member list
+    u32 fmtail[S2_NB], pmtail[S2_NB];  // member-list tails of the candidate / of its S0 target when the round started
     u32 nb, ncommit, mode, force_single, brounds, bdone, boff;
     u32 nlive, wsum[33];
     unsigned long long tph[16], tlast;
@@ -333,6 +342,8 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
             if (nm == 0xffffffffu) slow = true;
             else {
                 const u32 mycolor = ldv(&a.col[base + c]);
+                if (lane < 24) sh->frec[q][lane] = ldv(reinterpret_cast<const u32 *>(a.rec + base + c) + lane);
+                if (lane == 0) { sh->bcolor[q] = mycolor; sh->fmtail[q] = ldv(&a.mtail[base + c]); }
                 // adjacency ranges and boundary ranges of all members at once (lane i = member i): one round trip
                 u32 e0 = 0, e1 = 0, b0 = 0, b1 = 0;
                 if (lane < nm) {
@@ -376,7 +387,9 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
                     unsigned long long kbest = ~0ull;
                     if (lane < nd) {
                         const u32 v = sh->bnbr[q][lane];
-                        const i32 df = color_diff(mycolor, ldv(&a.col[base + v]));
+                        const u32 vc = ldv(&a.col[base + v]);
+                        sh->bncol[q][lane] = vc;
+                        const i32 df = color_diff(mycolor, vc);
                         kbest = ((unsigned long long)((u32)df * 65535u + v) << 32) | v;
                     }
                     const unsigned long long best = warp_min64(kbest);
@@ -401,11 +414,8 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
                     }
                     if (!slow) {
                         flags = BF_MERGE | (deepen ? BF_DEEPEN : 0u) | (needp ? BF_NEEDP : 0u) | (((u64)nd <= a.cfg.hollow_neighbours) ? BF_HOLLOW : 0u);
-                        if (lane == 0) {
-                            sh->bndist[q] = nd;
-                            sh->btarget[q] = tg;
-                            sh->bnewarea[q] = a.rec[base + tg].indices_len + area;
-                        }
+                        if (lane == 0) { sh->bndist[q] = nd; sh->btarget[q] = tg; sh->pmtail[q] = ldv(&a.mtail[base + tg]); }
+                        if (lane < 24) sh->prec[q][lane] = ldv(reinterpret_cast<const u32 *>(a.rec + base + tg) + lane);
                     }
                 }
             }
@@ -447,129 +457,153 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
         }
     }
     S2_TICK(TP_BP2);
-    // ---- C: conflicts with earlier candidates of the batch.  Candidate i modifies its own slot and its target; candidate q
-    // reads its own slot and its neighbour roots: lane k holds one of the slots q reads and compares it with the (at most
-    // 31) earlier merging candidates, all in shared memory
-    for (u32 q = warp; q < nb; q += nwarps) {
-        const u32 c = sh->bc[q];
-        const u32 f = sh->bflags[q];
-        bool conf = (f & BF_SLOW) != 0;                              // a slow candidate is handled alone by the single-pop path
-        const u32 nd = (f & BF_MERGE) ? sh->bndist[q] : 0u;
-        for (u32 k0 = 0; k0 <= nd; k0 += 32) {
-            const u32 k = k0 + lane;
-            if (k > nd) continue;
-            const u32 rd = k == nd ? c : sh->bnbr[q][k];
-            for (u32 i = 0; i < q; ++i)
-                if ((sh->bflags[i] & BF_MERGE) && (sh->bc[i] == rd || sh->btarget[i] == rd)) conf = true;
-        }
-        if (__any_sync(0xffffffffu, conf) && lane == 0) sh->bflags[q] = f | BF_CONFLICT;
-    }
-    __syncthreads();
-    S2_TICK(TP_BC);
-    // ---- D: warp 0 decides the committed prefix, output positions and the running maximum area
+    // ---- R: warp 0 replays the candidates in pop order.  Each was evaluated on the state the round started from (S0); what
+    // an earlier candidate of the round changes is patched in before the next one decides, all of it in shared memory:
+    //   * a candidate that has meanwhile been the TARGET of a merge is no longer a pop (its area grew: the key is stale);
+    //   * its neighbour roots are re-resolved through the forwarding words (a root absorbed by an earlier merge of the round
+    //     carries all its slots along, so resolving the S0 roots again is exact), deduplicated, and the arg-min of
+    //     diff * 65535 + index (builder.rs:452-454) is taken over the colours as they are now;
+    //   * the perimeter of patch_good depends only on the candidate's own pixels, which no other pop touches;
+    //   * the records of the targets live in a small cache (trec) for the round, so a chain of merges into one big
+    //     neighbour costs shared-memory updates instead of dependent global round trips.
+    // The replay stops in front of a candidate that needs the single-pop path, whose key exceeds a key created earlier in the
+    // round (the new cluster pops first), or whose deepen test now needs a perimeter that was not counted.
     if (warp == 0) {
-        const bool in = lane < nb;
-        const u32 f = in ? sh->bflags[lane] : 0u;
-        const u32 stopm = __ballot_sync(0xffffffffu, in && (f & BF_CONFLICT));
-        u32 J = stopm ? (u32)(__ffs((int)stopm) - 1) : nb;
-        // pop order: a candidate whose key exceeds a key created earlier in the batch must wait
-        const unsigned long long key = in ? sh->bkey[lane] : 0ull;
-        unsigned long long nk = (in && (f & BF_MERGE)) ? (((unsigned long long)sh->bnewarea[lane] << a.idx_bits) | sh->btarget[lane]) : ~0ull;
-        unsigned long long inc = nk;                                  // inclusive prefix min
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o); if ((int)lane >= o && t < inc) inc = t; }
-        unsigned long long pm = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (lane == 0) pm = ~0ull;
-        const u32 violm = __ballot_sync(0xffffffffu, in && key > pm);
-        if (violm) { const u32 j2 = (u32)(__ffs((int)violm) - 1); if (j2 < J) J = j2; }
-        const bool committed = lane < J;
-        // running maximum area (builder.rs:446: `iteration == cluster_areas.len() - 1`)
-        const u32 na = (committed && (f & BF_MERGE)) ? sh->bnewarea[lane] : 0u;
-        u32 imax = na;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, imax, o); if ((int)lane >= o && t > imax) imax = t; }
-        u32 pmax = __shfl_up_sync(0xffffffffu, imax, 1);
-        if (lane == 0) pmax = 0;
-        const u32 maxbefore = pmax > ist->maxarea ? pmax : ist->maxarea;
-        const bool outp = committed && ((f & BF_OUTONLY) || (f & BF_DEEPEN) ||
-                                        ((f & BF_ISOLATED) && (sh->barea[lane] == maxbefore || a.cfg.can_discard)));
-        const u32 outm = __ballot_sync(0xffffffffu, outp);
-        if (in) sh->bpos[lane] = outp ? ist->nout + (u32)__popc(outm & ((1u << lane) - 1u)) : NONE;
-        const u32 allmax = __shfl_sync(0xffffffffu, imax, 31);
-        const u32 nmerge = (u32)__popc(__ballot_sync(0xffffffffu, committed && (f & BF_MERGE)));
-        __syncwarp();
-        if (lane == 0) {
-            ist->nout += (u32)__popc(outm);
-            if (allmax > ist->maxarea) ist->maxarea = allmax;
-            ist->nmerge += nmerge;
-            sh->ncommit = J;
-            if (J < nb) sh->lo = sh->bseg[J];                         // the rest is read again next round
-            if (J == 0) sh->force_single = 1;                         // head candidate needs the single-pop path
-            // adaptive: where neighbouring candidates keep conflicting (dense small clusters around one big cluster) a round
-            // commits one or two pops and costs more than the single-pop path; give up for the rest of the epoch
-            sh->brounds += 1; sh->bdone += J;
-            ist->st_rounds += 1; ist->st_committed += J; ist->st_cands += nb;
-            if (sh->brounds >= 6 && sh->bdone < a.cfg.boff_min * sh->brounds) sh->boff = 1;
-        }
-    }
-    __syncthreads();
-    S2_TICK(TP_BD);
-    // ---- E: commit the prefix in parallel (independent by construction), then clear the tmin marks
-    const u32 J = sh->ncommit;
-    for (u32 q = warp; q < nb; q += nwarps) {
-        const u32 c = sh->bc[q], f = sh->bflags[q], area = sh->barea[q];
-        if (q < J) {
-            u32 newfw = 0;
-            if (lane == 0) {
-                const u32 pos = sh->bpos[q];
-                if (pos != NONE) { a.outputs[base + pos] = c; if (a.outpos[base + c] == NONE) a.outpos[base + c] = pos; }
-                if (f & BF_MERGE) {
-                    const u32 target = sh->btarget[q];
-                    const bool deepen = (f & BF_DEEPEN) != 0, hollow = (f & BF_HOLLOW) != 0;
-                    vcb_cluster_rec *rf = a.rec + base + c, *rt_ = a.rec + base + target;
-                    if (!deepen) for (int k2 = 0; k2 < 5; ++k2) rt_->residue_sum[k2] += rf->residue_sum[k2];
-                    for (int k2 = 0; k2 < 5; ++k2) rt_->sum[k2] += rf->sum[k2];
-                    if (!(rf->rect[2] - rf->rect[0] == 0 && rf->rect[3] - rf->rect[1] == 0)) {
-                        if (rt_->rect[2] - rt_->rect[0] == 0 && rt_->rect[3] - rt_->rect[1] == 0) {
-                            for (int k2 = 0; k2 < 4; ++k2) rt_->rect[k2] = rf->rect[k2];
-                        } else {
-                            rt_->rect[0] = rt_->rect[0] < rf->rect[0] ? rt_->rect[0] : rf->rect[0];
-                            rt_->rect[1] = rt_->rect[1] < rf->rect[1] ? rt_->rect[1] : rf->rect[1];
-                            rt_->rect[2] = rt_->rect[2] > rf->rect[2] ? rt_->rect[2] : rf->rect[2];
-                            rt_->rect[3] = rt_->rect[3] > rf->rect[3] ? rt_->rect[3] : rf->rect[3];
-                        }
-                    }
-                    a.col[base + target] = avg_color(rt_->sum);
-                    a.childoff[base + c] = rt_->indices_len;
-                    a.holeoff[base + c] = rt_->holes_len;
-                    rt_->indices_len += area;
-                    if (!deepen) {
-                        for (int k2 = 0; k2 < 5; ++k2) rf->sum[k2] = 0;
-                        for (int k2 = 0; k2 < 4; ++k2) rf->rect[k2] = 0;
-                        rf->indices_len = 0;
-                    } else {
-                        if (hollow) { rt_->holes_len += area; rt_->num_holes += 1; }
-                        rf->merged_into = target;
-                        rt_->depth += 1;
-                    }
-                    newfw = target | ((deepen && hollow) ? FLAGBIT : 0u);
-                    a.mpar[base + c] = target | (deepen ? FLAGBIT : 0u) | ((deepen && hollow) ? HOLLOWBIT : 0u);
-                    a.mnext[base + a.mtail[base + target]] = c;
-                    a.mtail[base + target] = a.mtail[base + c];
-                    const u32 na = rt_->indices_len;
-                    if ((31 - __clz((int)na)) == epoch) {             // same epoch: must still be popped in order
-                        const unsigned long long k = ((unsigned long long)na << a.idx_bits) | target;
-                        const u32 slot = atomicAdd(&sh->nurg, 1u);
-                        if (slot < (u32)S2_URGENT) sh->urgent[slot] = k;
-                        else { atomicSub(&sh->nurg, 1u); over[atomicAdd(&ist->nover, 1u)] = k; }
+        const u32 FULLM = 0xffffffffu;
+        u32 J = nb, ntc = 0, nmerge = 0, nmc = 0;
+        u32 nout = ist->nout, maxarea = ist->maxarea;
+        unsigned long long nkmin = ~0ull;
+        for (u32 q = 0; q < nb; ++q) {
+            __syncwarp();
+            const u32 c = sh->bc[q], f = sh->bflags[q], area = sh->barea[q];
+            if (__any_sync(FULLM, lane < ntc && sh->tslot[lane] == c)) continue;      // absorbed something in this round: stale key
+            if (f & BF_SLOW) { J = q; break; }
+            if (sh->bkey[q] > nkmin) { J = q; break; }
+            if (f & BF_OUTONLY) {                                                     // builder.rs:429-432
+                if (lane == 0) { a.outputs[base + nout] = c; atomicMin(&a.outpos[base + c], nout); }
+                ++nout;
+                continue;
+            }
+            if (f & BF_ISOLATED) {                                                    // builder.rs:444-450
+                if (area == maxarea || a.cfg.can_discard) {
+                    if (lane == 0) { a.outputs[base + nout] = c; atomicMin(&a.outpos[base + c], nout); }
+                    ++nout;
+                }
+                continue;
+            }
+            const u32 nd0 = sh->bndist[q];
+            u32 v = NONE;
+            if (lane < nd0) v = sh->bnbr[q][lane];
+            for (u32 i = 0; i < nmc; ++i) if (v == sh->mcs[i]) v = sh->mts[i];       // in commit order: chains resolve in one pass
+            sh->rtmp[lane] = v;
+            __syncwarp();
+            bool lead = v != NONE;
+            for (u32 j = 0; j + 1 < nd0; ++j) if (j < lane && sh->rtmp[j] == v) lead = false;
+            const u32 nd = (u32)__popc(__ballot_sync(FULLM, lead));
+            unsigned long long kbest = ~0ull;
+            if (lead) {
+                // colour now: a root that took part in a merge of this round is a cached target; any other is as it was at S0
+                u32 vc = sh->bncol[q][lane];
+                for (u32 i = 0; i < ntc; ++i) if (sh->tslot[i] == v) vc = sh->tcol[i];
+                const i32 df = color_diff(sh->bcolor[q], vc);
+                kbest = ((unsigned long long)((u32)df * 65535u + v) << 32) | v;
+            }
+            const unsigned long long best = warp_min64(kbest);
+            const u32 tg = (u32)best;
+            const i32 md = (i32)(((u32)(best >> 32) - tg) / 65535u);
+            bool deepen = false;
+            if (a.cfg.hier_max && a.cfg.good_min < (u64)area && (u64)area < a.cfg.good_max && md > a.cfg.deepen_diff) {
+                if (a.cfg.good_min == 0) deepen = true;
+                else if (f & BF_NEEDP) deepen = (u64)sh->bperim[q] < (u64)area;
+                else { J = q; break; }
+            }
+            const bool hollow = (u64)nd <= a.cfg.hollow_neighbours;
+            if (deepen) {                                                             // builder.rs:463-465
+                if (lane == 0) { a.outputs[base + nout] = c; atomicMin(&a.outpos[base + c], nout); }
+                ++nout;
+            }
+            // the target's record: already cached (modified earlier in the round), the S0 copy read by the candidate's
+            // warp (the usual case: the choice did not change), or a fresh load
+            const u32 hitm = __ballot_sync(FULLM, lane < ntc && sh->tslot[lane] == tg);
+            u32 ti;
+            if (hitm) ti = (u32)__ffs((int)hitm) - 1u;
+            else {
+                ti = ntc++;
+                const bool predicted = sh->btarget[q] == tg;
+                if (lane == 0) { sh->tslot[ti] = tg; sh->tmtail[ti] = predicted ? sh->pmtail[q] : ldv(&a.mtail[base + tg]); }
+                if (lane < 24) sh->trec[ti][lane] = predicted ? sh->prec[q][lane] : ldv(reinterpret_cast<const u32 *>(a.rec + base + tg) + lane);
+                __syncwarp();
+            }
+            u32 *tw = sh->trec[ti];
+            const u32 *fr = sh->frec[q];
+            // merge_cluster_into (builder.rs:495-539) on the cached words: 0-4 sum, 5-9 residue_sum, 10-13 rect, 14 num_holes,
+            // 15 depth, 16 merged_into, 17 indices_len, 22 holes_len
+            if (lane < 5) {
+                if (!deepen) tw[5 + lane] += fr[5 + lane];
+                tw[lane] += fr[lane];
+            } else if (lane == 5) {
+                const i32 f0 = (i32)fr[10], f1 = (i32)fr[11], f2 = (i32)fr[12], f3 = (i32)fr[13];
+                if (!(f2 - f0 == 0 && f3 - f1 == 0)) {                                // bound.rs:204-219
+                    const i32 t0 = (i32)tw[10], t1 = (i32)tw[11], t2 = (i32)tw[12], t3 = (i32)tw[13];
+                    if (t2 - t0 == 0 && t3 - t1 == 0) { tw[10] = (u32)f0; tw[11] = (u32)f1; tw[12] = (u32)f2; tw[13] = (u32)f3; }
+                    else {
+                        tw[10] = (u32)(t0 < f0 ? t0 : f0); tw[11] = (u32)(t1 < f1 ? t1 : f1);
+                        tw[12] = (u32)(t2 > f2 ? t2 : f2); tw[13] = (u32)(t3 > f3 ? t3 : f3);
                     }
                 }
+            } else if (lane == 6) {
+                a.childoff[base + c] = tw[17];                                        // builder.rs:529: to.indices.append(from.indices)
+                a.holeoff[base + c] = tw[22];
+                tw[17] += area;
+                if (deepen) {
+                    if (hollow) { tw[22] += area; tw[14] += 1; }
+                    tw[15] += 1;
+                }
+                a.mpar[base + c] = tg | (deepen ? FLAGBIT : 0u) | ((deepen && hollow) ? HOLLOWBIT : 0u);
+            } else if (lane == 7) {
+                stv(&a.mnext[base + sh->tmtail[ti]], c);                              // the member lists are concatenated
+                sh->tmtail[ti] = sh->fmtail[q];
+                sh->mcs[nmc] = c; sh->mts[nmc] = tg;
+            } else if (lane >= 8 && lane < 18) {
+                // the absorbed cluster's own record (global): cleared unless it keeps its pixels as a deepened layer
+                u32 *rw = reinterpret_cast<u32 *>(a.rec + base + c);
+                const u32 k = lane - 8;                                               // 0-4 sum, 5-8 rect, 9 indices_len
+                if (!deepen) rw[k < 5 ? k : (k < 9 ? k + 5 : 17)] = 0u;
+                else if (k == 0) rw[16] = tg;
             }
-            newfw = __shfl_sync(0xffffffffu, newfw, 0);
-            if (f & BF_MERGE) {
-                const u32 nm = sh->bnmem[q];
-                for (u32 i = lane; i < nm; i += 32) stv(&a.fw[base + sh->bmem[q][i]], newfw);
+            __syncwarp();
+            {   // ColorSum::average of the target's new sum
+                u32 ch = 0;
+                if (lane < 4) ch = ((tw[lane] / tw[4]) & 255u) << (8 * lane);
+                ch |= __shfl_xor_sync(FULLM, ch, 1);
+                ch |= __shfl_xor_sync(FULLM, ch, 2);
+                if (lane == 0) { stv(&a.col[base + tg], ch); sh->tcol[ti] = ch; }
             }
+            ++nmc;
+            const u32 newfw = tg | ((deepen && hollow) ? FLAGBIT : 0u);
+            const u32 nm = sh->bnmem[q];
+            if (lane < nm) stv(&a.fw[base + sh->bmem[q][lane]], newfw);
+            const u32 na = tw[17];
+            if (na > maxarea) maxarea = na;
+            ++nmerge;
+            const unsigned long long nk = ((unsigned long long)na << a.idx_bits) | tg;
+            if (nk < nkmin) nkmin = nk;
+            if (lane == 0 && (31 - __clz((int)na)) == epoch) {                        // same epoch: must still be popped in order
+                if (sh->nurg < (u32)S2_URGENT) sh->urgent[sh->nurg++] = nk; else over[ist->nover++] = nk;
+            }
+        }
+        __syncwarp();
+        for (u32 e = 0; e < ntc; ++e) {
+            if (lane < 24) reinterpret_cast<u32 *>(a.rec + base + sh->tslot[e])[lane] = sh->trec[e][lane];
+            if (lane == 24) stv(&a.mtail[base + sh->tslot[e]], sh->tmtail[e]);
+        }
+        if (lane == 0) {
+            ist->nout = nout; ist->maxarea = maxarea; ist->nmerge += nmerge;
+            sh->ncommit = J;
+            if (J < nb) sh->lo = sh->bseg[J];                             // the rest is read again next round
+            if (J == 0) sh->force_single = 1;                             // head candidate needs the single-pop path
+            sh->brounds += 1; sh->bdone += J;
+            ist->st_rounds += 1; ist->st_committed += J; ist->st_cands += nb;
         }
     }
     __threadfence_block();

@@ -390,15 +390,24 @@ int vcb_runner_run_batch_host(vcb_ctx *c, const vcb_runner_config *cfg, const ui
     };
     upload(0);
     c->s2_overlap = cfg->hierarchical != 0 && nchunks > 1;
+    // The hierarchical stage of a sub-batch is a long latency-bound kernel on a side stream (S2Set): its results are fetched
+    // `depth` sub-batches later, after that many further stage-1 passes have been queued behind it, so neither the host nor
+    // the main stream ever waits for it.  Without a hierarchical stage the result is complete when run_color returns.
+    size_t depth = 1;
+    if (cfg->hierarchical != 0) {
+        depth = (size_t)std::max(1, s2_set_count() - 1);
+        if (const char *ev = getenv("VCB_HOST_DEPTH")) depth = (size_t)std::max(1, std::min(s2_set_count() - 1, atoi(ev)));
+    }
+    size_t next_dl = 0;
     for (size_t k = 0; k < nchunks && rc == VCB_OK; ++k) {
         const size_t cnt = std::min(per, n - k * per);
         if (k + 1 < nchunks) upload(k + 1);                     // the other input buffer: its last reader (chunk k-1) is finished
         rt::stream_wait(c->st, ev_in[k]);
         e = run_color(c, cfg, c->d_in[k & 1], width, height, cnt, false, false, keep[k], nullptr, nchunks > 1);
         if (e) { rc = e; break; }
-        if (k > 0) { e = download(k - 1); if (e) { rc = e; break; } }
+        if (k >= depth) { e = download(next_dl++); if (e) { rc = e; break; } }
     }
-    if (rc == VCB_OK && nchunks > 0) rc = download(nchunks - 1);
+    while (rc == VCB_OK && next_dl < nchunks) rc = download(next_dl++);
     c->s2_overlap = false;
     if (rt::stream_sync(c->st_d2h) != 0 || rt::stream_sync(c->st_h2d) != 0) rc = rc ? rc : VCB_ERR_CUDA;
     if (rc == VCB_OK) {

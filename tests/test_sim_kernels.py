@@ -131,6 +131,26 @@ def test_sim_hierarchical_and_banded(sim, oracle):
         assert_same_clusters(got2, ref, pools=False, ctx=f"banded {k}")
 
 
+def test_sim_rag_row_sweep_shapes(sim, oracle):
+    """k_rag_rows (widths that are a multiple of 4): one and several 128-column strips, partial strips, heights around the
+    32-row strip height, a batch of two images -- the hierarchical result depends on every adjacency / boundary record."""
+    from parity import random_colour_image
+    from visioncortex_b200.runtime import make_config
+
+    rng = np.random.default_rng(77)
+    for (w, h) in [(4, 1), (8, 33), (128, 5), (132, 31), (256, 3), (260, 34), (12, 65)]:
+        img = random_colour_image(rng, w, h)
+        cfg = make_config(hierarchical=0xFFFFFFFF, is_same_color_a=int(rng.choice([2, 4])), is_same_color_b=1, good_min_area=2)
+        ref = oracle.runner_run(img, cfg, pools=True, color_image=True)
+        got = sim.runner_run(img, cfg, pools=True, color_image=True)
+        assert_same_clusters(got, ref, pools=True, ctx=f"rag rows {w}x{h}")
+    imgs = [random_colour_image(rng, 136, 9) for _ in range(2)]
+    cfg = make_config(hierarchical=0xFFFFFFFF, is_same_color_a=4, is_same_color_b=1)
+    got = sim.runner_run_batch(imgs, cfg, pools=True)
+    for k, im in enumerate(imgs):
+        assert_same_clusters(got[k], oracle.runner_run(im, cfg, pools=True), pools=True, ctx=f"rag rows batch {k}")
+
+
 def test_sim_batch_matches_single(sim, oracle):
     """several images in one launch sequence: per-image slot ranges, list offsets and the fused NEW / leaf compaction
     across image boundaries (one image is keyed away completely and owns a single slot)."""

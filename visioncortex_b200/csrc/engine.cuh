@@ -66,6 +66,7 @@ struct vcb_ctx {
     int s2_next = 0;
     int coop_blocks = 0;              // occupancy of the cooperative spanning-forest kernel on this device
     bool s2_overlap = false;          // the current call overlaps stage 2 with the following device batches
+    bool s2_tail = false;             // ... and this is its last device batch: no stage-1 kernels follow on the main stream
 #ifndef VCB_HOSTSIM
     cudaEvent_t events[16] = {};
 #endif
@@ -370,7 +371,10 @@ inline int run_stage1(vcb_ctx *c, const Dims &d, const P &pol_in, u32 base, bool
                 const u32 p0 = multi ? ds.row_begin(k, d) * d.w : 0, p1 = multi ? ds.row_begin(k + 1, d) * d.w : d.N;
                 if (p1 <= p0) continue;
                 rt::set_device(ck->device);
-                rt::launch(ck->st, "k_labels", rt::SEQ, k_labels, dim3(grid_for(ck, p1 - p0, K8_THREADS, 16)), dim3(K8_THREADS), 0, d, b, res->labels, p0, p1);
+                if (d.w % 4 == 0)
+                    rt::launch(ck->st, "k_labels", rt::SEQ, k_labels4, dim3(grid_for(ck, (p1 - p0) / 4, K8_THREADS, 16)), dim3(K8_THREADS), 0, b, res->labels, p0 / 4, p1 / 4);
+                else
+                    rt::launch(ck->st, "k_labels", rt::SEQ, k_labels, dim3(grid_for(ck, p1 - p0, K8_THREADS, 16)), dim3(K8_THREADS), 0, d, b, res->labels, p0, p1);
             }
             if (multi) { const int e = sync_devices(ds); if (e) return e; }
         }
@@ -586,10 +590,17 @@ inline int stage2_launch(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg
     const int gs = grid_for(c, total, 256, 16), gp = grid_for(c, d.N, 256, 16);
     rt::launch(st, "k_s2_init_img", rt::SEQ, k_s2_init_img, dim3((d.nimg + 127) / 128), dim3(128), 0, a);
     rt::launch(st, "k_s2_init", rt::SEQ, k_s2_init, dim3(gs), dim3(256), 0, a);
-    rt::launch(st, "k_rag_count", rt::SEQ, k_rag<false>, dim3(gp), dim3(256), 0, a);
+    // widths that are a multiple of 4 (128-bit label loads): the row-sweep form; VCB_RAG_PIXEL keeps the per-pixel kernel
+    static const bool rag_pixel = std::getenv("VCB_RAG_PIXEL") != nullptr;
+    const bool rag_rows = !rag_pixel && d.w % 4 == 0 && ((uintptr_t)a.l1 & 15) == 0 && d.n % 4 == 0;
+    const u32 rag_sx = (d.w + 127) / 128, rag_sy = (d.h + RAG_ROWS - 1) / RAG_ROWS;
+    const u32 rag_grid = (u32)(((u64)rag_sx * rag_sy * d.nimg + 7) / 8);
+    if (rag_rows) rt::launch(st, "k_rag_count", rt::THR, k_rag_rows<false>, dim3(rag_grid), dim3(256), 0, a, rag_sx, rag_sy);
+    else rt::launch(st, "k_rag_count", rt::SEQ, k_rag<false>, dim3(gp), dim3(256), 0, a);
     prims::scan(st, "scan_deg", DegScan{a}, set->chunksum, total, c->sms * 8);
     prims::scan(st, "scan_deg", BndScan{a}, set->chunksum, total, c->sms * 8);
-    rt::launch(st, "k_rag_fill", rt::SEQ, k_rag<true>, dim3(gp), dim3(256), 0, a);
+    if (rag_rows) rt::launch(st, "k_rag_fill", rt::THR, k_rag_rows<true>, dim3(rag_grid), dim3(256), 0, a, rag_sx, rag_sy);
+    else rt::launch(st, "k_rag_fill", rt::SEQ, k_rag<true>, dim3(gp), dim3(256), 0, a);
     int max_epoch = 0;
     while ((2ull << max_epoch) <= (u64)d.n) ++max_epoch;
     // few images: fat CTAs (and, in the rect-scan perimeter mode, a thread-block cluster per image whose other CTAs help with
@@ -599,7 +610,11 @@ inline int stage2_launch(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg
     const u32 G = (d.nimg == 1 && a.cfg.rect_perim) ? 2u : 1u;
 #else
     int s2_threads = d.nimg * 8 <= (u32)c->sms ? 1024 : d.nimg * 2 <= (u32)c->sms ? 512 : 256;
-    if (const char *ev = std::getenv("VCB_S2_THREADS")) s2_threads = std::max(32, std::min(1024, std::atoi(ev) / 32 * 32));
+    // the last device batch of an overlapped call shares the SMs with nothing that follows: one fat CTA per SM (a round
+    // evaluates its 32 candidates in one pass of 32 warps instead of four passes of 8) shortens the tail of the call
+    static const int tail_threads = std::getenv("VCB_S2_TAIL_THREADS") ? std::atoi(std::getenv("VCB_S2_TAIL_THREADS")) : 1024;
+    if (c->s2_tail && d.nimg <= (u32)c->sms) s2_threads = std::max(s2_threads, std::max(32, std::min(1024, tail_threads / 32 * 32)));
+    else if (const char *ev = std::getenv("VCB_S2_THREADS")) s2_threads = std::max(32, std::min(1024, std::atoi(ev) / 32 * 32));
     u32 G = 1;
     static const u32 maxg = std::getenv("VCB_S2_MAXG") ? (u32)std::atoi(std::getenv("VCB_S2_MAXG")) : 8u;
     while (a.cfg.rect_perim && G < maxg && d.nimg * (G * 2) * 2 <= (u32)c->sms) G *= 2;   // helpers only serve the rect-scan perimeter
@@ -615,6 +630,8 @@ inline int stage2_launch(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg
         // per-slot state in shared memory (k_s2_run): as many of (fw, col, mnext + mtail) as fit for the largest image.  While
         // other device batches overlap this kernel, part of every SM's shared memory is left to their stage-1 kernels
         size_t budget = (c->s2_overlap ? 0u : 216u) * 1024u;               // overlapped batches: measured slower (stage-1 kernels starve for shared memory)
+        static const int tail_smem_kb = std::getenv("VCB_S2_TAIL_SMEM_KB") ? std::atoi(std::getenv("VCB_S2_TAIL_SMEM_KB")) : 0;
+        if (c->s2_tail) budget = (size_t)std::max(0, tail_smem_kb) * 1024u;
         if (const char *ev = std::getenv("VCB_S2_SMEM_KB")) budget = (size_t)std::max(0, std::atoi(ev)) * 1024u;
         const size_t used = smem_fixed + (size_t)key_cap * 8;
         const size_t avail = budget > used ? budget - used : 0;
@@ -646,7 +663,8 @@ inline int stage2_launch(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg
                            (const u64 *)(flipped ? c->sk1 : c->sk0), ep, G);
         }
     }
-    rt::launch(st, "k_s2_labels", rt::SEQ, k_s2_labels, dim3(gp), dim3(256), 0, a, res->labels);
+    if (d.n % 4 == 0) rt::launch(st, "k_s2_labels", rt::SEQ, k_s2_labels4, dim3(grid_for(c, d.N / 4, 256, 16)), dim3(256), 0, a, res->labels);
+    else rt::launch(st, "k_s2_labels", rt::SEQ, k_s2_labels, dim3(gp), dim3(256), 0, a, res->labels);
     // offsets of the per-slot lists after the merges
     prims::scan(st, "scan_off", OffScan{res->rec, res->d_slot_base, res->d_slot_img, total, nullptr}, set->chunksum, total, c->sms * 8);
     rt::launch(st, "k_off_rebase", rt::SEQ, k_off_rebase, dim3(gs), dim3(REC_THREADS), 0, res->rec, res->d_slot_base, res->d_slot_img, total);

@@ -1323,4 +1323,19 @@ __global__ void __launch_bounds__(K8_THREADS) k_labels(Dims d, Bufs b, u32 *labe
     }
 }
 
+// four pixels per thread (pixel counts and ranges that are multiples of 4): 128-bit loads / stores, one record lookup per
+// run of equal leaves
+__global__ void __launch_bounds__(K8_THREADS) k_labels4(Bufs b, u32 *labels, u32 grp_lo, u32 grp_hi) {
+    const u32 stride = gridDim.x * K8_THREADS;
+    for (u32 q = grp_lo + blockIdx.x * K8_THREADS + threadIdx.x; q < grp_hi; q += stride) {
+        const uint4 leaf = __ldg(reinterpret_cast<const uint4 *>(b.pc) + q);
+        uint4 o;
+        o.x = leaf.x == NONE ? 0u : b.la[leaf.x].flabel;
+        o.y = leaf.y == leaf.x ? o.x : (leaf.y == NONE ? 0u : b.la[leaf.y].flabel);
+        o.z = leaf.z == leaf.y ? o.y : (leaf.z == NONE ? 0u : b.la[leaf.z].flabel);
+        o.w = leaf.w == leaf.z ? o.z : (leaf.w == NONE ? 0u : b.la[leaf.w].flabel);
+        reinterpret_cast<uint4 *>(labels)[q] = o;
+    }
+}
+
 }  // namespace vcb

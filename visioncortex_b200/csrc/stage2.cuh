@@ -133,6 +133,75 @@ template <bool FILL> __global__ void __launch_bounds__(256) k_rag(S2 a) {
     }
 }
 
+// Row-sweep form of k_rag for widths that are a multiple of 4: one warp walks down a strip of 128 columns x RAG_ROWS rows
+// with the rows above / at / below the current one in registers (one 128-bit label load per four pixels, left and right
+// strip halos on lanes 0 / 31), so every label is loaded once instead of seven times, and a thread whose 4 x 3 window
+// holds a single label -- the interior of a cluster, most pixels -- does nothing else.  Emits exactly the items of k_rag.
+constexpr int RAG_ROWS = 32;
+template <bool FILL> __global__ void __launch_bounds__(256) k_rag_rows(S2 a, u32 strips_x, u32 strips_y) {
+    const Dims d = a.d;
+    const u32 lane = threadIdx.x & 31;
+    const u32 wid = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const u32 per_img = strips_x * strips_y;
+    if (wid >= per_img * d.nimg) return;
+    const u32 img = wid / per_img, rr = wid - img * per_img, sy = rr / strips_x, sx = rr - sy * strips_x;
+    const u32 base = a.slot_base[img];
+    const u32 *L = a.l1 + (size_t)img * d.n;
+    const u32 x0 = sx * 128 + lane * 4;
+    const bool act = x0 < d.w;
+    const bool halo_l = lane == 0 && sx > 0, halo_r = lane == 31 && x0 + 4 < d.w;
+    const u32 y0 = sy * RAG_ROWS, y1 = y0 + RAG_ROWS < d.h ? y0 + RAG_ROWS : d.h;
+    const uint4 none4 = make_uint4(NONE, NONE, NONE, NONE);
+    uint4 up = none4, cur = none4, dn = none4;
+    u32 upl = NONE, upr = NONE, curl = NONE, curr = NONE, dnl = NONE, dnr = NONE;
+    // rows outside the image read as NONE (y0 - 1 wraps to 0xffffffff when y0 == 0)
+#define RAG_LOAD(y, v, hl, hr) do { const u32 y_ = (y); v = none4; hl = NONE; hr = NONE; if (y_ < d.h) { const u32 *row_ = L + (size_t)y_ * d.w; \
+        if (act) v = __ldg(reinterpret_cast<const uint4 *>(row_ + x0)); if (halo_l) hl = __ldg(row_ + x0 - 1); if (halo_r) hr = __ldg(row_ + x0 + 4); } } while (0)
+    RAG_LOAD(y0 - 1, up, upl, upr);
+    (void)upl;
+    RAG_LOAD(y0, cur, curl, curr);
+    for (u32 y = y0; y < y1; ++y) {
+        RAG_LOAD(y + 1, dn, dnl, dnr);
+        u32 cl = __shfl_up_sync(0xffffffffu, cur.w, 1), cr = __shfl_down_sync(0xffffffffu, cur.x, 1);
+        u32 ur = __shfl_down_sync(0xffffffffu, up.x, 1), dl = __shfl_up_sync(0xffffffffu, dn.w, 1);
+        if (lane == 0) { cl = curl; dl = dnl; }
+        if (lane == 31) { cr = curr; ur = upr; }
+        const u32 la0 = cur.x;
+        const bool flat = cl == la0 && cur.y == la0 && cur.z == la0 && cur.w == la0 && cr == la0 && up.x == la0 && up.y == la0 &&
+                          up.z == la0 && up.w == la0 && dn.x == la0 && dn.y == la0 && dn.z == la0 && dn.w == la0;
+        if (act && !flat) {
+            const u32 c[6] = {cl, cur.x, cur.y, cur.z, cur.w, cr};
+            const u32 u[5] = {up.x, up.y, up.z, up.w, ur};
+            const u32 dd[5] = {dl, dn.x, dn.y, dn.z, dn.w};
+            // all positions are claimed first (independent atomics in flight together), the records are written afterwards
+            bool fb[4], fh[4], fv[4];
+            u32 pb[4], ph0[4], ph1[4], pv0[4], pv1[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const u32 la = c[i + 1], nl = c[i], nr = c[i + 2], nu = u[i], nd = dd[i + 1];
+                fb[i] = nl != la || nr != la || nu != la || nd != la;
+                fh[i] = nr != NONE && la != nr && !(u[i] == la && u[i + 1] == nr);
+                fv[i] = nd != NONE && la != nd && !(c[i] == la && dd[i] == nd);
+                if (fb[i]) pb[i] = atomicAdd(&a.bcur[base + la], 1u);
+                if (fh[i]) { ph0[i] = atomicAdd(&a.cursor[base + la], 1u); ph1[i] = atomicAdd(&a.cursor[base + nr], 1u); }
+                if (fv[i]) { pv0[i] = atomicAdd(&a.cursor[base + la], 1u); pv1[i] = atomicAdd(&a.cursor[base + nd], 1u); }
+            }
+            if (FILL) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const u32 la = c[i + 1], nl = c[i], nr = c[i + 2], nu = u[i], nd = dd[i + 1];
+                    if (fb[i]) a.bnd_nb[a.bnd_off[base + la] + pb[i]] = make_uint4(nl, nr, nu, nd);
+                    if (fh[i]) { a.adj[a.adj_off[base + la] + ph0[i]] = nr; a.adj[a.adj_off[base + nr] + ph1[i]] = la; }
+                    if (fv[i]) { a.adj[a.adj_off[base + la] + pv0[i]] = nd; a.adj[a.adj_off[base + nd] + pv1[i]] = la; }
+                }
+            }
+        }
+        up = cur; upl = curl; upr = curr;
+        cur = dn; curl = dnl; curr = dnr;
+    }
+#undef RAG_LOAD
+}
+
 struct BndScan {
     S2 a;
     __device__ u32 count() const { return a.total_slots; }
@@ -1158,6 +1227,21 @@ __global__ void __launch_bounds__(256) k_s2_labels(S2 a, u32 *labels) {
     for (u32 g = blockIdx.x * 256 + threadIdx.x; g < d.N; g += stride) {
         const u32 base = a.slot_base[g / d.n];
         labels[g] = a.fw[base + a.l1[g]] & ~FLAGBIT;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_s2_labels4(S2 a, u32 *labels) {
+    const Dims d = a.d;
+    const u32 stride = gridDim.x * 256, ngrp = d.N / 4, gpi = d.n / 4;      // d.n % 4 == 0: a group never straddles two images
+    for (u32 q = blockIdx.x * 256 + threadIdx.x; q < ngrp; q += stride) {
+        const u32 base = a.slot_base[q / gpi];
+        const uint4 l = __ldg(reinterpret_cast<const uint4 *>(a.l1) + q);
+        uint4 o;
+        o.x = a.fw[base + l.x] & ~FLAGBIT;
+        o.y = l.y == l.x ? o.x : (a.fw[base + l.y] & ~FLAGBIT);
+        o.z = l.z == l.y ? o.y : (a.fw[base + l.z] & ~FLAGBIT);
+        o.w = l.w == l.z ? o.z : (a.fw[base + l.w] & ~FLAGBIT);
+        reinterpret_cast<uint4 *>(labels)[q] = o;
     }
 }
 

@@ -180,7 +180,9 @@ int run_color_device(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba,
     for (size_t i0 = 0; i0 < nimg && !e; i0 += per_chunk) {
         const size_t cnt = nimg - i0 < per_chunk ? nimg - i0 : per_chunk;
         std::shared_ptr<BatchResult> br;
+        c->s2_tail = c->s2_overlap && i0 + per_chunk >= nimg;
         e = run_color(c, cfg, d_rgba + i0 * n64 * 4, w, h, cnt, c->opt_materialize != 0, retain, br, nullptr, nimg > per_chunk);
+        c->s2_tail = false;
         if (!e) brs.push_back(br);
     }
     for (auto &br : brs) {                                      // complete the hierarchical stages still in flight
@@ -403,7 +405,9 @@ int vcb_runner_run_batch_host(vcb_ctx *c, const vcb_runner_config *cfg, const ui
         const size_t cnt = std::min(per, n - k * per);
         if (k + 1 < nchunks) upload(k + 1);                     // the other input buffer: its last reader (chunk k-1) is finished
         rt::stream_wait(c->st, ev_in[k]);
+        c->s2_tail = c->s2_overlap && k + 1 == nchunks;
         e = run_color(c, cfg, c->d_in[k & 1], width, height, cnt, false, false, keep[k], nullptr, nchunks > 1);
+        c->s2_tail = false;
         if (e) { rc = e; break; }
         if (k >= depth) { e = download(next_dl++); if (e) { rc = e; break; } }
     }

@@ -16,13 +16,15 @@ class Fenced(Exception):
 
 
 def run_gpu(gpu, img, cfg, **kw):
-    """Two kinds of input are rejected with VCB_ERR_UNSUPPORTED instead of silently diverging, and random tests skip them:
-    an unclean key colour and, with diagonal = true, a slot that is freed and resurrected at the
-    same pixel (the reference then overwrites a live slot, builder.rs:347-348, and its labels disagree with its lists)."""
+    """Inputs that hit the reference's order-dependent quirks (an unclean key colour; with
+    diagonal = true a resurrected slot that is overwritten, builder.rs:347-348) are replayed by the device's sequential
+    resolver and are exact.  What is still rejected with VCB_ERR_UNSUPPORTED instead of silently diverging is the
+    HIERARCHICAL stage on such an input when labels and cluster membership disagree (KeyingAction::Discard with an unclean
+    key; the overwritten slot): random tests skip exactly those."""
     try:
         return gpu.runner_run(img, cfg, **kw)
     except VcbError as e:
-        if e.status == 3 and ("not clean" in str(e) or "resurrected at the same pixel" in str(e)):
+        if e.status == 3 and cfg.hierarchical != 0 and "hierarchical stage" in str(e):
             raise Fenced(str(e))
         raise
 
@@ -274,7 +276,7 @@ def test_diagonal_colour(gpu, oracle):
         try:
             got = run_gpu(gpu, img, cfg, pools=True, color_image=True)
         except Fenced as e:
-            assert "not clean" in str(e) or k % 4 != 3, str(e)
+            assert k % 3 == 1 and ("Discard" in str(e) or "overwritten" in str(e)), str(e)
             continue
         assert_same_clusters(got, ref, pools=True, ctx=f"diag case {k} {img.shape}")
         ok += 1
@@ -302,7 +304,7 @@ def test_diagonal_stale_upleft_resurrection(gpu, oracle):
         try:
             got = run_gpu(gpu, img, cfg, pools=True, color_image=True)
         except Fenced as e:
-            assert "resurrected at the same pixel" in str(e)
+            assert k % 3 != 0 and "overwritten" in str(e), str(e)
             fenced += 1
             continue
         lc = gpu.last_counters()
@@ -314,12 +316,46 @@ def test_diagonal_stale_upleft_resurrection(gpu, oracle):
     img = near_threshold_noise(np.random.default_rng(73), 1280, 720)
     cfg = make_config(hierarchical=0, diagonal=1, is_same_color_a=2, is_same_color_b=2)
     ref = oracle.runner_run(img, cfg, pools=False)
-    try:
-        got = run_gpu(gpu, img, cfg, pools=False)
-    except Fenced:
-        pytest.skip("720p stale-upleft case hits the freed-slot overwrite")
-    assert gpu.last_counters()["resurrected_leaves"] > 0
+    got = gpu.runner_run(img, cfg, pools=False)             # hierarchical == 0 is never rejected
+    lc = gpu.last_counters()
+    assert lc["resurrected_leaves"] > 0 or lc["sequential"] == 1
     assert_same_clusters(got, ref, pools=False, ctx="stale 720p")
+
+
+def test_unclean_key_sequential_resolver(gpu, oracle):
+    """A non-key pixel color_same to the key: label 0 joins, merges, is emptied and refilled.  The
+    batch is replayed on the device by the sequential resolver (csrc/sequential.cuh) -- labels, records, clusters_output,
+    the exact indices order, to_color_image, and the hierarchical stage under KeyingAction::Keep."""
+    from quirk_cases import unclean_key_case
+
+    rng = np.random.default_rng(607)
+    took = 0
+    for k in range(160):
+        hier = [0, 0, HM, 48][k % 4]
+        img, cfg = unclean_key_case(rng, max_side=[12, 40, 90][k % 3], hierarchical=hier, keying_action=(0 if hier else None))
+        ref = oracle.runner_run(img, cfg, pools=True, color_image=True)
+        got = gpu.runner_run(img, cfg, pools=True, color_image=True)
+        took += gpu.last_counters()["sequential"]
+        assert_same_clusters(got, ref, pools=True, ctx=f"unclean case {k} {img.shape}")
+    assert took >= 140, took
+    # a photo-like scene whose key is one of its own colours: 640 x 360, both keying actions, and a batch next to a clean image
+    img = synth.g2_scene(640, 360, seed=11)
+    key = tuple(int(v) for v in img[100, 200])
+    for action in (0, 1):
+        cfg = c2_config(640, 360, key_color=key, keying_action=action)
+        ref = oracle.runner_run(img, cfg, pools=True, color_image=True)
+        got = gpu.runner_run(img, cfg, pools=True, color_image=True)
+        assert gpu.last_counters()["sequential"] == 1
+        assert_same_clusters(got, ref, pools=True, ctx=f"unclean 640x360 action {action}")
+    other = synth.g2_scene(640, 360, seed=12)
+    got = gpu.runner_run_batch([other, img], cfg, pools=False)
+    for g, im in zip(got, [other, img]):
+        assert_same_clusters(g, oracle.runner_run(im, cfg, pools=False), pools=False, ctx="unclean batch")
+    # the combination that stays rejected: hierarchical stage + Discard + unclean key
+    cfg = make_config(hierarchical=HM, key_color=key, keying_action=1)
+    with pytest.raises(VcbError) as e:
+        gpu.runner_run(img, cfg, pools=False)
+    assert e.value.status == 3 and "Discard" in str(e.value)
 
 
 def test_c5_giant_image_single_gpu(gpu, oracle):

@@ -95,12 +95,34 @@ def test_sim_diagonal_stale_upleft(sim, oracle):
     assert done == 4
 
 
-def test_sim_unclean_key_is_fenced(sim):
-    from visioncortex_b200.runtime import make_config
+def test_sim_unclean_key_sequential_resolver(sim, oracle):
+    """a non-key pixel color_same to the key: label 0 joins, merges, is emptied and refilled.  The
+    device replays such a batch with the sequential resolver; only the hierarchical stage under KeyingAction::Discard stays
+    rejected (labels and cluster membership disagree there)."""
+    from quirk_cases import unclean_key_case
 
+    rng = np.random.default_rng(606)
+    took = 0
+    for k in range(40):
+        hier = [0, 0, 0xFFFFFFFF, 48][k % 4]
+        img, cfg = unclean_key_case(rng, max_side=16, hierarchical=hier, keying_action=(0 if hier else None))
+        ref = oracle.runner_run(img, cfg, pools=True, color_image=True)
+        got = sim.runner_run(img, cfg, pools=True, color_image=True)
+        took += sim.last_counters()["sequential"]
+        assert_same_clusters(got, ref, pools=True, ctx=f"unclean case {k}")
+    assert took >= 30
+    # a batch of two images, one of them unclean
+    img, cfg = unclean_key_case(rng, max_side=12, hierarchical=0, diagonal=0)
+    clean = img.copy()
+    clean[...] = (3, 3, 3, 255)
+    got = sim.runner_run_batch([clean, img], cfg, pools=True)
+    for g, im in zip(got, [clean, img]):
+        assert_same_clusters(g, oracle.runner_run(im, cfg, pools=True), pools=True, ctx="unclean batch")
+    # the one combination that stays rejected
     img = np.full((4, 4, 4), 100, dtype=np.uint8)
     img[1, 1] = (101, 100, 100, 255)
-    cfg = make_config(hierarchical=0, is_same_color_a=0, is_same_color_b=2, key_color=(101, 100, 100, 255))
+    from visioncortex_b200.runtime import make_config
+    cfg = make_config(hierarchical=0xFFFFFFFF, is_same_color_a=0, is_same_color_b=2, key_color=(101, 100, 100, 255), keying_action=1)
     with pytest.raises(VcbError) as e:
         sim.runner_run(img, cfg, pools=False)
     assert e.value.status == 3

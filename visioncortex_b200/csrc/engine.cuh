@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "stage2.cuh"
+#include "sequential.cuh"
 #include "vmm.h"
 
 namespace vcb {
@@ -65,6 +66,8 @@ struct vcb_ctx {
     vcb::S2Set *s2_sets[MAX_S2_SETS] = {};
     int s2_next = 0;
     int coop_blocks = 0;              // occupancy of the cooperative spanning-forest kernel on this device
+    vcb::SeqSlot *seq_slots = nullptr; // sequential resolver (sequential.cuh): n + 1 slot records per image, allocated on first use
+    size_t seq_cap = 0;
     bool s2_overlap = false;          // the current call overlaps stage 2 with the following device batches
     bool s2_tail = false;             // ... and this is its last device batch: no stage-1 kernels follow on the main stream
 #ifndef VCB_HOSTSIM
@@ -89,6 +92,7 @@ struct BatchResult {
     u32 *childoff = nullptr, *holeoff = nullptr, *off1 = nullptr, *hpool = nullptr, *pool1 = nullptr;
     std::vector<u32> hpool_base, pool1_base;
     bool hier = false;
+    u32 *seq_nx = nullptr;            // sequential resolver: list links per pixel (0xFFFFFFFE = in no cluster's list)
     u32 *pool = nullptr;              // concatenated Cluster.indices of all images (exact order), when materialised
     u8 *pixels = nullptr;             // retained copy of the input (Clusters.pixels, container.rs:8; take_image :34-40)
     const u8 *ext_pixels = nullptr;   // device-resident runs: the caller's own buffer instead of a copy
@@ -108,7 +112,7 @@ inline BatchResult::~BatchResult() {
     if (pending) stage2_finish(ctx, this);
     for (void *p : {(void *)labels, (void *)rec, (void *)outputs, (void *)d_slot_base, (void *)d_slot_img, (void *)pool,
                     (void *)pixels, (void *)labels1, (void *)mpar, (void *)outpos, (void *)childoff, (void *)holeoff, (void *)off1,
-                    (void *)hpool, (void *)pool1})
+                    (void *)hpool, (void *)pool1, (void *)seq_nx})
         rt::dev_free_async(ctx->st, p);
 }
 
@@ -396,13 +400,39 @@ inline int run_stage1(vcb_ctx *c, const Dims &d, const P &pol_in, u32 base, bool
     meta_out.assign(hm, hm + d.nimg);
     ctr_out = *hc;
     c->last_counters[0] = hc->ncand; c->last_counters[1] = hc->kt; c->last_counters[2] = hc->lt; c->last_counters[3] = hc->rounds;
-    c->last_counters[4] = hc->err; c->last_counters[5] = hc->nres; c->last_counters[6] = (u32)npass;
+    c->last_counters[4] = hc->err; c->last_counters[5] = hc->nres; c->last_counters[6] = (u32)npass; c->last_counters[7] = 0;
+    return VCB_OK;
+}
+
+// Sequential resolver (sequential.cuh) for a device batch whose parallel pass reported an order-dependent quirk: replays
+// builder.rs:273-364 literally, one image per CTA.  Fills res->labels and the slot counts; the slot records stay in
+// c->seq_slots for build_records / materialize_pool_seq.
+inline int run_stage1_seq(vcb_ctx *c, const Dims &d, const ColorPolicy &pol, int keep_key, BatchResult *res, std::vector<ImgMeta> &meta_out) {
+    rt::Stream &st = c->st;
+    Bufs b = c->b;
+    const size_t need = (size_t)d.N + d.nimg;
+    if (need > c->seq_cap) {
+        if (!grow(c->seq_slots, need + 16)) { c->seq_cap = 0; return VCB_ERR_NOMEM; }
+        c->seq_cap = need;
+    }
+    res->seq_nx = (u32 *)rt::dev_malloc_async(st, (size_t)d.N * sizeof(u32));
+    if (!res->seq_nx) return VCB_ERR_NOMEM;
+    rt::launch(st, "k_seq_stage1", rt::SEQ, k_seq_stage1, dim3(d.nimg), dim3(SEQ_THREADS), 0, d, pol, keep_key, res->labels, res->seq_nx, c->seq_slots, b.meta, 0u);
+    ImgMeta *hm = (ImgMeta *)c->h_pinned;
+    rt::copy_d2h(st, hm, b.meta, d.nimg * sizeof(ImgMeta));
+    if (rt::stream_sync(st) != 0 || st.last_error) {
+        c->err = st.last_error ? st.last_error_text : std::string("stream synchronize failed");
+        st.last_error = 0;
+        return VCB_ERR_CUDA;
+    }
+    meta_out.assign(hm, hm + d.nimg);
+    c->last_counters[7] = 1;
     return VCB_OK;
 }
 
 // records + (optionally) the hierarchical == 0 output list
 inline int build_records(vcb_ctx *c, const Dims &d, const std::vector<ImgMeta> &meta, BatchResult *res, bool flat_outputs,
-                         bool keep_key) {
+                         bool keep_key, bool seq = false) {
     rt::Stream &st = c->st;
     Bufs b = c->b;
     res->slot_base.assign(d.nimg + 1, 0);
@@ -418,9 +448,14 @@ inline int build_records(vcb_ctx *c, const Dims &d, const std::vector<ImgMeta> &
     const int g = grid_for(c, total, REC_THREADS, 16);
     rt::launch(st, "k_rec_init", rt::SEQ, k_rec_init, dim3(g), dim3(REC_THREADS), 0, res->rec, total);
     rt::launch(st, "k_slot_img", rt::SEQ, k_slot_img, dim3(d.nimg), dim3(REC_THREADS), 0, res->d_slot_img, res->d_slot_base, d.nimg);
-    rt::launch(st, "k_rec_accum", rt::SEQ, k_rec_accum, dim3(grid_for(c, d.N / 4, REC_THREADS, 16)), dim3(REC_THREADS), 0, d, b, res->rec, res->d_slot_base);
-    if (keep_key)
-        rt::launch(st, "k_rec_key", rt::SEQ, k_rec_key, dim3((d.nimg + 127) / 128), dim3(128), 0, d, b, res->rec, res->d_slot_base);
+    if (seq)           // the sequential resolver already holds the per-slot sums (clusters[0] included)
+        rt::launch(st, "k_seq_rec_fill", rt::SEQ, k_seq_rec_fill, dim3(grid_for(c, total, 256, 16)), dim3(256), 0, d, (const SeqSlot *)c->seq_slots,
+                   res->rec, (const u32 *)res->d_slot_base, 0u, d.nimg);
+    else {
+        rt::launch(st, "k_rec_accum", rt::SEQ, k_rec_accum, dim3(grid_for(c, d.N / 4, REC_THREADS, 16)), dim3(REC_THREADS), 0, d, b, res->rec, res->d_slot_base);
+        if (keep_key)
+            rt::launch(st, "k_rec_key", rt::SEQ, k_rec_key, dim3((d.nimg + 127) / 128), dim3(128), 0, d, b, res->rec, res->d_slot_base);
+    }
     u32 *d_live = c->d_small;            // nimg counters
     u32 *d_total = c->d_small + d.nimg + 1;
     int key_bits = 1, img_bits = 1;
@@ -481,6 +516,23 @@ inline int materialize_pool(vcb_ctx *c, const Dims &d, BatchResult *res, bool ke
     res->pool = (u32 *)rt::dev_malloc_async(st, (size_t)total * sizeof(u32) + 4);
     if (!res->pool) return VCB_ERR_NOMEM;
     rt::copy_d2d(st, res->pool, flipped ? c->sv1 : c->sv0, (size_t)total * sizeof(u32));
+    return VCB_OK;
+}
+
+// the same for a batch replayed by the sequential resolver: every slot's linked list, in order
+inline int materialize_pool_seq(vcb_ctx *c, const Dims &d, BatchResult *res) {
+    rt::Stream &st = c->st;
+    u32 *d_pool_base = c->d_small + 2 * (d.nimg + 2);
+    rt::launch(st, "k_pool_base", rt::SEQ, k_pool_base, dim3(1), dim3(32), 0, (const vcb_cluster_rec *)res->rec,
+               (const u32 *)res->d_slot_base, d.nimg, d_pool_base);
+    rt::copy_d2h(st, c->h_pinned, d_pool_base, (d.nimg + 1) * sizeof(u32));
+    if (rt::stream_sync(st) != 0 || st.last_error) { c->err = st.last_error_text; st.last_error = 0; return VCB_ERR_CUDA; }
+    res->pool_base.assign((u32 *)c->h_pinned, (u32 *)c->h_pinned + d.nimg + 1);
+    const u32 total = res->pool_base[d.nimg];
+    res->pool = (u32 *)rt::dev_malloc_async(st, (size_t)total * sizeof(u32) + 4);
+    if (!res->pool) return VCB_ERR_NOMEM;
+    rt::launch(st, "k_seq_pool", rt::SEQ, k_seq_pool, dim3(grid_for(c, res->total_slots, 256, 16)), dim3(256), 0, d, (const SeqSlot *)c->seq_slots,
+               (const u32 *)res->seq_nx, (const vcb_cluster_rec *)res->rec, (const u32 *)res->d_slot_base, (const u32 *)d_pool_base, res->pool, 0u, d.nimg);
     return VCB_OK;
 }
 
@@ -612,7 +664,7 @@ inline int stage2_launch(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg
     int s2_threads = d.nimg * 8 <= (u32)c->sms ? 1024 : d.nimg * 2 <= (u32)c->sms ? 512 : 256;
     // the last device batch of an overlapped call shares the SMs with nothing that follows: one fat CTA per SM (a round
     // evaluates its 32 candidates in one pass of 32 warps instead of four passes of 8) shortens the tail of the call
-    static const int tail_threads = std::getenv("VCB_S2_TAIL_THREADS") ? std::atoi(std::getenv("VCB_S2_TAIL_THREADS")) : 1024;
+    static const int tail_threads = std::getenv("VCB_S2_TAIL_THREADS") ? std::atoi(std::getenv("VCB_S2_TAIL_THREADS")) : 512;   // measured: 256 -> 76.9 ms, 512 -> 72.6 ms, 1024 -> 76.1 ms per 512-image step
     if (c->s2_tail && d.nimg <= (u32)c->sms) s2_threads = std::max(s2_threads, std::max(32, std::min(1024, tail_threads / 32 * 32)));
     else if (const char *ev = std::getenv("VCB_S2_THREADS")) s2_threads = std::max(32, std::min(1024, std::atoi(ev) / 32 * 32));
     u32 G = 1;

@@ -221,13 +221,14 @@ __global__ void __launch_bounds__(REC_THREADS) k_out_keys(const vcb_cluster_rec 
 
 // ClustersView::to_color_image for hierarchical == 0: every pixel belongs to exactly one output cluster (its own);
 // residue_color = residue_sum.average() (cluster.rs:42-44, color.rs:295-302).  Keyed pixels under Discard stay 0.
-__global__ void __launch_bounds__(REC_THREADS) k_color_image_flat(u32 n, const u32 *labels, const vcb_cluster_rec *rec, u32 *out) {
+// `nx` (sequential resolver only, else null): pixels marked 0xFFFFFFFE are in no cluster's list and stay unpainted.
+__global__ void __launch_bounds__(REC_THREADS) k_color_image_flat(u32 n, const u32 *labels, const vcb_cluster_rec *rec, u32 *out, const u32 *nx) {
     const u32 stride = gridDim.x * REC_THREADS;
     for (u32 g = blockIdx.x * REC_THREADS + threadIdx.x; g < n; g += stride) {
         const vcb_cluster_rec *r = rec + labels[g];
         u32 c = 0;
         const u32 cnt = r->residue_sum[4];
-        if (r->indices_len && cnt)
+        if (r->indices_len && cnt && !(nx && nx[g] == 0xFFFFFFFEu))
             c = ((r->residue_sum[0] / cnt) & 255u) | (((r->residue_sum[1] / cnt) & 255u) << 8) |
                 (((r->residue_sum[2] / cnt) & 255u) << 16) | (((r->residue_sum[3] / cnt) & 255u) << 24);
         out[g] = c;

@@ -125,13 +125,26 @@ int run_color(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w,
     std::vector<ImgMeta> meta;
     Counters ctr{};
     e = run_stage1(c, d, pol, 1u, want_pool, keep ? 1 : 0, br.get(), meta, ctr, ds);
-    if (e) return e;
-    if (ctr.err & 1u) return fail(c, VCB_ERR_UNSUPPORTED, "key colour is not clean: a non-key pixel is color_same to the key (order-dependent in the reference)");
-    if (ctr.err & 4u) return fail(c, VCB_ERR_UNSUPPORTED, "diagonal=true: a slot freed by builder.rs:315-317 is resurrected at the same pixel through the stale cluster_upleft label (builder.rs:301-305,341-343) and then overwritten (builder.rs:347-348)");
-    e = build_records(c, d, meta, br.get(), cfg->hierarchical == 0, keep);
+    // Order-dependent quirk inputs (unclean key colour; a resurrected slot that is overwritten; a stale-upleft fixpoint that
+    // does not settle) are replayed by the sequential resolver on the device (sequential.cuh) instead of being rejected.
+    bool seq = e == VCB_ERR_UNSUPPORTED;
+    if (e && !seq) return e;
+    if (!seq && (ctr.err & 5u)) seq = true;
+    if (seq) {
+        if (ds) return fail(c, VCB_ERR_UNSUPPORTED, "row-band mode: the input needs the sequential resolver (unclean key colour or an overwritten resurrected slot)");
+        // What stays rejected: the hierarchical stage on such an input when cluster_indices and Cluster.indices disagree --
+        // discarded key pixels (label 0 without being members of clusters[0], which now has members of its own) and the
+        // orphan left by an overwritten resurrected slot.  Stage 2 here is built on labels == membership.
+        if (cfg->hierarchical != 0 && (((ctr.err & 1u) && !keep) || (ctr.err & 4u) || e == VCB_ERR_UNSUPPORTED))
+            return fail(c, VCB_ERR_UNSUPPORTED, (ctr.err & 1u) ? "hierarchical stage with an unclean key colour under KeyingAction::Discard (label 0 is shared by members of clusters[0] and discarded pixels)"
+                                                               : "hierarchical stage after a resurrected slot was overwritten (builder.rs:347-348): a pixel's label and the cluster lists disagree");
+        e = run_stage1_seq(c, d, pol, keep ? 1 : 0, br.get(), meta);
+        if (e) return fail(c, e, "sequential resolver failed");
+    }
+    e = build_records(c, d, meta, br.get(), cfg->hierarchical == 0, keep, seq);
     if (e) return e;
     if (want_pool) {
-        e = materialize_pool(c, d, br.get(), keep);
+        e = seq ? materialize_pool_seq(c, d, br.get()) : materialize_pool(c, d, br.get(), keep);
         if (e) return fail(c, e, "materialising the indices pool failed");
     }
     if (cfg->hierarchical != 0) {
@@ -644,7 +657,8 @@ int vcb_clusters_to_color_image(const vcb_clusters *h, uint8_t *rgba_out) {
         rt::dev_free_async(c->st, slot_color);
     } else
     rt::launch(c->st, "k_color_image_flat", rt::SEQ, k_color_image_flat, dim3(grid_for(c, n, REC_THREADS, 16)), dim3(REC_THREADS), 0,
-               n, (const u32 *)(br->labels + (size_t)h->img * n), (const vcb_cluster_rec *)(br->rec + br->slot_base[h->img]), (u32 *)d);
+               n, (const u32 *)(br->labels + (size_t)h->img * n), (const vcb_cluster_rec *)(br->rec + br->slot_base[h->img]), (u32 *)d,
+               (const u32 *)(br->seq_nx ? br->seq_nx + (size_t)h->img * n : nullptr));
     rt::copy_d2h(c->st, rgba_out, d, (size_t)n * 4);
     return check_stream(c);
 }

@@ -140,7 +140,7 @@ class Context:
         arr = (C.c_uint32 * 8)()
         self.lib.check(self.lib.fn("ctx_last_counters")(self.handle, C.byref(arr)), self.handle)
         return {"candidate_events": arr[0], "new_events": arr[1], "leaves": arr[2], "msf_rounds": arr[3], "err": arr[4],
-                "resurrected_leaves": arr[5], "stage1_passes": arr[6]}
+                "resurrected_leaves": arr[5], "stage1_passes": arr[6], "sequential": arr[7]}
 
 
 def runner_run_banded(contexts, rgba: np.ndarray, cfg: RunnerConfigC, pools: bool = False, color_image: bool = False) -> dict:

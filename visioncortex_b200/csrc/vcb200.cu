@@ -99,7 +99,7 @@ int run_color(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w,
     if (!d_rgba) return fail(c, VCB_ERR_INVALID_ARG, "null image");
     rt::set_device(c->device);
     Dims d{w, h, (u32)n64, (u32)nimg, (u32)(n64 * nimg)};
-    e = ensure_workspace(c, d.N, d.nimg);
+    e = ensure_workspace(c, d.N, d.nimg, ds != nullptr);        // row-band mode: the per-pixel arrays are the striped ones (not ours to grow)
     if (e) return fail(c, e, "device out of memory (workspace)");
 
     auto br = std::make_shared<BatchResult>();

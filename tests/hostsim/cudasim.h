@@ -156,6 +156,16 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
     w.bar.arrive_and_wait();
     return r;
 }
+static inline unsigned __match_any_sync(unsigned, unsigned v) {
+    sim::WarpState &w = sim::warp();
+    w.slot[sim::tc.lane] = v;
+    w.bar.arrive_and_wait();
+    unsigned r = 0;
+    int n = (int)std::min<unsigned>(32, blockDim.x * blockDim.y * blockDim.z - sim::tc.warp * 32);
+    for (int i = 0; i < n; ++i) r |= (unsigned)((unsigned)w.slot[i] == v) << i;
+    w.bar.arrive_and_wait();
+    return r;
+}
 static inline int __any_sync(unsigned m, int p) { return __ballot_sync(m, p) != 0; }
 static inline int __all_sync(unsigned m, int p) {
     int n = (int)std::min<unsigned>(32, blockDim.x * blockDim.y * blockDim.z - sim::tc.warp * 32);

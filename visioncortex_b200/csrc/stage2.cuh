@@ -63,6 +63,7 @@ struct S2 {
     u32 *live;                     // fused kernel: per image, its live roots in index order (compacted as clusters merge)
     u32 key_cap;                   // fused kernel: capacity of the shared-memory key array
     u32 state_cap, state_mask;     // fused kernel: slots per shared-memory state array; bit 0 fw, bit 1 col, bit 2 mnext + mtail
+    u32 state_live;                // ... and which of them this CTA really holds in shared memory (set inside the kernel)
 };
 
 // Where the pop keys of the current epoch come from: the globally sorted (image | area - 2^epoch | index) array of the
@@ -312,10 +313,10 @@ struct S2Shared {
     u32 frec[S2_NB][24];               // the candidate's own record (vcb_cluster_rec as 24 words) when the round started
     u32 prec[S2_NB][24];               // the record of the target chosen on the state the round started from
     u32 trec[S2_NB][24], tslot[S2_NB]; // records of the targets modified in this round (written back when the round ends)
-    u32 rtmp[32];
     u32 bncol[S2_NB][S2_CAPN];         // colours of the candidate's neighbour roots when the round started
-    u32 mcs[S2_NB], mts[S2_NB];        // merges committed in this round, in order: absorbed root -> target
+    u32 mcs[S2_NB], mts[S2_NB];        // merges committed in this round, in order: absorbed root -> target (global-state mode)
     u32 tcol[S2_NB], tmtail[S2_NB];    // per cached target: current colour, current tail of its member list
+    u32 rtmp[32];
     u32 fmtail[S2_NB], pmtail[S2_NB];  // member-list tails of the candidate / of its S0 target when the round started
     u32 nb, ncommit, mode, force_single, brounds, bdone, boff;
     u32 nlive, wsum[33];
@@ -563,17 +564,23 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
             const u32 nd0 = sh->bndist[q];
             u32 v = NONE;
             if (lane < nd0) v = sh->bnbr[q][lane];
-            for (u32 i = 0; i < nmc; ++i) if (v == sh->mcs[i]) v = sh->mts[i];       // in commit order: chains resolve in one pass
-            sh->rtmp[lane] = v;
-            __syncwarp();
-            bool lead = v != NONE;
-            for (u32 j = 0; j + 1 < nd0; ++j) if (j < lane && sh->rtmp[j] == v) lead = false;
+            // A root absorbed earlier in this round: every commit rewrites the forwarding words of the absorbed members
+            // (the S0 root itself among them) before the next candidate is looked at, and a root that absorbed something
+            // is never absorbed in the same round (stale key, above), so one look at the forwarding word resolves it.
+            // With the per-slot state in shared memory that look-up (and the colour below) is a few cycles; with the state
+            // in global memory (overlapped device batches) the round's own small tables are cheaper than two L2 round trips.
+            const bool local = (a.state_live & 3u) == 3u;
+            if (local) { if (nmc && v != NONE) v = ldv(&a.fw[base + v]) & ~FLAGBIT; }
+            else for (u32 i = 0; i < nmc; ++i) if (v == sh->mcs[i]) v = sh->mts[i];
+            const u32 grp = __match_any_sync(FULLM, v);                               // lanes holding the same root
+            const bool lead = v != NONE && (u32)(__ffs((int)grp) - 1) == lane;
             const u32 nd = (u32)__popc(__ballot_sync(FULLM, lead));
             unsigned long long kbest = ~0ull;
             if (lead) {
-                // colour now: a root that took part in a merge of this round is a cached target; any other is as it was at S0
+                // colour now: col[] is kept current by every commit (below); a root no merge touched is as it was at S0
                 u32 vc = sh->bncol[q][lane];
-                for (u32 i = 0; i < ntc; ++i) if (sh->tslot[i] == v) vc = sh->tcol[i];
+                if (local) { if (nmc) vc = ldv(&a.col[base + v]); }
+                else for (u32 i = 0; i < ntc; ++i) if (sh->tslot[i] == v) vc = sh->tcol[i];
                 const i32 df = color_diff(sh->bcolor[q], vc);
                 kbest = ((unsigned long long)((u32)df * 65535u + v) << 32) | v;
             }
@@ -1167,6 +1174,7 @@ __global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_run(S2 a_in, int max_epoc
     // forwarding words too, so that mode keeps everything in global memory.
     const u32 smask = (G == 1 && nslots <= a.state_cap) ? a.state_mask : 0u;
     u32 *gfw = a.fw;
+    a.state_live = smask;
     if (smask & 1u) { u32 *p = sstate; sstate += a.state_cap; for (u32 s = tid; s < nslots; s += T) p[s] = a.fw[base + s]; a.fw = p - base; }
     if (smask & 2u) { u32 *p = sstate; sstate += a.state_cap; for (u32 s = tid; s < nslots; s += T) p[s] = a.col[base + s]; a.col = p - base; }
     if (smask & 4u) {

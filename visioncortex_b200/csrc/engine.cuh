@@ -620,6 +620,7 @@ inline int stage2_launch(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg
     a.cfg.batch_rounds = std::getenv("VCB_S2_NOBATCH") ? 0 : 1;
     a.cfg.rect_perim = std::getenv("VCB_S2_RECT_PERIM") ? 1 : 0;
     a.cfg.timing = std::getenv("VCB_S2_STATS") ? 1 : 0;
+    a.cfg.replay_loads = c->s2_overlap ? 0 : 1;
     a.cfg.prefetch = std::getenv("VCB_S2_PREFETCH") ? std::atoi(std::getenv("VCB_S2_PREFETCH")) : 0;
     a.cfg.boff_min = std::getenv("VCB_S2_BOFF") ? (u32)std::atoi(std::getenv("VCB_S2_BOFF")) : 6u;
 #ifdef VCB_HOSTSIM

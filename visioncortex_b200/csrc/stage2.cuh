@@ -23,6 +23,8 @@ struct S2Cfg {
     int rect_perim;    // 1: perimeter by scanning the bounding rect (cluster helpers); 0: by the boundary-pixel lists
     int prefetch;      // warm L2 with the image's records / adjacency / boundary lists when the fused kernel starts
     u32 boff_min;      // batch rounds are given up for the rest of an epoch when they commit fewer pops per round than this
+    int replay_loads;  // batch-round replay resolves roots / colours by loads even when the state is in global memory (runs that do not
+                       // share the device with other batches: measured C3 pass 2 4.31 -> 4.01 ms, C5 76.1 -> 72.9 ms; overlapped C4: slower)
     int timing;        // VCB_S2_STATS: thread 0 accumulates the cycles spent in each phase of a pop / batch round (S2ImgState.tph)
 };
 
@@ -301,6 +303,7 @@ struct S2Shared {
     u32 eoff[S2_MEMCHUNK];
     u32 deg[S2_MEMCHUNK + 1];
     u32 cur, area, ndist, perim, nmem, more, mycolor, nurg, lo, hi, stamp, nchunks, newfw, target, want_perim, deepen, single;
+    u32 wpos[32], full, pending, nslots;   // member scan (s2_scan_members): per-warp cursors over the image's slots
     i32 rect[4];
     // batch rounds
     unsigned long long bbest[S2_NB], bkey[S2_NB];
@@ -569,7 +572,7 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
             // is never absorbed in the same round (stale key, above), so one look at the forwarding word resolves it.
             // With the per-slot state in shared memory that look-up (and the colour below) is a few cycles; with the state
             // in global memory (overlapped device batches) the round's own small tables are cheaper than two L2 round trips.
-            const bool local = (a.state_live & 3u) == 3u;
+            const bool local = (a.state_live & 3u) == 3u || a.cfg.replay_loads;
             if (local) { if (nmc && v != NONE) v = ldv(&a.fw[base + v]) & ~FLAGBIT; }
             else for (u32 i = 0; i < nmc; ++i) if (v == sh->mcs[i]) v = sh->mts[i];
             const u32 grp = __match_any_sync(FULLM, v);                               // lanes holding the same root
@@ -688,6 +691,71 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
     return true;
 }
 
+// Members of cluster c WITHOUT walking its linked list: every slot points directly at its current cluster, so the members
+// are the slots whose forwarding word (hollow flag ignored) is c.  Each warp scans its own slice of the image's slots with
+// four coalesced loads in flight and appends the matches to sh->mem (order is irrelevant to every user: distinct-neighbour
+// sets, perimeters and relabelling); a chunk holds S2_MEMCHUNK members, the per-warp cursors carry on from there.  A list
+// walk costs one dependent load per member on a single thread -- 190 k cycles per pop of a region that has absorbed a few
+// hundred speckles (C5) -- the scan costs nslots / (32 * warps) steps.  Used when the image has few enough slots.
+constexpr u32 S2_SCAN_PER_THREAD = 256;     // scan when nslots <= this many slots per thread of the CTA
+__device__ static __forceinline__ bool s2_scan_mode(const S2Shared *sh) { return sh->nslots <= S2_SCAN_PER_THREAD * blockDim.x; }
+__device__ static __forceinline__ void s2_scan_begin(S2Shared *sh) {            // call by all threads; followed by a barrier in s2_scan_members
+    const u32 nw = blockDim.x >> 5;
+    const u32 slice = ((sh->nslots + nw - 1) / nw + 31u) & ~31u;
+    if (threadIdx.x < 32) sh->wpos[threadIdx.x] = threadIdx.x * slice;
+}
+// fills sh->mem / sh->nmem with the next chunk; sh->more = NONE when every slice is exhausted.  `exact`: only slots whose
+// word is exactly c (no hollow flag) -- the slots that hold pixels of c.
+__device__ static __forceinline__ void s2_scan_members(const S2 &a, S2Shared *sh, u32 base, u32 c, bool exact) {
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const u32 nslots = sh->nslots;
+    const u32 slice = ((nslots + nw - 1) / nw + 31u) & ~31u;
+    __syncthreads();
+    if (tid == 0) { sh->nmem = 0; sh->full = 0; sh->pending = 0; }
+    __syncthreads();
+    u32 pos = sh->wpos[warp];
+    const u32 end = (warp + 1) * slice < nslots ? (warp + 1) * slice : nslots;
+    bool stop = false;
+    // (the flag is read by one lane and broadcast: the loop condition must be uniform across the warp)
+    while (pos < end && !stop && !__shfl_sync(0xffffffffu, ldv(&sh->full), 0)) {
+        u32 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const u32 sl = pos + u * 32 + lane; v[u] = sl < end ? ldv(&a.fw[base + sl]) : NONE; }
+        u32 done = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (stop) break;
+            const u32 sl = pos + u * 32 + lane;
+            const bool match = sl < end && (exact ? v[u] == c : (v[u] & ~FLAGBIT) == c);
+            const u32 m = __ballot_sync(0xffffffffu, match);
+            if (m) {
+                const u32 cnt = (u32)__popc(m);
+                u32 k = 0;
+                if (lane == 0) {
+                    // reserve [k, k + cnt) only if it fits (compare-and-swap: an add that is taken back later would let
+                    // another warp's reservation land behind the hole)
+                    k = ldv(&sh->nmem);
+                    while (true) {
+                        if (k + cnt > (u32)S2_MEMCHUNK) { stv(&sh->full, 1u); k = NONE; break; }
+                        const u32 seen = atomicCAS(&sh->nmem, k, k + cnt);
+                        if (seen == k) break;
+                        k = seen;
+                    }
+                }
+                k = __shfl_sync(0xffffffffu, k, 0);
+                if (k == NONE) { stop = true; break; }
+                if (match) sh->mem[k + (u32)__popc(m & ((1u << lane) - 1u))] = sl;
+            }
+            done = (u32)u + 1;
+        }
+        pos += done * 32;
+    }
+    if (lane == 0) { sh->wpos[warp] = pos; if (pos < end) stv(&sh->pending, 1u); }
+    __syncthreads();
+    if (tid == 0) sh->more = sh->pending ? c : NONE;
+    __syncthreads();
+}
+
 // Perimeter of cluster c from the boundary-pixel lists of its member slots (block-parallel).  A pixel whose four
 // neighbours carry its own stage-1 label stays interior whatever merges happen, so only the stage-1 boundary pixels of the
 // members need to be looked at: the cost is the boundary length of the members, not the area of the bounding rect.
@@ -697,10 +765,13 @@ __device__ static __forceinline__ void s2_perimeter_bnd(const S2 &a, S2Shared *s
     const u32 tid = threadIdx.x, T = blockDim.x;
     const u32 *l1 = a.l1 + (size_t)img * d.n;
     u32 cntp = 0;
+    const bool scan = s2_scan_mode(sh) && sh->single == 0;     // a cluster that never absorbed anything is its own only member
     if (tid == 0) sh->more = c;
+    if (scan) s2_scan_begin(sh);
     __syncthreads();
     while (true) {
-        if (tid == 0) {
+        if (scan) s2_scan_members(a, sh, base, c, true);
+        else if (tid == 0) {
             u32 n = 0, m = sh->more;
             while (m != NONE && n < S2_MEMCHUNK) { sh->mem[n++] = m; m = a.mnext[base + m]; }
             sh->nmem = n; sh->more = m;
@@ -896,9 +967,12 @@ __device__ static __forceinline__ void s2_epoch_leader(const S2 &a, S2Shared *sh
         // ---- neighbours of c (cluster.rs:132-171) over the member lists and the static adjacency
         const u32 stamp = sh->stamp, mycolor = sh->mycolor;
         const bool single = sh->single != 0;                          // uniform (written before the barrier above)
+        const bool scan = !single && s2_scan_mode(sh);
+        if (scan) s2_scan_begin(sh);
         while (true) {
             if (!single) {
-                if (tid == 0) {
+                if (scan) { s2_scan_members(a, sh, base, c, false); if (tid == 0) sh->nchunks++; }
+                else if (tid == 0) {
                     u32 n = 0, m = sh->more;
                     while (m != NONE && n < S2_MEMCHUNK) { sh->mem[n++] = m; m = a.mnext[base + m]; }
                     sh->nmem = n; sh->more = m; sh->nchunks++;
@@ -1040,7 +1114,11 @@ __device__ static __forceinline__ void s2_epoch_leader(const S2 &a, S2Shared *sh
         // relabel: every member slot of c now resolves to the target (builder.rs:527-529)
         {
             const u32 nf = sh->newfw;
-            if (sh->nchunks <= 1) {
+            if (scan) {
+                // every slot that resolves to c (hole members included), wherever it sits in the list
+                const u32 ns = sh->nslots;
+                for (u32 sl = tid; sl < ns; sl += S2_THREADS) if ((ldv(&a.fw[base + sl]) & ~FLAGBIT) == c) stv(&a.fw[base + sl], nf);
+            } else if (sh->nchunks <= 1) {
                 const u32 nm = sh->nmem;
                 for (u32 i = tid; i < nm; i += S2_THREADS) stv(&a.fw[base + sh->mem[i]], nf);
             } else {
@@ -1086,6 +1164,7 @@ __global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_epoch(S2 a, const u64 *gk
         while (l2 < hi) { const u32 mid = (l2 + hi) / 2; if ((u32)(gkeys[mid] >> kshift) <= img) l2 = mid + 1; else hi = mid; }
         sh->hi = l2;
         sh->nurg = 0; sh->force_single = 0; sh->mode = 0; sh->brounds = 0; sh->bdone = 0; sh->boff = 0;
+        sh->nslots = a.slot_base[img + 1] - base;
     }
     __syncthreads();
     const S2Keys keys{gkeys, nullptr, (1ull << kshift) - 1ull, (u64)(1u << epoch) << a.idx_bits};
@@ -1203,7 +1282,7 @@ __global__ void __launch_bounds__(S2_MAX_THREADS) k_s2_run(S2 a_in, int max_epoc
     // the image's counters stay in shared memory while the kernel runs (helper CTAs exchange tasks through the global copy)
     S2ImgState *ist = gist;
     if (G == 1) { if (tid == 0) sh->ist_l = *gist; ist = &sh->ist_l; }
-    if (tid == 0) { sh->nlive = nslots; for (int k = 0; k < 16; ++k) sh->tph[k] = 0; sh->tlast = clock64(); }
+    if (tid == 0) { sh->nlive = nslots; sh->nslots = nslots; for (int k = 0; k < 16; ++k) sh->tph[k] = 0; sh->tlast = clock64(); }
     __syncthreads();
     for (int ep = 0; ep <= max_epoch; ++ep) {
         // the roots still alive bound the number of keys: shared memory when they fit, the image's global key range otherwise

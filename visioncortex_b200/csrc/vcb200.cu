@@ -351,8 +351,13 @@ int vcb_runner_run_batch_host(vcb_ctx *c, const vcb_runner_config *cfg, const ui
         if (rt::stream_create(c->st_h2d) != 0 || rt::stream_create(c->st_d2h) != 0) return fail(c, VCB_ERR_CUDA, "stream creation failed");
         c->pipe_ready = true;
     }
-    // sub-batches: 8 per call (VCB_HOST_CHUNKS) so that the copies overlap the compute, at most MAX_CHUNK_PX pixels each
+    // sub-batches so that the copies overlap the compute, at most MAX_CHUNK_PX pixels each.  Without a hierarchical stage: 8 per
+    // call.  With one, the download of a sub-batch can only start once its latency-bound stage 2 has finished, `depth`
+    // sub-batches later: small sub-batches start the 5.5 GB of downloads early, but `depth` of them must still cover one
+    // stage-2 latency -- about 40 Mpixel each (19 x 1080p) measured best (512 x 1080p: 8 / 16 / 32 / 48 / 64 sub-batches ->
+    // 6.6 / 7.2 / 7.4 / 6.2 / 4.9 Gpix/s end to end).  VCB_HOST_CHUNKS overrides the count.
     u64 want_chunks = 8;
+    if (cfg->hierarchical != 0) want_chunks = std::max<u64>(1, ((u64)n * npx + (40ull << 20) - 1) / (40ull << 20));
     if (const char *ev = getenv("VCB_HOST_CHUNKS")) want_chunks = std::max<u64>(1, (u64)atoll(ev));
     size_t per = (size_t)std::max<u64>(1, std::min<u64>((n + want_chunks - 1) / want_chunks, MAX_CHUNK_PX / npx));
     const size_t bytes_img = (size_t)npx * 4;

@@ -31,7 +31,8 @@ typedef enum vcb_status {
     VCB_ERR_UNSUPPORTED = 3,     /* hierarchical stage on an order-dependent quirk input whose labels and cluster lists disagree
                                     (DESIGN.md section 1); every other quirk input is replayed exactly by the sequential resolver */
     VCB_ERR_CUDA = 4,
-    VCB_ERR_NCCL = 5,
+    VCB_ERR_NCCL = 5,            /* reserved, never returned: no path makes an NCCL call (the row-band exchange is in-kernel peer
+                                    memory traffic; batches shard without a collective) -- kept so the numbering stays stable */
     VCB_ERR_NOMEM = 6
 } vcb_status;
 
@@ -163,6 +164,19 @@ int  vcb_clusters_indices_pool(const vcb_clusters *c, uint32_t *out /* indices_t
 int  vcb_clusters_holes_pool(const vcb_clusters *c, uint32_t *out /* holes_total */);
 /* ClustersView::to_color_image (color_clusters/container.rs:104-116) */
 int  vcb_clusters_to_color_image(const vcb_clusters *c, uint8_t *rgba_out /* width*height*4 */);
+/* Device-resident Cluster queries: computed on the GPU from what the result keeps in HBM
+ * (stage-1 / final labels, the stage-2 merge forest, the records); no indices / holes pool is built or copied.
+ *   perimeters : Cluster::perimeter (color_clusters/cluster.rs:46-48 -> shape/geometry.rs:52-75) of EVERY cluster of the image in one
+ *                pass; out[slot] for slot < num_slots, 0 for clusters that hold no pixels
+ *   neighbours : Cluster::neighbours (cluster.rs:132-165): sorted indices of the clusters adjacent to `slot`; *count = length
+ *                (VCB_ERR_NOMEM with *count set if cap is too small; VCB_ERR_INVALID_ARG for a cluster without pixels, where
+ *                the reference unwraps indices.first())
+ *   to_image   : Cluster::to_image_with_hole(parent.width, hole) (cluster.rs:60-80) as BitVec storage of the rect-sized image
+ *                (u32 blocks, pixel i at block i/32 bit i%32, image/format.rs:10-14); rect_out = the cluster's BoundingRect
+ * Results of the sequential resolver (unclean key colours) return VCB_ERR_UNSUPPORTED here: use the pools. */
+int  vcb_clusters_perimeters(const vcb_clusters *c, uint32_t *out /* num_slots */);
+int  vcb_clusters_neighbours(const vcb_clusters *c, uint32_t slot, uint32_t *out, size_t cap, size_t *count);
+int  vcb_clusters_to_image(const vcb_clusters *c, uint32_t slot, int hole, uint32_t *bits_out, size_t cap_words, int32_t rect_out[4]);
 /* device pointer of the label map (width*height u32) for callers that stay on the GPU; NULL if released */
 const uint32_t *vcb_clusters_device_labels(const vcb_clusters *c);
 /* Clusters::take_image (container.rs:34-40): the retained RGBA8 input, copied to the caller */

@@ -88,6 +88,10 @@ extern "C" {
     pub fn vcb_clusters_indices_pool(c: *const vcb_clusters, out: *mut u32) -> c_int;
     pub fn vcb_clusters_holes_pool(c: *const vcb_clusters, out: *mut u32) -> c_int;
     pub fn vcb_clusters_free(c: *mut vcb_clusters);
+    // device-resident Cluster queries (include/vcb200.h): no pools are built or copied
+    pub fn vcb_clusters_perimeters(c: *const vcb_clusters, out: *mut u32) -> c_int;
+    pub fn vcb_clusters_neighbours(c: *const vcb_clusters, slot: u32, out: *mut u32, cap: usize, count: *mut usize) -> c_int;
+    pub fn vcb_clusters_to_image(c: *const vcb_clusters, slot: u32, hole: c_int, bits_out: *mut u32, cap_words: usize, rect_out: *mut i32) -> c_int;
     pub fn vcb_binary_to_clusters(ctx: *mut vcb_ctx, bits: *const u32, width: u32, height: u32, diagonal: c_int,
                                   out: *mut *mut vcb_bin_clusters) -> c_int;
     pub fn vcb_bin_clusters_info_get(c: *const vcb_bin_clusters, info: *mut vcb_bin_clusters_info) -> c_int;

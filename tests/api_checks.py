@@ -48,6 +48,20 @@ def check_runner_api(ctx, img: np.ndarray, **kw):
         im = got.to_image(view)
         assert (im.width, im.height) == (bw, bh) and bytes(im.pixels.astype(np.uint8)) == bytes(bits)
         assert got.perimeter(view) == R.image_boundary_count(bits, bw, bh)
+    # the same queries computed on the device from labels + merge forest + records (no pools): every cluster that holds pixels
+    if w * h:
+        perims = clusters.device_perimeters()
+        for idx, want in enumerate(ref.clusters):
+            if want.area() == 0:
+                assert perims[idx] == 0
+                continue
+            bits, bw, bh = R.to_image_with_hole(want, w, True)
+            assert int(perims[idx]) == R.image_boundary_count(bits, bw, bh), idx
+            assert clusters.device_neighbours(idx) == ref.neighbours_internal(want), idx
+            for hole in (True, False):
+                bits, bw, bh = R.to_image_with_hole(want, w, hole)
+                im = clusters.device_to_image(idx, hole)
+                assert (im.width, im.height) == (bw, bh) and bytes(im.pixels.astype(np.uint8)) == bytes(bits), (idx, hole)
     if w * h:
         assert view.get_cluster_at(0) == ref.cluster_indices[0]
         assert view.get_cluster_at_point(api.PointI32(w - 1, h - 1)) == ref.cluster_indices[-1]

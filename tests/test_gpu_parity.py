@@ -232,6 +232,36 @@ def test_c4_default_config_1080p(gpu, oracle):
     assert_same_clusters(got, ref, pools=False, ctx="C4 image 0")
 
 
+def test_device_resident_queries_1080p(gpu):
+    """SURVEY section 8(f) row f4: Cluster::perimeter of every cluster in one device pass, Cluster::neighbours and
+    to_image_with_hole from the labels / merge forest / records kept in HBM, against the host-side mirror of the reference
+    methods over the indices / holes pools (itself checked against the independent restatement in tests/api_checks.py)."""
+    import time
+
+    from visioncortex_b200 import api
+
+    img = synth.g2_scene(1920, 1080, seed=100)
+    for cfg in (api.RunnerConfig(), api.RunnerConfig(hierarchical=0, is_same_color_a=2, good_max_area=1920 * 1080)):
+        clusters = api.Runner(cfg, api.ColorImage.from_array(img), ctx=gpu).run()
+        view = clusters.view()
+        t0 = time.time()
+        perims = clusters.device_perimeters()
+        dt = time.time() - t0
+        outs = [int(v) for v in view.clusters_output]
+        assert len(outs) > 100
+        for idx in outs:
+            assert int(perims[idx]) == view.get_cluster(idx).perimeter(view), idx
+        rng = np.random.default_rng(5)
+        for idx in [outs[int(k)] for k in rng.integers(0, len(outs), 40)] + outs[-3:]:
+            cl = view.get_cluster(idx)
+            assert clusters.device_neighbours(idx) == cl.neighbours(view), idx
+            for hole in (True, False):
+                want = cl.to_image_with_hole(view.width, hole)
+                got = clusters.device_to_image(idx, hole)
+                assert (got.width, got.height) == (want.width, want.height) and np.array_equal(got.pixels, want.pixels), (idx, hole)
+        assert dt < 1.0, dt
+
+
 def test_c3_cutout_two_pass_4k(gpu, oracle):
     """BASELINE config 3: 3840x2160 posterised image with key colour; pass 1 hierarchical MAX + deepen, rendered with
     to_color_image, pass 2 hierarchical 64 with Discard keying."""

@@ -361,6 +361,40 @@ class Clusters:                        # color_clusters/container.rs:4-41
     def output_len(self) -> int:                                # container.rs:18-20
         return len(self._clusters_output)
 
+    # ---- device-resident queries (include/vcb200.h: vcb_clusters_perimeters / _neighbours / _to_image): computed on the GPU from
+    # the labels, the merge forest and the records the result keeps in HBM -- the host pools above are not involved
+    def device_perimeters(self) -> np.ndarray:                  # Cluster::perimeter (cluster.rs:46-48) of every cluster, one pass
+        out = np.zeros(len(self._clusters), dtype=np.uint32)
+        lib = self._ctx.lib
+        lib.check(lib.fn("clusters_perimeters")(self._handle, out.ctypes.data_as(C.c_void_p)), self._ctx.handle)
+        return out
+
+    def device_neighbours(self, index: int) -> list:            # Cluster::neighbours (cluster.rs:132-165)
+        lib = self._ctx.lib
+        cap = 64
+        while True:
+            out = np.zeros(cap, dtype=np.uint32)
+            n = C.c_size_t(0)
+            st = lib.fn("clusters_neighbours")(self._handle, int(index), out.ctypes.data_as(C.c_void_p), cap, C.byref(n))
+            if st == 6 and n.value > cap:                       # VCB_ERR_NOMEM: the list is longer than the buffer
+                cap = int(n.value)
+                continue
+            lib.check(st, self._ctx.handle)
+            return [int(v) for v in out[:n.value]]
+
+    def device_to_image(self, index: int, hole: bool = True) -> BinaryImage:   # Cluster::to_image_with_hole (cluster.rs:60-80)
+        lib = self._ctx.lib
+        rect = (C.c_int32 * 4)()
+        r = self._clusters[int(index)].rect
+        nwords = (r.width() * r.height() + 31) // 32
+        bits = np.zeros(max(1, nwords), dtype=np.uint32)
+        lib.check(lib.fn("clusters_to_image")(self._handle, int(index), int(hole), bits.ctypes.data_as(C.c_void_p), nwords, C.byref(rect)), self._ctx.handle)
+        img = BinaryImage.new_w_h(rect[2] - rect[0], rect[3] - rect[1])
+        n = img.width * img.height
+        if n:
+            img.pixels[:] = np.unpackbits(bits.view(np.uint8), bitorder="little")[:n].astype(bool)
+        return img
+
     def view(self) -> ClustersView:                             # container.rs:22-31
         return ClustersView(self)
 

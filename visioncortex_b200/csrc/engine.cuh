@@ -472,7 +472,7 @@ inline int build_records(vcb_ctx *c, const Dims &d, const std::vector<ImgMeta> &
                    (const vcb_cluster_rec *)res->rec, (const u32 *)res->d_slot_base, d.nimg, (const u32 *)c->chunksum, d_img_base);
         const u32 nchunks = (total + prims::SCAN_CHUNK - 1) / prims::SCAN_CHUNK;
         const u32 gf = std::max<u32>(1, std::min<u32>(nchunks, (u32)c->sms * 8));
-        // the sort keys of stage_1_output (k_out_keys) come out of the same pass
+        // the sort keys of stage_1_output come out of the same pass
         rt::launch(st, "k_rec_finalize", rt::THR, k_rec_finalize, dim3(gf), dim3(REC_THREADS), RF_SMEM, res->rec, total,
                    (const u32 *)c->chunksum, (const u32 *)res->d_slot_img, (const u32 *)d_img_base, (const u32 *)res->d_slot_base,
                    key_bits, flat_outputs ? c->sk0 : (u64 *)nullptr, c->sv0, d_live);

@@ -64,18 +64,6 @@ __global__ void k_rec_key(Dims d, Bufs b, vcb_cluster_rec *rec, const u32 *slot_
     r->rect[0] = m.key_rect[0]; r->rect[1] = m.key_rect[2]; r->rect[2] = m.key_rect[1]; r->rect[3] = m.key_rect[3];
 }
 
-// per slot: half-open rect, residue_sum = sum (prepare_stage_2, builder.rs:380-382), indices_len = area
-__global__ void __launch_bounds__(REC_THREADS) k_rec_final(vcb_cluster_rec *rec, u32 total) {
-    const u32 stride = gridDim.x * REC_THREADS;
-    for (u32 s = blockIdx.x * REC_THREADS + threadIdx.x; s < total; s += stride) {
-        vcb_cluster_rec *r = rec + s;
-        if (r->sum[4] == 0) { r->rect[0] = r->rect[1] = r->rect[2] = r->rect[3] = 0; }
-        else { r->rect[2] += 1; r->rect[3] += 1; }
-        for (int k = 0; k < 5; ++k) r->residue_sum[k] = r->sum[k];
-        r->indices_len = r->sum[4];
-    }
-}
-
 // stage-1 finalisation fused into the offset scan: half-open rect, residue_sum = sum (prepare_stage_2, builder.rs:380-382),
 // indices_len = area, indices_off = exclusive scan (rebased per image afterwards)
 struct OffScanFinal {
@@ -111,7 +99,8 @@ __global__ void __launch_bounds__(REC_THREADS) k_img_base(const vcb_cluster_rec 
 // through shared memory: 256 records = 1536 16-byte words are loaded and stored fully coalesced, each thread edits its own.
 constexpr int RF_WORDS = 24;
 constexpr size_t RF_SMEM = (size_t)REC_THREADS * RF_WORDS * 4 + 64;
-// With keys != nullptr the sort keys of stage_1_output (k_out_keys below) are produced in the same pass.
+// With keys != nullptr the sort keys of stage_1_output (builder.rs:366-377: slots with area > 0, stable sort by
+// area * 65535 + index) and the per-image live counts are produced in the same pass.
 __global__ void __launch_bounds__(REC_THREADS) k_rec_finalize(vcb_cluster_rec *rec, u32 total, const u32 *chunkpref,
                                                               const u32 *slot_img, const u32 *img_base, const u32 *slot_base,
                                                               int key_bits, u64 *keys, u32 *vals, u32 *live) {
@@ -141,7 +130,7 @@ __global__ void __launch_bounds__(REC_THREADS) k_rec_finalize(vcb_cluster_rec *r
                 img = slot_img[s0 + threadIdx.x];
                 r[18] = ex - img_base[img]; r[19] = 0;
             }
-            if (keys) {                                  // uniform; stage_1_output key (builder.rs:366-377), as in k_out_keys
+            if (keys) {                                  // uniform; stage_1_output key (builder.rs:366-377)
                 const u32 s = s0 + threadIdx.x;
                 if (mine) {
                     const u32 idx = s - slot_base[img];
@@ -189,34 +178,6 @@ __global__ void __launch_bounds__(REC_THREADS) k_slot_img(u32 *slot_img, const u
     const u32 img = blockIdx.x;
     if (img >= nimg) return;
     for (u32 s = slot_base[img] + threadIdx.x; s < slot_base[img + 1]; s += REC_THREADS) slot_img[s] = img;
-}
-
-// stage_1_output (builder.rs:366-377): slots with area > 0, stable sort by area * 65535 + index
-__global__ void __launch_bounds__(REC_THREADS) k_out_keys(const vcb_cluster_rec *rec, const u32 *slot_base, const u32 *slot_img,
-                                                          u32 total, int key_bits, u64 *keys, u32 *vals, u32 *live) {
-    const u32 stride = gridDim.x * REC_THREADS;
-    const int lane = threadIdx.x & 31;
-    const u32 nloop = (total + stride - 1) / stride;
-    for (u32 it = 0; it < nloop; ++it) {
-        const u32 s = it * stride + blockIdx.x * REC_THREADS + threadIdx.x;
-        u32 img = 0xffffffffu;
-        bool alive = false;
-        if (s < total) {
-            img = slot_img[s];
-            const u32 idx = s - slot_base[img];
-            const u64 area = rec[s].indices_len;
-            u64 key = area ? area * 65535ull + idx : ((1ull << key_bits) - 1ull);
-            keys[s] = ((u64)img << key_bits) | key;
-            vals[s] = idx;
-            alive = area != 0;
-        }
-        // slots of one image are contiguous: aggregate the live count per warp when the whole warp is in one image
-        const u32 img0 = __shfl_sync(0xffffffffu, img, 0);
-        const bool uniform = __all_sync(0xffffffffu, img == img0 || s >= total);
-        const u32 m = __ballot_sync(0xffffffffu, alive);
-        if (uniform) { if (lane == 0 && m && img0 != 0xffffffffu) atomicAdd(&live[img0], (u32)__popc(m)); }
-        else if (alive) atomicAdd(&live[img], 1u);
-    }
 }
 
 // ClustersView::to_color_image for hierarchical == 0: every pixel belongs to exactly one output cluster (its own);

@@ -2,6 +2,7 @@
 // every entry point that produces results launches kernels on the context's device and fails if there is none.
 #include "binary.cuh"
 #include "engine.cuh"
+#include "queries.cuh"
 
 #include <algorithm>
 #include <mutex>
@@ -665,6 +666,100 @@ int vcb_clusters_to_color_image(const vcb_clusters *h, uint8_t *rgba_out) {
                n, (const u32 *)(br->labels + (size_t)h->img * n), (const vcb_cluster_rec *)(br->rec + br->slot_base[h->img]), (u32 *)d,
                (const u32 *)(br->seq_nx ? br->seq_nx + (size_t)h->img * n : nullptr));
     rt::copy_d2h(c->st, rgba_out, d, (size_t)n * 4);
+    return check_stream(c);
+}
+
+// ---- device-resident Cluster queries (queries.cuh)
+namespace {
+int query_args(const vcb_clusters *h, QArgs &q, vcb_ctx *&c) {
+    if (!h || !h->br || !h->br->ctx) return VCB_ERR_INVALID_ARG;
+    BatchResult *br = h->br.get();
+    c = br->ctx;
+    rt::set_device(c->device);
+    if (br->pending) { const int e = stage2_finish(c, br); if (e) return e; }
+    if (br->binary || br->d.n == 0 || !br->labels) return fail(c, VCB_ERR_INVALID_ARG, "no label map in this result");
+    if (br->seq_nx) return fail(c, VCB_ERR_UNSUPPORTED, "device-resident queries on a result of the sequential resolver (labels and cluster lists may disagree): use the indices pool");
+    const size_t n = br->d.n;
+    q.d = Dims{br->d.w, br->d.h, br->d.n, 1u, br->d.n};
+    q.fin = br->labels + (size_t)h->img * n;
+    q.l1 = br->hier ? br->labels1 + (size_t)h->img * n : q.fin;
+    q.mpar = br->hier ? br->mpar + br->slot_base[h->img] : nullptr;
+    q.rec = br->rec + br->slot_base[h->img];
+    q.nslots = br->slot_base[h->img + 1] - br->slot_base[h->img];
+    return VCB_OK;
+}
+int query_rect(vcb_ctx *c, const vcb_clusters *h, uint32_t slot, const QArgs &q, vcb_cluster_rec &r) {
+    if (slot >= q.nslots) return fail(c, VCB_ERR_INVALID_ARG, "cluster index out of range");
+    rt::copy_d2h(c->st, c->h_pinned, q.rec + slot, sizeof(vcb_cluster_rec));
+    const int e = check_stream(c);
+    if (e) return e;
+    r = *(const vcb_cluster_rec *)c->h_pinned;
+    (void)h;
+    return VCB_OK;
+}
+}  // namespace
+
+int vcb_clusters_perimeters(const vcb_clusters *h, uint32_t *out) {
+    QArgs q{}; vcb_ctx *c = nullptr;
+    int e = query_args(h, q, c);
+    if (e) return e;
+    if (!out) return fail(c, VCB_ERR_INVALID_ARG, "null output");
+    u32 *d = (u32 *)rt::dev_malloc_async(c->st, (size_t)q.nslots * 4 + 4);
+    if (!d) return fail(c, VCB_ERR_NOMEM, "device out of memory");
+    rt::fill(c->st, d, 0, (size_t)q.nslots * 4);
+    rt::launch(c->st, "k_q_perimeters", rt::SEQ, k_q_perimeters, dim3(grid_for(c, q.d.n, 256, 16)), dim3(256), 0, q, d);
+    rt::copy_d2h(c->st, out, d, (size_t)q.nslots * 4);
+    rt::dev_free_async(c->st, d);
+    return check_stream(c);
+}
+
+int vcb_clusters_neighbours(const vcb_clusters *h, uint32_t slot, uint32_t *out, size_t cap, size_t *count) {
+    QArgs q{}; vcb_ctx *c = nullptr;
+    int e = query_args(h, q, c);
+    if (e) return e;
+    if (!count || (cap && !out)) return fail(c, VCB_ERR_INVALID_ARG, "null output");
+    *count = 0;
+    vcb_cluster_rec r;
+    e = query_rect(c, h, slot, q, r);
+    if (e) return e;
+    if (r.indices_len == 0) return fail(c, VCB_ERR_INVALID_ARG, "cluster holds no pixels (the reference unwraps indices.first())");
+    const u32 rw = (u32)(r.rect[2] - r.rect[0]), rh = (u32)(r.rect[3] - r.rect[1]);
+    u32 *flags = (u32 *)rt::dev_malloc_async(c->st, ((size_t)q.nslots + cap + 2) * 4);
+    if (!flags) return fail(c, VCB_ERR_NOMEM, "device out of memory");
+    u32 *list = flags + q.nslots, *cnt = list + cap;
+    rt::fill(c->st, flags, 0, (size_t)q.nslots * 4);
+    rt::launch(c->st, "k_q_neighbours", rt::SEQ, k_q_neighbours, dim3(grid_for(c, (u64)rw * rh, 256, 16)), dim3(256), 0, q, slot, r.rect[0], r.rect[1], rw, rh, flags);
+    rt::launch(c->st, "k_q_compact", rt::THR, k_q_compact, dim3(1), dim3(256), 260 * 4, (const u32 *)flags, q.nslots, list, (u32)cap, cnt);
+    u32 *hp = (u32 *)c->h_pinned;
+    rt::copy_d2h(c->st, hp, cnt, 4);
+    e = check_stream(c);
+    if (!e) {
+        *count = hp[0];
+        const size_t take = std::min<size_t>(hp[0], cap);
+        if (take) { rt::copy_d2h(c->st, out, list, take * 4); e = check_stream(c); }
+        if (!e && hp[0] > cap) e = fail(c, VCB_ERR_NOMEM, "neighbour list larger than the caller's buffer (count holds the size needed)");
+    }
+    rt::dev_free_async(c->st, flags);
+    return e;
+}
+
+int vcb_clusters_to_image(const vcb_clusters *h, uint32_t slot, int hole, uint32_t *bits_out, size_t cap_words, int32_t rect_out[4]) {
+    QArgs q{}; vcb_ctx *c = nullptr;
+    int e = query_args(h, q, c);
+    if (e) return e;
+    vcb_cluster_rec r;
+    e = query_rect(c, h, slot, q, r);
+    if (e) return e;
+    if (rect_out) for (int k = 0; k < 4; ++k) rect_out[k] = r.rect[k];
+    const u32 rw = (u32)(r.rect[2] - r.rect[0]), rh = (u32)(r.rect[3] - r.rect[1]);
+    const size_t nwords = ((size_t)rw * rh + 31) / 32;
+    if (nwords == 0) return VCB_OK;
+    if (!bits_out || cap_words < nwords) return fail(c, VCB_ERR_NOMEM, "bit buffer too small: (rect width * rect height + 31) / 32 words are needed");
+    u32 *d = (u32 *)rt::dev_malloc_async(c->st, nwords * 4);
+    if (!d) return fail(c, VCB_ERR_NOMEM, "device out of memory");
+    rt::launch(c->st, "k_q_to_image", rt::THR, k_q_to_image, dim3(grid_for(c, nwords * 32, 256, 16)), dim3(256), 0, q, slot, r.rect[0], r.rect[1], rw, rh, hole, d);
+    rt::copy_d2h(c->st, bits_out, d, nwords * 4);
+    rt::dev_free_async(c->st, d);
     return check_stream(c);
 }
 

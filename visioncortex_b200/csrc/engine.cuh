@@ -105,11 +105,11 @@ struct BatchResult {
     ~BatchResult();
 };
 
-inline int stage2_finish(vcb_ctx *c, BatchResult *res);
+inline int stage2_finish(vcb_ctx *c, BatchResult *res, bool sync_main = true);
 inline BatchResult::~BatchResult() {
     if (!ctx) return;
     rt::set_device(ctx->device);
-    if (pending) stage2_finish(ctx, this);
+    if (pending) stage2_finish(ctx, this, true);
     for (void *p : {(void *)labels, (void *)rec, (void *)outputs, (void *)d_slot_base, (void *)d_slot_img, (void *)pool,
                     (void *)pixels, (void *)labels1, (void *)mpar, (void *)outpos, (void *)childoff, (void *)holeoff, (void *)off1,
                     (void *)hpool, (void *)pool1, (void *)seq_nx})
@@ -539,7 +539,7 @@ inline int materialize_pool_seq(vcb_ctx *c, const Dims &d, BatchResult *res) {
 // Stage 2 (builder.rs:379-539) on the records / labels produced by stage 1.  See stage2.cuh.
 inline int s2_set_count();
 inline S2Set *acquire_s2_set(vcb_ctx *c, bool async);
-inline int stage2_finish(vcb_ctx *c, BatchResult *res);
+inline int stage2_finish(vcb_ctx *c, BatchResult *res, bool sync_main);
 
 inline int ensure_s2_set(vcb_ctx *c, S2Set *s, const Dims &d, u32 total) {
     if (!s->ready) {
@@ -731,13 +731,15 @@ inline int stage2_launch(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg
     res->s2args = a;
     res->pending = set;
     set->busy = res;
-    if (!async) return stage2_finish(c, res);
+    if (!async) return stage2_finish(c, res, true);
     return VCB_OK;
 }
 
 // Completes a result whose stage 2 was launched on a workspace set: waits for the set's stream, reads the output counts and
 // (when the ordered lists were requested) scatters the indices / holes pools.  c->st is ordered after the set's work.
-inline int stage2_finish(vcb_ctx *c, BatchResult *res) {
+// sync_main = false (host pipeline, no pools requested): only the set's stream is waited for -- the main stream keeps the stage-1
+// work of the following sub-batches queued and the host must not drain it.
+inline int stage2_finish(vcb_ctx *c, BatchResult *res, bool sync_main) {
     S2Set *set = res->pending;
     if (!set) return VCB_OK;
     res->pending = nullptr;
@@ -749,7 +751,9 @@ inline int stage2_finish(vcb_ctx *c, BatchResult *res) {
     if (set->ready && rt::stream_sync(set->st) != 0) { c->err = set->st.last_error_text; set->st.last_error = 0; return VCB_ERR_CUDA; }
     if (set->st.last_error) { c->err = set->st.last_error_text; set->st.last_error = 0; return VCB_ERR_CUDA; }
     (void)on_set;
-    if (rt::stream_sync(st) != 0 || st.last_error) { c->err = st.last_error_text; st.last_error = 0; return VCB_ERR_CUDA; }
+    if (sync_main || res->pool1) {
+        if (rt::stream_sync(st) != 0 || st.last_error) { c->err = st.last_error_text; st.last_error = 0; return VCB_ERR_CUDA; }
+    }
     S2ImgState *h = (S2ImgState *)set->h_pinned;
     for (u32 i = 0; i < d.nimg; ++i) res->nout[i] = h[i].nout;
     if (std::getenv("VCB_S2_STATS"))
@@ -795,7 +799,7 @@ inline S2Set *acquire_s2_set(vcb_ctx *c, bool async) {
     if (async) { k = c->s2_next % nsets; c->s2_next = (k + 1) % nsets; }
     if (!c->s2_sets[k]) c->s2_sets[k] = new (std::nothrow) S2Set();
     S2Set *s = c->s2_sets[k];
-    if (s && s->busy) stage2_finish(c, s->busy);
+    if (s && s->busy) stage2_finish(c, s->busy, true);
     return s;
 }
 

@@ -385,10 +385,11 @@ int vcb_runner_run_batch_host(vcb_ctx *c, const vcb_runner_config *cfg, const ui
     auto download = [&](size_t k) -> int {
         const size_t i0 = k * per, cnt = std::min(per, n - i0);
         BatchResult *br = keep[k].get();
-        int e2 = stage2_finish(c, br);
+        S2Set *set = br->pending;
+        int e2 = stage2_finish(c, br, false);
         if (e2) return e2;
-        rt::event_record(ev_done[k], c->st);
-        rt::stream_wait(c->st_d2h, ev_done[k]);
+        if (set && set->ready) rt::stream_wait(c->st_d2h, set->ev_done);   // everything of this sub-batch ends on its set's stream
+        else { rt::event_record(ev_done[k], c->st); rt::stream_wait(c->st_d2h, ev_done[k]); }
         // the last record of every image carries the list totals: one small read for the whole sub-batch
         for (size_t i = 0; i < cnt; ++i) {
             vcb_host_result &r = results[i0 + i];

@@ -110,6 +110,8 @@ void vcb_runner_config_default(vcb_runner_config *cfg);
 
 /* context: one device, streams, workspace arena */
 int  vcb_ctx_create(int device, vcb_ctx **out);
+/* Result handles of the context may outlive this call: the context is then released by the last vcb_clusters_free (no other
+ * call may be made on a destroyed context). */
 void vcb_ctx_destroy(vcb_ctx *ctx);
 int  vcb_ctx_device(const vcb_ctx *ctx);
 /* options.  VCB_OPT_MATERIALIZE_INDICES (default 0): build the ordered `Cluster.indices` pool (color_clusters/cluster.rs:8)

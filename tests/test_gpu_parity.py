@@ -586,3 +586,21 @@ def test_many_tiny_images_after_a_large_one(gpu, oracle):
     got = gpu.runner_run_batch(tiny, cfg)
     for k in range(0, 9000, 601):
         assert_same_clusters(got[k], oracle.runner_run(tiny[k], cfg, pools=False), pools=False, ctx=f"tiny {k}")
+
+
+def test_result_outlives_context(oracle):
+    """vcb_clusters_free after vcb_ctx_destroy: the context lives on until its last result is freed (include/vcb200.h)."""
+    import ctypes as C
+
+    from visioncortex_b200.runtime import Context
+
+    ctx = Context(0)
+    img = synth.g2_scene(320, 200, seed=4)
+    cfg = make_config()
+    handle = ctx.runner_run_handle(img, cfg)
+    lib = ctx.lib
+    raw = ctx.handle
+    ctx.handle = None                                      # the Python wrapper must not destroy it again
+    lib.fn("ctx_destroy")(raw)
+    got = lib.read_clusters(handle, pools=True, free=True)   # reads device buffers of the zombie context, then frees them
+    assert_same_clusters(got, oracle.runner_run(img, cfg, pools=True), pools=True, ctx="result after ctx_destroy")

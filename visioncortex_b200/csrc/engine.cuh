@@ -69,6 +69,8 @@ struct vcb_ctx {
     vcb::SeqSlot *seq_slots = nullptr; // sequential resolver (sequential.cuh): n + 1 slot records per image, allocated on first use
     size_t seq_cap = 0;
     bool s2_overlap = false;          // the current call overlaps stage 2 with the following device batches
+    int live_results = 0;             // result objects that still point at this context
+    bool zombie = false;              // vcb_ctx_destroy was called while results were alive: destroyed by the last vcb_clusters_free
     bool s2_tail = false;             // ... and this is its last device batch: no stage-1 kernels follow on the main stream
 #ifndef VCB_HOSTSIM
     cudaEvent_t events[16] = {};
@@ -102,10 +104,13 @@ struct BatchResult {
     bool keep_key = false;
     S2Set *pending = nullptr;         // stage 2 launched on this set, not yet finished (stage2_finish)
     S2 s2args{};
+    void attach(vcb_ctx *c);          // binds the result to its context (counted: see vcb_ctx_destroy)
     ~BatchResult();
 };
 
 inline int stage2_finish(vcb_ctx *c, BatchResult *res, bool sync_main = true);
+inline void ctx_destroy_now(vcb_ctx *c);
+inline void BatchResult::attach(vcb_ctx *c) { ctx = c; if (c) c->live_results++; }
 inline BatchResult::~BatchResult() {
     if (!ctx) return;
     rt::set_device(ctx->device);
@@ -114,6 +119,8 @@ inline BatchResult::~BatchResult() {
                     (void *)pixels, (void *)labels1, (void *)mpar, (void *)outpos, (void *)childoff, (void *)holeoff, (void *)off1,
                     (void *)hpool, (void *)pool1, (void *)seq_nx})
         rt::dev_free_async(ctx->st, p);
+    // a context destroyed before its results lives on until the last of them is freed (include/vcb200.h)
+    if (--ctx->live_results == 0 && ctx->zombie) ctx_destroy_now(ctx);
 }
 
 inline int grid_for(const vcb_ctx *c, u64 items, int threads, int per_sm = 8) {

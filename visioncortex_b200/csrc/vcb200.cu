@@ -70,7 +70,7 @@ int fetch_last_record(vcb_clusters *h) {
 int run_color_empty(vcb_ctx *c, const vcb_runner_config *cfg, u32 w, u32 h, size_t nimg, std::shared_ptr<BatchResult> &out_br) {
     rt::set_device(c->device);
     auto br = std::make_shared<BatchResult>();
-    br->ctx = c; br->cfg = *cfg;
+    br->attach(c); br->cfg = *cfg;
     br->d = Dims{w, h, 0u, (u32)nimg, 0u};
     br->total_slots = (u32)nimg;
     br->rec = (vcb_cluster_rec *)rt::dev_malloc_async(c->st, nimg * sizeof(vcb_cluster_rec));
@@ -104,7 +104,7 @@ int run_color(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w,
     if (e) return fail(c, e, "device out of memory (workspace)");
 
     auto br = std::make_shared<BatchResult>();
-    br->ctx = c; br->d = d; br->cfg = *cfg;
+    br->attach(c); br->d = d; br->cfg = *cfg;
     br->labels = (u32 *)rt::dev_malloc_async(c->st, (size_t)d.N * sizeof(u32));
     if (!br->labels) return fail(c, VCB_ERR_NOMEM, "device out of memory (labels)");
     if (retain) {
@@ -250,6 +250,28 @@ template <class F> void for_each_stream(vcb_ctx *c, F f) {
 
 }  // namespace
 
+namespace vcb {
+inline void ctx_destroy_now(vcb_ctx *c) {
+    rt::set_device(c->device);
+    rt::stream_sync(c->st);
+    Bufs &b = c->b;
+    rt::dev_free(b.flags); rt::dev_free(b.pc); rt::dev_free(b.la); rt::dev_free(b.ls); rt::dev_free(b.lr); rt::dev_free(b.ev);
+    rt::dev_free(b.cand); rt::dev_free(b.ea); rt::dev_free(b.eb); rt::dev_free(b.newlist); rt::dev_free(b.attr); rt::dev_free(b.labex); rt::dev_free(b.leaflist); rt::dev_free(b.meta); rt::dev_free(b.ctr);
+    rt::dev_free(c->chunksum); rt::dev_free(c->rs_table); rt::dev_free(c->sk0); rt::dev_free(c->sk1);
+    rt::dev_free(c->sv0); rt::dev_free(c->sv1); rt::dev_free(c->d_small); rt::dev_free(c->d_stage);
+    for (S2Set *&set : c->s2_sets) { if (set && set->ready) rt::stream_sync(set->st); free_s2_set(set); set = nullptr; }
+    rt::dev_free(c->d_in[0]); rt::dev_free(c->d_in[1]);
+    if (c->pipe_ready) { rt::stream_destroy(c->st_h2d); rt::stream_destroy(c->st_d2h); }
+    for (rt::VmmArray *a : {&c->bw_flags, &c->bw_pc, &c->bw_la, &c->bw_ls, &c->bw_lr, &c->bw_ev, &c->bw_rgba}) rt::vmm_free(*a);
+    rt::host_free(c->h_pinned);
+#ifndef VCB_HOSTSIM
+    for (auto &ev : c->events) if (ev) cudaEventDestroy(ev);
+#endif
+    rt::stream_destroy(c->st);
+    delete c;
+}
+}  // namespace vcb
+
 extern "C" {
 
 const char *vcb_strerror(int status) {
@@ -293,23 +315,10 @@ int vcb_ctx_create(int device, vcb_ctx **out) {
 
 void vcb_ctx_destroy(vcb_ctx *c) {
     if (!c) return;
-    rt::set_device(c->device);
-    rt::stream_sync(c->st);
-    Bufs &b = c->b;
-    rt::dev_free(b.flags); rt::dev_free(b.pc); rt::dev_free(b.la); rt::dev_free(b.ls); rt::dev_free(b.lr); rt::dev_free(b.ev);
-    rt::dev_free(b.cand); rt::dev_free(b.ea); rt::dev_free(b.eb); rt::dev_free(b.newlist); rt::dev_free(b.attr); rt::dev_free(b.labex); rt::dev_free(b.leaflist); rt::dev_free(b.meta); rt::dev_free(b.ctr);
-    rt::dev_free(c->chunksum); rt::dev_free(c->rs_table); rt::dev_free(c->sk0); rt::dev_free(c->sk1);
-    rt::dev_free(c->sv0); rt::dev_free(c->sv1); rt::dev_free(c->d_small); rt::dev_free(c->d_stage);
-    for (S2Set *&set : c->s2_sets) { if (set && set->ready) rt::stream_sync(set->st); free_s2_set(set); set = nullptr; }
-    rt::dev_free(c->d_in[0]); rt::dev_free(c->d_in[1]);
-    if (c->pipe_ready) { rt::stream_destroy(c->st_h2d); rt::stream_destroy(c->st_d2h); }
-    for (rt::VmmArray *a : {&c->bw_flags, &c->bw_pc, &c->bw_la, &c->bw_ls, &c->bw_lr, &c->bw_ev, &c->bw_rgba}) rt::vmm_free(*a);
-    rt::host_free(c->h_pinned);
-#ifndef VCB_HOSTSIM
-    for (auto &ev : c->events) if (ev) cudaEventDestroy(ev);
-#endif
-    rt::stream_destroy(c->st);
-    delete c;
+    // results still alive keep device buffers and the stream of this context: the context becomes a zombie and is destroyed by the
+    // last vcb_clusters_free (no further call may be made on it)
+    if (c->live_results > 0) { c->zombie = true; return; }
+    vcb::ctx_destroy_now(c);
 }
 
 int vcb_ctx_device(const vcb_ctx *c) { return c ? c->device : -1; }
@@ -788,7 +797,7 @@ int vcb_binary_to_clusters_device(vcb_ctx *c, const uint32_t *d_bits, uint32_t w
     int e = ensure_workspace(c, d.N, 1);
     if (e) { delete hb; return fail(c, e, "device out of memory (workspace)"); }
     BatchResult br;
-    br.ctx = c; br.d = d; br.binary = true;
+    br.attach(c); br.d = d; br.binary = true;
     BinaryPolicy pol;
     pol.bits = d_bits; pol.n = d.n; pol.words_per_img = (d.n + 31) / 32; pol.diagonal = diagonal != 0;
     std::vector<ImgMeta> meta;

@@ -179,6 +179,17 @@ int  vcb_clusters_to_color_image(const vcb_clusters *c, uint8_t *rgba_out /* wid
 int  vcb_clusters_perimeters(const vcb_clusters *c, uint32_t *out /* num_slots */);
 int  vcb_clusters_neighbours(const vcb_clusters *c, uint32_t slot, uint32_t *out, size_t cap, size_t *count);
 int  vcb_clusters_to_image(const vcb_clusters *c, uint32_t slot, int hole, uint32_t *bits_out, size_t cap_words, int32_t rect_out[4]);
+/* SURVEY.md section 8(f) row f1 -- the clustering step of Cluster::to_compound_path (color_clusters/cluster.rs:108-128):
+ * `self.to_image_with_hole(parent.width, hole).to_clusters(false)` for EVERY output cluster of the image, batched on the device:
+ * the clusters' images are written straight from the result in HBM (no pools), grouped into size classes, and each class runs
+ * through the BinaryImage::to_clusters kernels (clusters.rs:270-349) as one batch.  Per output cluster k (position in
+ * clusters_output) the components comp_off[k] .. comp_off[k+1]: rect and points are relative to the cluster's image, exactly as
+ * the reference's inner `cluster.rect` / `cluster.points` (the caller adds self.rect.left / top, cluster.rs:120-123). */
+typedef struct vcb_components vcb_components;
+int  vcb_clusters_components(const vcb_clusters *c, int hole, vcb_components **out);
+int  vcb_components_info(const vcb_components *r, uint32_t *num_outputs, uint64_t *num_components, uint64_t *points_total);
+int  vcb_components_get(const vcb_components *r, uint32_t *comp_off /* num_outputs + 1 */, vcb_bin_cluster_rec *recs, int32_t *xy);
+void vcb_components_free(vcb_components *r);
 /* device pointer of the label map (width*height u32) for callers that stay on the GPU; NULL if released */
 const uint32_t *vcb_clusters_device_labels(const vcb_clusters *c);
 /* Clusters::take_image (container.rs:34-40): the retained RGBA8 input, copied to the caller */

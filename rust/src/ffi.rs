@@ -72,6 +72,7 @@ pub struct vcb_bin_clusters_info {
 pub enum vcb_ctx {}
 pub enum vcb_clusters {}
 pub enum vcb_bin_clusters {}
+pub enum vcb_components {}
 
 extern "C" {
     pub fn vcb_strerror(status: c_int) -> *const c_char;
@@ -92,6 +93,11 @@ extern "C" {
     pub fn vcb_clusters_perimeters(c: *const vcb_clusters, out: *mut u32) -> c_int;
     pub fn vcb_clusters_neighbours(c: *const vcb_clusters, slot: u32, out: *mut u32, cap: usize, count: *mut usize) -> c_int;
     pub fn vcb_clusters_to_image(c: *const vcb_clusters, slot: u32, hole: c_int, bits_out: *mut u32, cap_words: usize, rect_out: *mut i32) -> c_int;
+    // row f1: to_image_with_hole(..).to_clusters(false) of every output cluster, batched on the device (cluster.rs:108-128)
+    pub fn vcb_clusters_components(c: *const vcb_clusters, hole: c_int, out: *mut *mut vcb_components) -> c_int;
+    pub fn vcb_components_info(r: *const vcb_components, num_outputs: *mut u32, num_components: *mut u64, points_total: *mut u64) -> c_int;
+    pub fn vcb_components_get(r: *const vcb_components, comp_off: *mut u32, recs: *mut vcb_bin_cluster_rec, xy: *mut i32) -> c_int;
+    pub fn vcb_components_free(r: *mut vcb_components);
     pub fn vcb_binary_to_clusters(ctx: *mut vcb_ctx, bits: *const u32, width: u32, height: u32, diagonal: c_int,
                                   out: *mut *mut vcb_bin_clusters) -> c_int;
     pub fn vcb_bin_clusters_info_get(c: *const vcb_bin_clusters, info: *mut vcb_bin_clusters_info) -> c_int;

@@ -62,6 +62,22 @@ def check_runner_api(ctx, img: np.ndarray, **kw):
                 bits, bw, bh = R.to_image_with_hole(want, w, hole)
                 im = clusters.device_to_image(idx, hole)
                 assert (im.width, im.height) == (bw, bh) and bytes(im.pixels.astype(np.uint8)) == bytes(bits), (idx, hole)
+    # row f1: to_image_with_hole(...).to_clusters(false) of every output cluster, batched on the device, against the independent
+    # restatement of BinaryImage::to_clusters on the restated cluster image
+    if w * h:
+        for hole in (True, False):
+            comps = clusters.device_components(hole)
+            assert len(comps) == len(ref.clusters_output)
+            for k, idx in enumerate(ref.clusters_output):
+                bits, bw, bh = R.to_image_with_hole(ref.clusters[idx], w, hole)
+                if bw * bh == 0:
+                    assert comps[k] == []
+                    continue
+                want = R.to_clusters(np.array(list(bits), dtype=bool).reshape(bh, bw), False)
+                assert len(comps[k]) == len(want["records"]), (k, idx, hole)
+                for (rect, pts), wr in zip(comps[k], want["records"]):
+                    o, n = int(wr["points_off"]), int(wr["points_len"])
+                    assert rect == tuple(int(v) for v in wr["rect"]) and np.array_equal(pts, want["points"][o:o + n]), (k, idx, hole)
     if w * h:
         assert view.get_cluster_at(0) == ref.cluster_indices[0]
         assert view.get_cluster_at_point(api.PointI32(w - 1, h - 1)) == ref.cluster_indices[-1]

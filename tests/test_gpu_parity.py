@@ -262,6 +262,36 @@ def test_device_resident_queries_1080p(gpu):
         assert dt < 1.0, dt
 
 
+def test_batched_components_1080p(gpu, oracle):
+    """SURVEY section 8(f) row f1: the clustering step of Cluster::to_compound_path (cluster.rs:108-128) --
+    to_image_with_hole(parent.width, hole).to_clusters(false) -- for every output cluster of a 1080p image in one batched device
+    call, against the CPU oracle's to_clusters on the host-side cluster image (rects, point order, component order)."""
+    import time
+
+    from visioncortex_b200 import api
+
+    img = synth.g2_scene(1920, 1080, seed=101)
+    for cfg in (api.RunnerConfig(), api.RunnerConfig(hierarchical=0, is_same_color_a=2, good_max_area=1920 * 1080)):
+        clusters = api.Runner(cfg, api.ColorImage.from_array(img), ctx=gpu).run()
+        view = clusters.view()
+        t0 = time.time()
+        comps = clusters.device_components(True)
+        dt = time.time() - t0
+        outs = [int(v) for v in view.clusters_output]
+        assert len(comps) == len(outs) > 100
+        ncomp = 0
+        for k, idx in enumerate(outs):
+            im = view.get_cluster(idx).to_image_with_hole(view.width, True)
+            ref = oracle.to_clusters(im.pixels.reshape(im.height, im.width), False)
+            assert len(comps[k]) == len(ref["records"]), (k, idx)
+            for (rect, pts), wr in zip(comps[k], ref["records"]):
+                o, n = int(wr["points_off"]), int(wr["points_len"])
+                assert rect == tuple(int(v) for v in wr["rect"]) and np.array_equal(pts, ref["points"][o:o + n]), (k, idx)
+            ncomp += len(comps[k])
+        assert ncomp >= len(outs)
+        print(f"components of {len(outs)} output clusters ({ncomp} binary clusters): {dt * 1e3:.1f} ms incl. host assembly")
+
+
 def test_c3_cutout_two_pass_4k(gpu, oracle):
     """BASELINE config 3: 3840x2160 posterised image with key colour; pass 1 hierarchical MAX + deepen, rendered with
     to_color_image, pass 2 hierarchical 64 with Discard keying."""

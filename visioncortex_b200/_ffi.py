@@ -106,6 +106,7 @@ EXPORTED_SYMBOLS = [
     "vcb_clusters_indices_pool", "vcb_clusters_holes_pool", "vcb_clusters_to_color_image",
     "vcb_clusters_device_labels", "vcb_clusters_free",
     "vcb_clusters_perimeters", "vcb_clusters_neighbours", "vcb_clusters_to_image",
+    "vcb_clusters_components", "vcb_components_info", "vcb_components_get", "vcb_components_free",
     "vcb_binary_to_clusters", "vcb_binary_to_clusters_device", "vcb_bin_clusters_info_get",
     "vcb_bin_clusters_records", "vcb_bin_clusters_points", "vcb_bin_clusters_free",
     "vcb_ctx_synchronize", "vcb_ctx_kernel_launches", "vcb_ctx_profile_reset", "vcb_ctx_profile_read",
@@ -157,6 +158,11 @@ class Library:
             f("clusters_perimeters").argtypes = [p, p]
             f("clusters_neighbours").argtypes = [p, C.c_uint32, p, C.c_size_t, C.POINTER(C.c_size_t)]
             f("clusters_to_image").argtypes = [p, C.c_uint32, C.c_int, p, C.c_size_t, C.POINTER(C.c_int32 * 4)]
+            f("clusters_components").argtypes = [p, C.c_int, pp]
+            f("components_info").argtypes = [p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+            f("components_get").argtypes = [p, p, p, p]
+            f("components_free").argtypes = [p]
+            f("components_free").restype = None
         f("binary_to_clusters").argtypes = ctx + [p, C.c_uint32, C.c_uint32, C.c_int, pp]
         f("bin_clusters_info_get").argtypes = [p, C.POINTER(BinClustersInfoC)]
         f("bin_clusters_records").argtypes = [p, p]

@@ -382,6 +382,33 @@ class Clusters:                        # color_clusters/container.rs:4-41
             lib.check(st, self._ctx.handle)
             return [int(v) for v in out[:n.value]]
 
+    def device_components(self, hole: bool = True) -> list:
+        """The clustering step of Cluster::to_compound_path (cluster.rs:108-128) for every output cluster, batched on the device
+        (vcb_clusters_components): element k = the binary clusters of `clusters_output[k].to_image_with_hole(width, hole)
+        .to_clusters(false)` as (rect tuple, points (n, 2) int32 array), relative to the cluster's image."""
+        from ._ffi import BIN_CLUSTER_REC_DTYPE
+
+        lib = self._ctx.lib
+        hnd = C.c_void_p()
+        lib.check(lib.fn("clusters_components")(self._handle, int(hole), C.byref(hnd)), self._ctx.handle)
+        try:
+            nout, ncomp, npts = C.c_uint32(), C.c_uint64(), C.c_uint64()
+            lib.check(lib.fn("components_info")(hnd, C.byref(nout), C.byref(ncomp), C.byref(npts)), self._ctx.handle)
+            off = np.zeros(nout.value + 1, dtype=np.uint32)
+            rec = np.zeros(max(1, ncomp.value), dtype=BIN_CLUSTER_REC_DTYPE)
+            xy = np.zeros((max(1, npts.value), 2), dtype=np.int32)
+            lib.check(lib.fn("components_get")(hnd, off.ctypes.data_as(C.c_void_p), rec.ctypes.data_as(C.c_void_p), xy.ctypes.data_as(C.c_void_p)), self._ctx.handle)
+        finally:
+            lib.fn("components_free")(hnd)
+        out = []
+        for k in range(nout.value):
+            comps = []
+            for r in rec[off[k]:off[k + 1]]:
+                o, n = int(r["points_off"]), int(r["points_len"])
+                comps.append((tuple(int(v) for v in r["rect"]), xy[o:o + n].copy()))
+            out.append(comps)
+        return out
+
     def device_to_image(self, index: int, hole: bool = True) -> BinaryImage:   # Cluster::to_image_with_hole (cluster.rs:60-80)
         lib = self._ctx.lib
         rect = (C.c_int32 * 4)()

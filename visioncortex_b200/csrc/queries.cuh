@@ -125,4 +125,28 @@ __global__ void __launch_bounds__(256) k_q_to_image(QArgs q, u32 X, i32 left, i3
     }
 }
 
+// The images of MANY clusters at once (row f1: Cluster::to_compound_path starts with to_image_with_hole(...).to_clusters(false),
+// cluster.rs:108-128): item k = cluster slots[k] with rect rects[4k..], written as a Wp x Hp bit image (pixels outside the
+// rect unset) of words_per_img words -- the layout the batched binary pipeline reads.  One warp per 32 pixels.
+__global__ void __launch_bounds__(256) k_q_to_image_batch(QArgs q, const u32 *slots, const i32 *rects, u32 nitems, u32 Wp, u32 Hp,
+                                                          u32 words_per_img, int hole, u32 *bits) {
+    const Dims d = q.d;
+    const u32 lane = threadIdx.x & 31;
+    const u64 nwords = (u64)nitems * words_per_img;
+    for (u64 wd = ((u64)blockIdx.x * 256 + threadIdx.x) >> 5; wd < nwords; wd += ((u64)gridDim.x * 256) >> 5) {
+        const u32 k = (u32)(wd / words_per_img), t = (u32)(wd - (u64)k * words_per_img) * 32 + lane;
+        bool set = false;
+        if (t < Wp * Hp) {
+            const u32 lx = t % Wp, ly = t / Wp;
+            const i32 left = rects[4 * k], top = rects[4 * k + 1], right = rects[4 * k + 2], bottom = rects[4 * k + 3];
+            if ((i32)lx < right - left && (i32)ly < bottom - top) {
+                bool h;
+                set = q_on_chain(q, q.l1[((u32)top + ly) * d.w + (u32)left + lx], slots[k], &h) && !(hole && h);
+            }
+        }
+        const u32 m = __ballot_sync(0xffffffffu, set);
+        if (lane == 0) bits[wd] = m;
+    }
+}
+
 }  // namespace vcb

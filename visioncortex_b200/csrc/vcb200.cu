@@ -5,6 +5,7 @@
 #include "queries.cuh"
 
 #include <algorithm>
+#include <map>
 #include <mutex>
 #include <new>
 
@@ -22,6 +23,13 @@ struct vcb_bin_clusters {
     vcb_bin_clusters_info info{};
     std::vector<vcb_bin_cluster_rec> rec;
     std::vector<int32_t> xy;
+};
+
+// vcb_clusters_components: for every output cluster, the binary clusters of its image (row f1)
+struct vcb_components {
+    std::vector<uint32_t> comp_off;               // num_outputs + 1
+    std::vector<vcb_bin_cluster_rec> rec;         // all components, output cluster by output cluster
+    std::vector<int32_t> xy;                      // their points (x, y pairs), relative to the cluster's image
 };
 
 namespace {
@@ -241,6 +249,57 @@ u8 *stage_input(vcb_ctx *c, size_t bytes) {
         c->d_stage_cap = c->d_stage ? bytes : 0;
     }
     return c->d_stage;
+}
+
+// BinaryImage::to_clusters(diagonal) (clusters.rs:270-349) for nimg equally sized bit images stored back to back
+// (words_per_img words each): the same kernels as vcb_binary_to_clusters_device in one launch sequence; per image the
+// non-empty slots in slot order with their rect and their points in listing order (image-local coordinates).
+struct BinImage {
+    std::vector<vcb_bin_cluster_rec> rec;
+    std::vector<int32_t> xy;
+};
+int run_binary_batch(vcb_ctx *c, const u32 *d_bits, u32 w, u32 h, u32 nimg, int diagonal, std::vector<BinImage> &out) {
+    out.assign(nimg, BinImage());
+    const u64 n64 = (u64)w * h;
+    if (n64 == 0 || nimg == 0) return VCB_OK;
+    if (n64 * nimg >= 0x7fffff00ull) return VCB_ERR_INVALID_ARG;
+    Dims d{w, h, (u32)n64, nimg, (u32)(n64 * nimg)};
+    int e = ensure_workspace(c, d.N, d.nimg);
+    if (e) return e;
+    BatchResult br;
+    br.attach(c); br.d = d; br.binary = true;
+    BinaryPolicy pol;
+    pol.bits = d_bits; pol.n = d.n; pol.words_per_img = (d.n + 31) / 32; pol.diagonal = diagonal != 0;
+    std::vector<ImgMeta> meta;
+    Counters ctr{};
+    e = run_stage1(c, d, pol, 0u, true, 0, &br, meta, ctr);
+    if (e) return e;
+    for (u32 i = 0; i < nimg; ++i)                          // panic!("overflow") (clusters.rs:322-324) in any of the images
+        if (meta[i].slots > 0 && meta[i].maxlabel >= 65534u) return fail(c, VCB_ERR_LABEL_OVERFLOW, "overflow");
+    e = build_records(c, d, meta, &br, false, false);
+    if (!e) e = materialize_pool(c, d, &br, false);
+    if (e) return e;
+    const u32 total = br.total_slots, npts = br.pool_base[nimg];
+    std::vector<vcb_cluster_rec> hrec(total);
+    std::vector<u32> hpool(npts);
+    if (total) rt::copy_d2h(c->st, hrec.data(), br.rec, (size_t)total * sizeof(vcb_cluster_rec));
+    if (npts) rt::copy_d2h(c->st, hpool.data(), br.pool, (size_t)npts * 4);
+    e = check_stream(c);
+    if (e) return e;
+    for (u32 i = 0; i < nimg; ++i) {
+        BinImage &bi = out[i];
+        for (u32 s = br.slot_base[i]; s < br.slot_base[i + 1]; ++s) {
+            const vcb_cluster_rec &r = hrec[s];
+            if (!r.indices_len) continue;
+            vcb_bin_cluster_rec o{};
+            for (int k = 0; k < 4; ++k) o.rect[k] = r.rect[k];
+            o.points_off = bi.xy.size() / 2; o.points_len = r.indices_len;
+            const u32 *pp = hpool.data() + br.pool_base[i] + r.indices_off;
+            for (u32 k = 0; k < r.indices_len; ++k) { bi.xy.push_back((int32_t)(pp[k] % w)); bi.xy.push_back((int32_t)(pp[k] / w)); }
+            bi.rec.push_back(o);
+        }
+    }
+    return VCB_OK;
 }
 
 template <class F> void for_each_stream(vcb_ctx *c, F f) {
@@ -772,6 +831,89 @@ int vcb_clusters_to_image(const vcb_clusters *h, uint32_t slot, int hole, uint32
     rt::dev_free_async(c->st, d);
     return check_stream(c);
 }
+
+int vcb_clusters_components(const vcb_clusters *h, int hole, vcb_components **out) {
+    QArgs q{}; vcb_ctx *c = nullptr;
+    int e = query_args(h, q, c);
+    if (e) return e;
+    if (!out) return fail(c, VCB_ERR_INVALID_ARG, "null output");
+    *out = nullptr;
+    BatchResult *br = h->br.get();
+    const u32 s0 = br->slot_base[h->img], nout = br->nout[h->img];
+    std::vector<u32> outs(nout);
+    std::vector<vcb_cluster_rec> recs(q.nslots);
+    if (nout) rt::copy_d2h(c->st, outs.data(), br->outputs + s0, (size_t)nout * 4);
+    rt::copy_d2h(c->st, recs.data(), q.rec, (size_t)q.nslots * sizeof(vcb_cluster_rec));
+    e = check_stream(c);
+    if (e) return e;
+    // size classes: rect width / height rounded up to a power of two (at least 8); a class is one batched run of the binary
+    // pipeline over equally sized bit images (pixels beyond a cluster's rect are unset, which changes nothing for
+    // to_clusters(false): an unset pixel joins nothing)
+    auto cls = [](i32 v) { u32 p = 8; while ((i32)p < v) p <<= 1; return p; };
+    std::map<std::pair<u32, u32>, std::vector<u32>> buckets;          // (Wp, Hp) -> positions in clusters_output
+    for (u32 k = 0; k < nout; ++k) {
+        const vcb_cluster_rec &r = recs[outs[k]];
+        const i32 rw = r.rect[2] - r.rect[0], rh = r.rect[3] - r.rect[1];
+        if (rw <= 0 || rh <= 0) continue;                             // empty image: no clusters
+        buckets[{cls(rw), cls(rh)}].push_back(k);
+    }
+    std::vector<BinImage> per_out(nout);
+    for (auto &kv : buckets) {
+        const u32 Wp = kv.first.first, Hp = kv.first.second;
+        const u32 wpi = (Wp * Hp + 31) / 32;
+        const size_t max_items = std::max<size_t>(1, (size_t)(64ull << 20) / ((size_t)Wp * Hp));      // <= 64 Mpixel per run
+        for (size_t i0 = 0; i0 < kv.second.size(); i0 += max_items) {
+            const u32 cnt = (u32)std::min(max_items, kv.second.size() - i0);
+            std::vector<u32> hs(cnt);
+            std::vector<i32> hr((size_t)cnt * 4);
+            for (u32 k = 0; k < cnt; ++k) {
+                const u32 slot = outs[kv.second[i0 + k]];
+                hs[k] = slot;
+                for (int j = 0; j < 4; ++j) hr[4 * k + j] = recs[slot].rect[j];
+            }
+            u32 *d_slots = (u32 *)rt::dev_malloc_async(c->st, (size_t)cnt * 4);
+            i32 *d_rects = (i32 *)rt::dev_malloc_async(c->st, (size_t)cnt * 16);
+            u32 *d_bits = (u32 *)rt::dev_malloc_async(c->st, (size_t)cnt * wpi * 4);
+            if (!d_slots || !d_rects || !d_bits) return fail(c, VCB_ERR_NOMEM, "device out of memory");
+            rt::copy_h2d(c->st, d_slots, hs.data(), (size_t)cnt * 4);
+            rt::copy_h2d(c->st, d_rects, hr.data(), (size_t)cnt * 16);
+            rt::launch(c->st, "k_q_to_image_batch", rt::THR, k_q_to_image_batch, dim3(grid_for(c, (u64)cnt * wpi * 32, 256, 16)), dim3(256), 0,
+                       q, (const u32 *)d_slots, (const i32 *)d_rects, cnt, Wp, Hp, wpi, hole, d_bits);
+            e = check_stream(c);                                       // hs / hr are read by the copies above
+            std::vector<BinImage> got;
+            if (!e) e = run_binary_batch(c, d_bits, Wp, Hp, cnt, 0, got);
+            rt::dev_free_async(c->st, d_slots); rt::dev_free_async(c->st, d_rects); rt::dev_free_async(c->st, d_bits);
+            if (e) return e;
+            for (u32 k = 0; k < cnt; ++k) per_out[kv.second[i0 + k]] = std::move(got[k]);
+        }
+    }
+    vcb_components *res = new (std::nothrow) vcb_components();
+    if (!res) return fail(c, VCB_ERR_NOMEM, "host out of memory");
+    res->comp_off.assign(nout + 1, 0);
+    for (u32 k = 0; k < nout; ++k) {
+        const uint64_t pbase = res->xy.size() / 2;
+        for (vcb_bin_cluster_rec r : per_out[k].rec) { r.points_off += pbase; res->rec.push_back(r); }
+        res->xy.insert(res->xy.end(), per_out[k].xy.begin(), per_out[k].xy.end());
+        res->comp_off[k + 1] = (uint32_t)res->rec.size();
+    }
+    *out = res;
+    return VCB_OK;
+}
+int vcb_components_info(const vcb_components *r, uint32_t *num_outputs, uint64_t *num_components, uint64_t *points_total) {
+    if (!r) return VCB_ERR_INVALID_ARG;
+    if (num_outputs) *num_outputs = (uint32_t)(r->comp_off.size() - 1);
+    if (num_components) *num_components = r->rec.size();
+    if (points_total) *points_total = r->xy.size() / 2;
+    return VCB_OK;
+}
+int vcb_components_get(const vcb_components *r, uint32_t *comp_off, vcb_bin_cluster_rec *recs, int32_t *xy) {
+    if (!r) return VCB_ERR_INVALID_ARG;
+    if (comp_off) std::copy(r->comp_off.begin(), r->comp_off.end(), comp_off);
+    if (recs) std::copy(r->rec.begin(), r->rec.end(), recs);
+    if (xy) std::copy(r->xy.begin(), r->xy.end(), xy);
+    return VCB_OK;
+}
+void vcb_components_free(vcb_components *r) { delete r; }
 
 const uint32_t *vcb_clusters_device_labels(const vcb_clusters *h) {
     if (!h) return nullptr;

@@ -235,6 +235,28 @@ def secondary_configs(ctx, local, world, peak, steps=3):
         out["c1_diag%d" % diag] = {"ms": ms, "Mpix_s": 1024 * 1024 / ms / 1e3, "whole_step_frac": (algo / (ms * 1e-3) / 1e9) / peak,
                                    "parity": bin_clusters_digest(res) == hashes.get("c1_diag%d" % diag),
                                    "note": "includes D2H of the points list (the result object is host-side)"}
+    # "next" rows of SURVEY section 8(f) on C4 image 0 (default config): f4 = Cluster::perimeter of every cluster in one device
+    # pass, f1 = to_image_with_hole(..).to_clusters(false) of every output cluster as one batched device call (wall time incl. the
+    # host-side assembly of the result lists); parity against the committed digests of the oracle's results
+    try:
+        from confighash import components_digest, perimeters_digest
+        from visioncortex_b200 import api
+
+        img0 = synth.g2_scene_torch(W, H, 100, dev).cpu().numpy()
+        cl = api.Runner(api.RunnerConfig(), api.ColorImage.from_array(img0), ctx=ctx).run()
+        outs = [int(v) for v in cl.view().clusters_output]
+        for name, fn, dig in (("f4_perimeters_c4_image", lambda: cl.device_perimeters(), lambda r: perimeters_digest(r, outs)),
+                              ("f1_components_c4_image", lambda: cl.device_components(True), components_digest)):
+            fn()
+            ctx.synchronize()
+            t0 = time.time()
+            for _ in range(steps):
+                r = fn()
+            ms = (time.time() - t0) * 1e3 / steps
+            out[name] = {"ms_wall": ms, "output_clusters": len(outs), "parity": dig(r) == hashes.get("c4_0_" + name.split("_")[1])}
+        del cl
+    except Exception as e:      # never lose the headline line over a secondary row
+        out["f1_f4_error"] = repr(e)
     # C5: one 16384^2 posterised image, default config, on this GPU
     torch.cuda.empty_cache()
     c5 = synth.g3_posterised_torch(16384, 16384, 5, dev, cell=256)[None]

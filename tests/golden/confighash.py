@@ -40,6 +40,26 @@ def bin_clusters_digest(res: dict) -> str:
     return h.hexdigest()
 
 
+def components_digest(comps) -> str:
+    """vcb_clusters_components / the oracle's to_image_with_hole(..).to_clusters(false) per output cluster: for every output
+    cluster its components in order, each (rect, points)."""
+    h = hashlib.blake2b(digest_size=16)
+    h.update(np.array([len(comps)], dtype=np.uint64).tobytes())
+    for cl in comps:
+        h.update(np.array([len(cl)], dtype=np.uint64).tobytes())
+        for rect, pts in cl:
+            _upd(h, np.array(rect), np.int64)
+            _upd(h, pts, np.int32)
+    return h.hexdigest()
+
+
+def perimeters_digest(perims, outputs) -> str:
+    """Cluster::perimeter of the output clusters, in clusters_output order"""
+    h = hashlib.blake2b(digest_size=16)
+    _upd(h, np.asarray(perims)[np.asarray(outputs, dtype=np.int64)], np.int64)
+    return h.hexdigest()
+
+
 def load_hashes() -> dict:
     with open(HASH_FILE) as f:
         return json.load(f)

@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, HERE)
 
-from confighash import HASH_FILE, bin_clusters_digest, clusters_digest  # noqa: E402
+from confighash import HASH_FILE, bin_clusters_digest, clusters_digest, components_digest, perimeters_digest  # noqa: E402
 from oracle_lib import load_oracle  # noqa: E402
 from visioncortex_b200 import synth  # noqa: E402
 from visioncortex_b200 import workloads as W  # noqa: E402
@@ -48,6 +48,29 @@ def main():
     if want("c4"):
         for k in range(args.c4_images):
             out[f"c4_{k}"] = clusters_digest(o.runner_run(W.c4_input(k), W.c4_config(), pools=False))
+    if want("c4_queries"):
+        # rows f1 / f4 of SURVEY section 8(f) on C4 image 0: per output cluster the perimeter (cluster.rs:46-48) and the binary
+        # clusters of to_image_with_hole(width, true).to_clusters(false) (cluster.rs:108-128), from the oracle's pools
+        import numpy as np
+        r = o.runner_run(W.c4_input(0), W.c4_config(), pools=True)
+        w = r["width"]
+        comps, perims = [], np.zeros(r["num_slots"], dtype=np.int64)
+        for idx in r["clusters_output"]:
+            rec = r["records"][int(idx)]
+            left, top, right, bottom = [int(v) for v in rec["rect"]]
+            m = np.zeros((bottom - top, right - left), dtype=bool)
+            for pool, off, ln, val in ((r["indices_pool"], int(rec["indices_off"]), int(rec["indices_len"]), True),
+                                       (r["holes_pool"], int(rec["holes_off"]), int(rec["holes_len"]), False)):
+                ii = pool[off:off + ln].astype(np.int64)
+                m[ii // w - top, ii % w - left] = val
+            bc = o.to_clusters(m, False)
+            comps.append([(tuple(int(v) for v in q["rect"]), bc["points"][int(q["points_off"]):int(q["points_off"]) + int(q["points_len"])])
+                          for q in bc["records"]])
+            pm = np.pad(m, 1)
+            c = pm[1:-1, 1:-1]
+            perims[int(idx)] = int((c & ~(pm[1:-1, :-2] & pm[1:-1, 2:] & pm[:-2, 1:-1] & pm[2:, 1:-1])).sum())
+        out["c4_0_components"] = components_digest(comps)
+        out["c4_0_perimeters"] = perimeters_digest(perims, r["clusters_output"])
     if want("c5"):
         t0 = time.time()
         img = W.c5_input()

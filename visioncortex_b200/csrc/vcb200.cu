@@ -846,10 +846,10 @@ int vcb_clusters_components(const vcb_clusters *h, int hole, vcb_components **ou
     rt::copy_d2h(c->st, recs.data(), q.rec, (size_t)q.nslots * sizeof(vcb_cluster_rec));
     e = check_stream(c);
     if (e) return e;
-    // size classes: rect width / height rounded up to a power of two (at least 8); a class is one batched run of the binary
+    // size classes: rect width / height rounded up to a power of two (at least 32); a class is one batched run of the binary
     // pipeline over equally sized bit images (pixels beyond a cluster's rect are unset, which changes nothing for
     // to_clusters(false): an unset pixel joins nothing)
-    auto cls = [](i32 v) { u32 p = 8; while ((i32)p < v) p <<= 1; return p; };
+    auto cls = [](i32 v) { u32 p = 32; while ((i32)p < v) p <<= 1; return p; };
     std::map<std::pair<u32, u32>, std::vector<u32>> buckets;          // (Wp, Hp) -> positions in clusters_output
     for (u32 k = 0; k < nout; ++k) {
         const vcb_cluster_rec &r = recs[outs[k]];

@@ -286,16 +286,27 @@ int run_binary_batch(vcb_ctx *c, const u32 *d_bits, u32 w, u32 h, u32 nimg, int 
     if (npts) rt::copy_d2h(c->st, hpool.data(), br.pool, (size_t)npts * 4);
     e = check_stream(c);
     if (e) return e;
+    const bool pow2 = (w & (w - 1)) == 0;
+    u32 lg = 0;
+    while (pow2 && (1u << lg) < w) ++lg;
     for (u32 i = 0; i < nimg; ++i) {
         BinImage &bi = out[i];
+        size_t npi = 0, nci = 0;
+        for (u32 s = br.slot_base[i]; s < br.slot_base[i + 1]; ++s) if (hrec[s].indices_len) { npi += hrec[s].indices_len; ++nci; }
+        bi.xy.resize(npi * 2);
+        bi.rec.reserve(nci);
+        int32_t *xy = bi.xy.data();
+        size_t at = 0;
         for (u32 s = br.slot_base[i]; s < br.slot_base[i + 1]; ++s) {
             const vcb_cluster_rec &r = hrec[s];
             if (!r.indices_len) continue;
             vcb_bin_cluster_rec o{};
             for (int k = 0; k < 4; ++k) o.rect[k] = r.rect[k];
-            o.points_off = bi.xy.size() / 2; o.points_len = r.indices_len;
+            o.points_off = at; o.points_len = r.indices_len;
             const u32 *pp = hpool.data() + br.pool_base[i] + r.indices_off;
-            for (u32 k = 0; k < r.indices_len; ++k) { bi.xy.push_back((int32_t)(pp[k] % w)); bi.xy.push_back((int32_t)(pp[k] / w)); }
+            if (pow2) for (u32 k = 0; k < r.indices_len; ++k) { xy[2 * (at + k)] = (int32_t)(pp[k] & (w - 1)); xy[2 * (at + k) + 1] = (int32_t)(pp[k] >> lg); }
+            else for (u32 k = 0; k < r.indices_len; ++k) { xy[2 * (at + k)] = (int32_t)(pp[k] % w); xy[2 * (at + k) + 1] = (int32_t)(pp[k] / w); }
+            at += r.indices_len;
             bi.rec.push_back(o);
         }
     }
@@ -890,6 +901,11 @@ int vcb_clusters_components(const vcb_clusters *h, int hole, vcb_components **ou
     vcb_components *res = new (std::nothrow) vcb_components();
     if (!res) return fail(c, VCB_ERR_NOMEM, "host out of memory");
     res->comp_off.assign(nout + 1, 0);
+    {
+        size_t nr = 0, np = 0;
+        for (u32 k = 0; k < nout; ++k) { nr += per_out[k].rec.size(); np += per_out[k].xy.size(); }
+        res->rec.reserve(nr); res->xy.reserve(np);
+    }
     for (u32 k = 0; k < nout; ++k) {
         const uint64_t pbase = res->xy.size() / 2;
         for (vcb_bin_cluster_rec r : per_out[k].rec) { r.points_off += pbase; res->rec.push_back(r); }

@@ -28,8 +28,8 @@ typedef enum vcb_status {
     VCB_OK = 0,
     VCB_ERR_INVALID_ARG = 1,     /* mirrors assert!(is_same_color_a < 8) (color_clusters/runner.rs:78), size mismatch, batch_size == 0 */
     VCB_ERR_LABEL_OVERFLOW = 2,  /* mirrors panic!("overflow") (clusters.rs:322-324) */
-    VCB_ERR_UNSUPPORTED = 3,     /* hierarchical stage on an order-dependent quirk input whose labels and cluster lists disagree
-                                    (DESIGN.md section 1); every other quirk input is replayed exactly by the sequential resolver */
+    VCB_ERR_UNSUPPORTED = 3,     /* hierarchical stage on a diagonal=true input whose resurrected slot was overwritten (DESIGN.md
+                                    section 1); every other order-dependent quirk input is replayed exactly by the sequential resolver */
     VCB_ERR_CUDA = 4,
     VCB_ERR_NCCL = 5,            /* reserved, never returned: no path makes an NCCL call (the row-band exchange is in-kernel peer
                                     memory traffic; batches shard without a collective) -- kept so the numbering stays stable */

@@ -95,6 +95,7 @@ struct BatchResult {
     std::vector<u32> hpool_base, pool1_base;
     bool hier = false;
     u32 *seq_nx = nullptr;            // sequential resolver: list links per pixel (0xFFFFFFFE = in no cluster's list)
+    bool inert_key = false;           // sequential resolver + Discard + hierarchical stage: discarded key pixels carry INERT in labels1
     u32 *pool = nullptr;              // concatenated Cluster.indices of all images (exact order), when materialised
     u8 *pixels = nullptr;             // retained copy of the input (Clusters.pixels, container.rs:8; take_image :34-40)
     const u8 *ext_pixels = nullptr;   // device-resident runs: the caller's own buffer instead of a copy
@@ -425,6 +426,8 @@ inline int run_stage1_seq(vcb_ctx *c, const Dims &d, const ColorPolicy &pol, int
     res->seq_nx = (u32 *)rt::dev_malloc_async(st, (size_t)d.N * sizeof(u32));
     if (!res->seq_nx) return VCB_ERR_NOMEM;
     rt::launch(st, "k_seq_stage1", rt::SEQ, k_seq_stage1, dim3(d.nimg), dim3(SEQ_THREADS), 0, d, pol, keep_key, res->labels, res->seq_nx, c->seq_slots, b.meta, 0u);
+    if (res->inert_key)   // a hierarchical stage follows: discarded key pixels leave label 0 to the members of clusters[0] (stage2.cuh INERT)
+        rt::launch(st, "k_seq_inert", rt::SEQ, k_seq_inert, dim3(grid_for(c, d.N, 256, 16)), dim3(256), 0, d, pol, res->labels);
     ImgMeta *hm = (ImgMeta *)c->h_pinned;
     rt::copy_d2h(st, hm, b.meta, d.nimg * sizeof(ImgMeta));
     if (rt::stream_sync(st) != 0 || st.last_error) {
@@ -625,7 +628,8 @@ inline int stage2_launch(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg
     a.cfg.can_discard = (cfg->keying_action == VCB_KEYING_DISCARD && has_key) ? 1 : 0;
     a.cfg.hier_max = cfg->hierarchical == VCB_HIERARCHICAL_MAX;
     a.cfg.batch_rounds = std::getenv("VCB_S2_NOBATCH") ? 0 : 1;
-    a.cfg.rect_perim = std::getenv("VCB_S2_RECT_PERIM") ? 1 : 0;
+    a.cfg.inert = res->inert_key ? 1 : 0;
+    a.cfg.rect_perim = (std::getenv("VCB_S2_RECT_PERIM") && !a.cfg.inert) ? 1 : 0;
     a.cfg.timing = std::getenv("VCB_S2_STATS") ? 1 : 0;
     a.cfg.replay_loads = c->s2_overlap ? 0 : 1;
     a.cfg.prefetch = std::getenv("VCB_S2_PREFETCH") ? std::atoi(std::getenv("VCB_S2_PREFETCH")) : 0;
@@ -652,7 +656,7 @@ inline int stage2_launch(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg
     rt::launch(st, "k_s2_init", rt::SEQ, k_s2_init, dim3(gs), dim3(256), 0, a);
     // widths that are a multiple of 4 (128-bit label loads): the row-sweep form; VCB_RAG_PIXEL keeps the per-pixel kernel
     static const bool rag_pixel = std::getenv("VCB_RAG_PIXEL") != nullptr;
-    const bool rag_rows = !rag_pixel && d.w % 4 == 0 && ((uintptr_t)a.l1 & 15) == 0 && d.n % 4 == 0;
+    const bool rag_rows = !rag_pixel && !a.cfg.inert && d.w % 4 == 0 && ((uintptr_t)a.l1 & 15) == 0 && d.n % 4 == 0;
     const u32 rag_sx = (d.w + 127) / 128, rag_sy = (d.h + RAG_ROWS - 1) / RAG_ROWS;
     const u32 rag_grid = (u32)(((u64)rag_sx * rag_sy * d.nimg + 7) / 8);
     if (rag_rows) rt::launch(st, "k_rag_count", rt::THR, k_rag_rows<false>, dim3(rag_grid), dim3(256), 0, a, rag_sx, rag_sy);
@@ -723,7 +727,7 @@ inline int stage2_launch(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg
                            (const u64 *)(flipped ? c->sk1 : c->sk0), ep, G);
         }
     }
-    if (d.n % 4 == 0) rt::launch(st, "k_s2_labels", rt::SEQ, k_s2_labels4, dim3(grid_for(c, d.N / 4, 256, 16)), dim3(256), 0, a, res->labels);
+    if (d.n % 4 == 0 && !a.cfg.inert) rt::launch(st, "k_s2_labels", rt::SEQ, k_s2_labels4, dim3(grid_for(c, d.N / 4, 256, 16)), dim3(256), 0, a, res->labels);
     else rt::launch(st, "k_s2_labels", rt::SEQ, k_s2_labels, dim3(gp), dim3(256), 0, a, res->labels);
     // offsets of the per-slot lists after the merges
     prims::scan(st, "scan_off", OffScan{res->rec, res->d_slot_base, res->d_slot_img, total, nullptr}, set->chunksum, total, c->sms * 8);

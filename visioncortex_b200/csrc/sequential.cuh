@@ -129,6 +129,14 @@ __global__ void __launch_bounds__(SEQ_THREADS) k_seq_stage1(Dims d, ColorPolicy 
     meta[img].slots = len;
 }
 
+// Discarded key pixels get the INERT stage-1 label when a hierarchical stage follows (they are label 0 in the reference but in
+// no cluster's list; clusters[0] has members of its own here, and stage 2 is built on labels == membership)
+__global__ void __launch_bounds__(256) k_seq_inert(Dims d, ColorPolicy pol, u32 *labels) {
+    const u32 stride = gridDim.x * 256;
+    for (u32 g = blockIdx.x * 256 + threadIdx.x; g < d.N; g += stride)
+        if (pol.rgba[g] == pol.key) labels[g] = 0xFFFFFFFEu;               // == INERT (stage2.cuh)
+}
+
 // slot records of the replay -> the accumulation format the common record tail expects (k_rec_init / k_rec_finalize:
 // sum[0..3], sum[4] = pixel count, rect = inclusive min / max; an empty slot keeps the k_rec_init sentinels)
 __global__ void __launch_bounds__(256) k_seq_rec_fill(Dims d, const SeqSlot *cl_all, vcb_cluster_rec *rec, const u32 *slot_base, u32 img0, u32 nimg_grp) {

@@ -25,6 +25,7 @@ struct S2Cfg {
     u32 boff_min;      // batch rounds are given up for the rest of an epoch when they commit fewer pops per round than this
     int replay_loads;  // batch-round replay resolves roots / colours by loads even when the state is in global memory (runs that do not
                        // share the device with other batches: measured C3 pass 2 4.31 -> 4.01 ms, C5 76.1 -> 72.9 ms; overlapped C4: slower)
+    int inert;         // the stage-1 labels hold INERT pixels (sequential resolver, unclean key under KeyingAction::Discard)
     int timing;        // VCB_S2_STATS: thread 0 accumulates the cycles spent in each phase of a pop / batch round (S2ImgState.tph)
 };
 
@@ -83,6 +84,11 @@ enum { TP_SELECT = 0, TP_NBR, TP_DECIDE, TP_PERIM, TP_MERGE, TP_RELABEL, TP_BF, 
 template <class T> __device__ static __forceinline__ T ldv(const T *p) { return *reinterpret_cast<const volatile T *>(p); }
 template <class T> __device__ static __forceinline__ void stv(T *p, T v) { *reinterpret_cast<volatile T *>(p) = v; }
 
+// Stage-1 label of a pixel that belongs to no cluster's list although the reference labels it 0: a discarded key pixel of an
+// image whose clusters[0] has members of its own (unclean key, sequential.cuh).  For the graph build it is outside every
+// cluster (no adjacency, no boundary record of its own; as a neighbour it reads as NONE, like the image edge -- the
+// reference skips label-0 neighbours, cluster.rs:150, and to_image never sets it); its final label stays 0.
+constexpr u32 INERT = 0xFFFFFFFEu;
 constexpr u32 FLAGBIT = 0x80000000u;
 constexpr u32 HOLLOWBIT = 0x40000000u;
 constexpr u32 MPAR_MASK = 0x3fffffffu;
@@ -106,6 +112,29 @@ template <bool FILL> __global__ void __launch_bounds__(256) k_rag(S2 a) {
         const u32 img = g / d.n, p = g - img * d.n, x = p % d.w, y = p / d.w;
         const u32 base = a.slot_base[img];
         const u32 la = a.l1[g];
+        if (a.cfg.inert) {                                  // rare path (see INERT): the row-sweep kernel does the same
+            if (la == INERT) continue;
+            auto L = [&](u32 i) { const u32 v = a.l1[i]; return v == INERT ? NONE : v; };
+            const u32 nl = x > 0 ? L(g - 1) : NONE, nr = x + 1 < d.w ? L(g + 1) : NONE;
+            const u32 nu = y > 0 ? L(g - d.w) : NONE, nd = y + 1 < d.h ? L(g + d.w) : NONE;
+            if (nl != la || nr != la || nu != la || nd != la) {
+                if (FILL) a.bnd_nb[a.bnd_off[base + la] + atomicAdd(&a.bcur[base + la], 1u)] = make_uint4(nl, nr, nu, nd);
+                else atomicAdd(&a.bcur[base + la], 1u);
+            }
+            if (nr != NONE && la != nr && !(y > 0 && L(g - d.w) == la && L(g + 1 - d.w) == nr)) {
+                if (FILL) {
+                    a.adj[a.adj_off[base + la] + atomicAdd(&a.cursor[base + la], 1u)] = nr;
+                    a.adj[a.adj_off[base + nr] + atomicAdd(&a.cursor[base + nr], 1u)] = la;
+                } else { atomicAdd(&a.cursor[base + la], 1u); atomicAdd(&a.cursor[base + nr], 1u); }
+            }
+            if (nd != NONE && la != nd && !(x > 0 && L(g - 1) == la && L(g + d.w - 1) == nd)) {
+                if (FILL) {
+                    a.adj[a.adj_off[base + la] + atomicAdd(&a.cursor[base + la], 1u)] = nd;
+                    a.adj[a.adj_off[base + nd] + atomicAdd(&a.cursor[base + nd], 1u)] = la;
+                } else { atomicAdd(&a.cursor[base + la], 1u); atomicAdd(&a.cursor[base + nd], 1u); }
+            }
+            continue;
+        }
         {   // boundary pixel of its stage-1 slot: only these can ever be on the perimeter of a merged cluster.  What the
             // perimeter test needs of such a pixel is the labels of its four neighbours (outside the image: NONE)
             const u32 nl = x > 0 ? a.l1[g - 1] : NONE, nr = x + 1 < d.w ? a.l1[g + 1] : NONE;
@@ -1313,7 +1342,8 @@ __global__ void __launch_bounds__(256) k_s2_labels(S2 a, u32 *labels) {
     const u32 stride = gridDim.x * 256;
     for (u32 g = blockIdx.x * 256 + threadIdx.x; g < d.N; g += stride) {
         const u32 base = a.slot_base[g / d.n];
-        labels[g] = a.fw[base + a.l1[g]] & ~FLAGBIT;
+        const u32 l = a.l1[g];
+        labels[g] = (a.cfg.inert && l == INERT) ? 0u : (a.fw[base + l] & ~FLAGBIT);
     }
 }
 
@@ -1374,7 +1404,10 @@ __global__ void __launch_bounds__(256) k_s2_slot_color(S2 a, u32 *slot_color) {
 __global__ void __launch_bounds__(256) k_s2_paint(S2 a, const u32 *slot_color, u32 img, u32 *out) {
     const u32 stride = gridDim.x * 256;
     const u32 base = a.slot_base[img];
-    for (u32 p = blockIdx.x * 256 + threadIdx.x; p < a.d.n; p += stride) out[p] = slot_color[base + a.l1[(size_t)img * a.d.n + p]];
+    for (u32 p = blockIdx.x * 256 + threadIdx.x; p < a.d.n; p += stride) {
+        const u32 l = a.l1[(size_t)img * a.d.n + p];
+        out[p] = (a.cfg.inert && l == INERT) ? 0u : slot_color[base + l];      // a discarded key pixel is in no list: unpainted
+    }
 }
 
 // Ordered `Cluster.indices` / `Cluster.holes` after the hierarchical stage.  A merge appends the absorbed cluster's whole

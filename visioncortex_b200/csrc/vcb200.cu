@@ -141,12 +141,13 @@ int run_color(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w,
     if (!seq && (ctr.err & 5u)) seq = true;
     if (seq) {
         if (ds) return fail(c, VCB_ERR_UNSUPPORTED, "row-band mode: the input needs the sequential resolver (unclean key colour or an overwritten resurrected slot)");
-        // What stays rejected: the hierarchical stage on such an input when cluster_indices and Cluster.indices disagree --
-        // discarded key pixels (label 0 without being members of clusters[0], which now has members of its own) and the
-        // orphan left by an overwritten resurrected slot.  Stage 2 here is built on labels == membership.
-        if (cfg->hierarchical != 0 && (((ctr.err & 1u) && !keep) || (ctr.err & 4u) || e == VCB_ERR_UNSUPPORTED))
-            return fail(c, VCB_ERR_UNSUPPORTED, (ctr.err & 1u) ? "hierarchical stage with an unclean key colour under KeyingAction::Discard (label 0 is shared by members of clusters[0] and discarded pixels)"
-                                                               : "hierarchical stage after a resurrected slot was overwritten (builder.rs:347-348): a pixel's label and the cluster lists disagree");
+        // What stays rejected: the hierarchical stage when a pixel's label and the cluster lists disagree because a resurrected
+        // slot was overwritten (the orphan keeps a label whose cluster does not list it).  Stage 2 is built on labels ==
+        // membership; discarded key pixels, the other such case, are given the INERT stage-1 label instead (stage2.cuh).
+        if (cfg->hierarchical != 0 && ((ctr.err & 4u) || e == VCB_ERR_UNSUPPORTED))
+            return fail(c, VCB_ERR_UNSUPPORTED, "hierarchical stage after a resurrected slot was overwritten (builder.rs:347-348): a pixel's label and the cluster lists disagree");
+        // unclean key under KeyingAction::Discard with a hierarchical stage: the discarded pixels are taken out of label 0
+        br->inert_key = cfg->hierarchical != 0 && pol.has_key && !keep;
         e = run_stage1_seq(c, d, pol, keep ? 1 : 0, br.get(), meta);
         if (e) return fail(c, e, "sequential resolver failed");
     }
@@ -736,6 +737,7 @@ int vcb_clusters_to_color_image(const vcb_clusters *h, uint8_t *rgba_out) {
         S2 a{};
         a.d = br->d; a.l1 = br->labels1; a.rec = br->rec; a.slot_base = br->d_slot_base; a.slot_img = br->d_slot_img;
         a.total_slots = br->total_slots; a.mpar = br->mpar; a.outpos = br->outpos;
+        a.cfg.inert = br->inert_key ? 1 : 0;
         u32 *slot_color = (u32 *)rt::dev_malloc_async(c->st, (size_t)br->total_slots * 4 + 4);
         if (!slot_color) return fail(c, VCB_ERR_NOMEM, "device out of memory");
         rt::launch(c->st, "k_s2_slot_color", rt::SEQ, k_s2_slot_color, dim3(grid_for(c, br->total_slots, 256, 16)), dim3(256), 0, a, slot_color);

@@ -75,7 +75,8 @@ typedef struct vcb_cluster_rec {
 typedef struct vcb_clusters_info {
     uint32_t width, height;
     uint32_t num_slots;          /* clusters.len(), dead slots included */
-    uint32_t num_outputs;        /* clusters_output.len() */
+    uint32_t num_outputs;        /* clusters_output.len(); after a hierarchical stage up to 2 * num_slots (a cluster output as isolated can
+                                    grow and be output again, builder.rs:444-450) */
     uint64_t indices_total;      /* sum of indices_len over all slots */
     uint64_t holes_total;
 } vcb_clusters_info;

@@ -33,6 +33,8 @@ struct Color {
     bool operator!=(const Color &o) const { return !(*this == o); }
 };
 
+struct ReferencePanic { const char *what; };          // the reference would panic on this input
+
 // ---------------------------------------------------------------- color.rs:40-47, 256-311
 struct ColorSum {
     uint32_t r = 0, g = 0, b = 0, a = 0, counter = 0;
@@ -43,6 +45,10 @@ struct ColorSum {
         r += o.r; g += o.g; b += o.b; a += o.a; counter += o.counter;
     }
     Color average() const {                         // color.rs:295-302 (integer division, `as u8` truncation)
+        // counter == 0: Rust panics ("attempt to divide by zero") in every profile.  Reachable in stage 2 through the
+        // diagonal = true orphan pixel: its label names a slot that has been merged away, which
+        // then shows up as a neighbour with an empty cluster (builder.rs:436-442).
+        if (counter == 0) throw ReferencePanic{"attempt to divide by zero (color.rs:295-302)"};
         Color c;
         c.r = (uint8_t)(r / counter); c.g = (uint8_t)(g / counter);
         c.b = (uint8_t)(b / counter); c.a = (uint8_t)(a / counter);
@@ -516,7 +522,11 @@ int vco_runner_run(const vcb_runner_config *cfg, const uint8_t *rgba, uint32_t w
     b.pixels.assign(rgba, rgba + (size_t)width * height * 4);
     b.clusters.assign(1, vco::Cluster());                                   // builder.rs:189
     b.cluster_indices.assign((size_t)width * height, 0);                    // builder.rs:190
-    while (!b.tick()) {}                                                    // builder.rs:92
+    try {
+        while (!b.tick()) {}                                                // builder.rs:92
+    } catch (const vco::ReferencePanic &) {
+        return VCB_ERR_UNSUPPORTED;                                         // the reference panics on this input
+    }
     auto *r = new (std::nothrow) vco_clusters();
     if (!r) return VCB_ERR_NOMEM;
     r->width = width; r->height = height;
@@ -571,7 +581,8 @@ int vco_clusters_to_color_image(const vco_clusters *c, uint8_t *rgba_out) {
     std::memset(rgba_out, 0, (size_t)c->width * c->height * 4);              // ColorImage::new_w_h zero-filled
     for (size_t k = c->clusters_output.size(); k-- > 0;) {
         const auto &cl = c->clusters[c->clusters_output[k]];
-        const vco::Color col = cl.residue_color();
+        vco::Color col;
+        try { col = cl.residue_color(); } catch (const vco::ReferencePanic &) { return VCB_ERR_UNSUPPORTED; }   // the reference panics
         for (uint32_t i : cl.indices) {
             rgba_out[(size_t)i * 4 + 0] = col.r; rgba_out[(size_t)i * 4 + 1] = col.g;
             rgba_out[(size_t)i * 4 + 2] = col.b; rgba_out[(size_t)i * 4 + 3] = col.a;

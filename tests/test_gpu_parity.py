@@ -635,3 +635,45 @@ def test_result_outlives_context(oracle):
     lib.fn("ctx_destroy")(raw)
     got = lib.read_clusters(handle, pools=True, free=True)   # reads device buffers of the zombie context, then frees them
     assert_same_clusters(got, oracle.runner_run(img, cfg, pools=True), pools=True, ctx="result after ctx_destroy")
+
+
+def test_reference_panic_case_is_rejected(gpu, oracle):
+    """tests/golden/orphan_case_80x83.npy (found by tools/fuzz_gpu.py): diagonal = true, a resurrected slot is overwritten and
+    leaves an orphan pixel.  With a hierarchical stage the reference then divides by zero on the empty
+    cluster the orphan's label names (color.rs:295-302 via builder.rs:436-442): the oracle reports the panic, the device
+    rejects the input; without a hierarchical stage the sequential resolver is exact."""
+    import os
+
+    img = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "orphan_case_80x83.npy"))
+    kw = dict(diagonal=1, is_same_color_a=2, is_same_color_b=2, good_min_area=0, good_max_area=50, deepen_diff=64, hollow_neighbours=2)
+    cfg = make_config(hierarchical=HM, **kw)
+    with pytest.raises(VcbError) as e_ref:
+        oracle.runner_run(img, cfg, pools=False)
+    assert e_ref.value.status == 3
+    with pytest.raises(VcbError) as e_gpu:
+        gpu.runner_run(img, cfg, pools=False)
+    assert e_gpu.value.status == 3 and "overwritten" in str(e_gpu.value)
+    cfg = make_config(hierarchical=0, **kw)
+    got = gpu.runner_run(img, cfg, pools=True, color_image=True)
+    assert gpu.last_counters()["sequential"] == 1
+    assert_same_clusters(got, oracle.runner_run(img, cfg, pools=True, color_image=True), pools=True, ctx="orphan case, hierarchical 0")
+
+
+def test_reference_panic_case_with_unclean_key(gpu, oracle):
+    """tests/golden/orphan_case_unclean_70x37.npy (tools/fuzz_gpu.py): the same orphan under an unclean key colour -- only the
+    sequential replay itself sees the overwritten slot.  Hierarchical: reference panic == device rejection; flat: exact."""
+    import os
+
+    img = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "orphan_case_unclean_70x37.npy"))
+    kw = dict(diagonal=1, is_same_color_a=0, is_same_color_b=1, good_min_area=0, good_max_area=65536, deepen_diff=0, hollow_neighbours=1,
+              key_color=(83, 171, 177, 255), keying_action=0)
+    cfg = make_config(hierarchical=HM, **kw)
+    with pytest.raises(VcbError) as e_ref:
+        oracle.runner_run(img, cfg, pools=False)
+    assert e_ref.value.status == 3
+    with pytest.raises(VcbError) as e_gpu:
+        gpu.runner_run(img, cfg, pools=False)
+    assert e_gpu.value.status == 3 and "overwritten" in str(e_gpu.value)
+    cfg = make_config(hierarchical=0, **kw)
+    got = gpu.runner_run(img, cfg, pools=True, color_image=True)
+    assert_same_clusters(got, oracle.runner_run(img, cfg, pools=True, color_image=True), pools=True, ctx="unclean orphan case, hierarchical 0")

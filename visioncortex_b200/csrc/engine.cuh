@@ -86,7 +86,8 @@ struct BatchResult {
     vcb_runner_config cfg{};
     u32 *labels = nullptr;            // N
     vcb_cluster_rec *rec = nullptr;   // total_slots
-    u32 *outputs = nullptr;           // total_slots (per image: [slot_base, slot_base + nout))
+    u32 *outputs = nullptr;           // out_mul * total_slots (per image: [out_mul * slot_base, ... + nout))
+    u32 out_mul = 1;                  // 2 after a hierarchical stage (see S2::out_mul)
     u32 *d_slot_base = nullptr;       // nimg + 1
     u32 *d_slot_img = nullptr;        // total_slots
     u32 *labels1 = nullptr;           // stage-1 labels when a hierarchical stage ran (labels then holds the final ones)
@@ -415,7 +416,8 @@ inline int run_stage1(vcb_ctx *c, const Dims &d, const P &pol_in, u32 base, bool
 // Sequential resolver (sequential.cuh) for a device batch whose parallel pass reported an order-dependent quirk: replays
 // builder.rs:273-364 literally, one image per CTA.  Fills res->labels and the slot counts; the slot records stay in
 // c->seq_slots for build_records / materialize_pool_seq.
-inline int run_stage1_seq(vcb_ctx *c, const Dims &d, const ColorPolicy &pol, int keep_key, BatchResult *res, std::vector<ImgMeta> &meta_out) {
+inline int run_stage1_seq(vcb_ctx *c, const Dims &d, const ColorPolicy &pol, int keep_key, BatchResult *res, std::vector<ImgMeta> &meta_out,
+                          bool *orphans) {
     rt::Stream &st = c->st;
     Bufs b = c->b;
     const size_t need = (size_t)d.N + d.nimg;
@@ -436,6 +438,8 @@ inline int run_stage1_seq(vcb_ctx *c, const Dims &d, const ColorPolicy &pol, int
         return VCB_ERR_CUDA;
     }
     meta_out.assign(hm, hm + d.nimg);
+    *orphans = false;
+    for (u32 i = 0; i < d.nimg; ++i) if (hm[i].pad[0]) *orphans = true;
     c->last_counters[7] = 1;
     return VCB_OK;
 }
@@ -612,6 +616,10 @@ inline int stage2_launch(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg
     res->childoff = (u32 *)rt::dev_malloc_async(c->st, (size_t)total * 4 + 4);
     res->holeoff = (u32 *)rt::dev_malloc_async(c->st, (size_t)total * 4 + 4);
     res->labels1 = res->labels;
+    rt::dev_free_async(c->st, res->outputs);                  // room for two outputs per slot (S2::out_mul)
+    res->outputs = (u32 *)rt::dev_malloc_async(c->st, (size_t)total * 8 + 16);
+    res->out_mul = 2;
+    if (!res->outputs) return VCB_ERR_NOMEM;
     res->labels = (u32 *)rt::dev_malloc_async(c->st, (size_t)d.N * 4);
     if (!res->mpar || !res->outpos || !res->labels || !res->childoff || !res->holeoff) return VCB_ERR_NOMEM;
     res->hier = true;
@@ -643,7 +651,7 @@ inline int stage2_launch(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg
     a.childoff = res->childoff; a.holeoff = res->holeoff;
     a.fw = set->fw; a.mpar = res->mpar; a.mnext = set->mnext; a.mtail = set->mtail; a.mark = set->mark; a.tmin = set->tmin; a.outpos = res->outpos;
     a.bnd_off = set->bnd_off; a.bcur = set->bcur; a.bnd_nb = set->bnd_nb; a.col = set->col;
-    a.adj_off = set->adj_off; a.adj = set->adj; a.cursor = set->cursor; a.outputs = res->outputs; a.over = set->over;
+    a.adj_off = set->adj_off; a.adj = set->adj; a.cursor = set->cursor; a.outputs = res->outputs; a.out_mul = res->out_mul; a.over = set->over;
     a.ist = set->ist; a.keys = legacy ? c->sk0 : set->keys; a.vals = c->sv0; a.live = set->live;
     u32 *d_count = set->small + 3 * (d.nimg + 2) + 3;
     a.count = d_count;

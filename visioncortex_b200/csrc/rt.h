@@ -33,6 +33,7 @@ __device__ static inline u8 ldcg8(const u8 *p) { return __atomic_load_n(p, __ATO
 #include <cooperative_groups.h>
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <execinfo.h>
 #define VCB_SMEM(T, name)                                      \
     extern __shared__ __align__(128) unsigned char _vcb_smem[]; \
     T *name = reinterpret_cast<T *>(_vcb_smem)
@@ -112,7 +113,8 @@ inline int device_count() { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess
 inline int set_device(int d) { return (int)cudaSetDevice(d); }
 inline int sm_count(int d) { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }
 inline void *dev_malloc(size_t n) { void *p = nullptr; if (cudaMalloc(&p, n ? n : 1) != cudaSuccess) return nullptr; return p; }
-inline void dev_free(void *p) { if (p) cudaFree(p); }
+inline int api_check(int e, const char *what, const void *p, size_t n);
+inline void dev_free(void *p) { if (p) api_check((int)cudaFree(p), "dev_free", p, 0); }
 inline void *host_malloc(size_t n) { void *p = nullptr; if (cudaMallocHost(&p, n ? n : 1) != cudaSuccess) return nullptr; return p; }
 inline void host_free(void *p) { if (p) cudaFreeHost(p); }
 // stream-ordered allocations from the device's default memory pool (kept resident: release threshold = max), so that
@@ -122,7 +124,8 @@ inline void *dev_malloc_async(Stream &st, size_t n) {
     if (cudaMallocAsync(&p, n ? n : 1, st.s) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return p;
 }
-inline void dev_free_async(Stream &st, void *p) { if (p) cudaFreeAsync(p, st.s); }
+inline int api_check(int e, const char *what, const void *p, size_t n);
+inline void dev_free_async(Stream &st, void *p) { if (p) api_check((int)cudaFreeAsync(p, st.s), "dev_free_async", p, 0); }
 inline int stream_create(Stream &st) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -144,10 +147,21 @@ inline int stream_sync(Stream &st) {
     if (e != cudaSuccess && !st.last_error) { st.last_error = (int)e; st.last_error_text = std::string("stream synchronize: ") + cudaGetErrorString(e); }
     return (int)e;
 }
-inline int copy_h2d(Stream &st, void *d, const void *h, size_t n) { return (int)cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, st.s); }
-inline int copy_d2h(Stream &st, void *h, const void *d, size_t n) { return (int)cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, st.s); }
-inline int copy_d2d(Stream &st, void *d, const void *s, size_t n) { return (int)cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st.s); }
-inline int fill(Stream &st, void *d, int byte, size_t n) { return (int)cudaMemsetAsync(d, byte, n, st.s); }
+// VCB_CHECK_API=1 (debugging aid): report the runtime call that fails, with its arguments -- a failing copy / fill / free is
+// otherwise only seen as the "last error" of the next kernel launch
+inline int api_check(int e, const char *what, const void *p, size_t n) {
+    static const bool on = std::getenv("VCB_CHECK_API") != nullptr;
+    if (on && e != 0) {
+        std::fprintf(stderr, "[vcb] %s(%p, %zu) failed: %s\n", what, p, n, cudaGetErrorString((cudaError_t)e));
+        void *frames[16];
+        backtrace_symbols_fd(frames, backtrace(frames, 16), 2);
+    }
+    return e;
+}
+inline int copy_h2d(Stream &st, void *d, const void *h, size_t n) { return api_check((int)cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, st.s), "copy_h2d", d, n); }
+inline int copy_d2h(Stream &st, void *h, const void *d, size_t n) { return api_check((int)cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, st.s), "copy_d2h", d, n); }
+inline int copy_d2d(Stream &st, void *d, const void *s, size_t n) { return api_check((int)cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st.s), "copy_d2d", d, n); }
+inline int fill(Stream &st, void *d, int byte, size_t n) { return api_check((int)cudaMemsetAsync(d, byte, n, st.s), "fill", d, n); }
 inline const char *error_string(int e) { return cudaGetErrorString((cudaError_t)e); }
 inline int max_coop_blocks(const void *k, int threads, size_t smem, int dev) {
     int per_sm = 0;

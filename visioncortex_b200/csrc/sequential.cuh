@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(SEQ_THREADS) k_seq_stage1(Dims d, ColorPolicy 
     const SeqSlot fresh = {NONE, NONE, 0u, 0u, {0u, 0u, 0u, 0u}, {0, 0, 0, 0}};
     cl[0] = fresh;                                           // clusters = vec![Cluster::new()] (builder.rs:189)
     u32 len = 1, next_index = 1;                             // next_index: builder.rs:190
+    u32 orphans = 0;                                         // overwritten resurrected slots (labels and lists disagree afterwards)
     const bool has_key = pol.has_key != 0, diagonal = pol.diagonal != 0;
     const u32 key = pol.key, w = d.w;
     u32 i = 0;
@@ -116,8 +117,10 @@ __global__ void __launch_bounds__(SEQ_THREADS) k_seq_stage1(Dims d, ColorPolicy 
             } else if (diagonal && s_cul) {                                   // :341-343 (cluster_upleft was read before the merge)
                 lab[i] = cluster_upleft; seq_add(cl, nx, cluster_upleft, i, color, (i32)x, (i32)y);
             } else {                                                          // :344-353
-                if (next_index < len && cl[next_index].area)                  // a resurrected slot is overwritten: its pixels keep their label
+                if (next_index < len && cl[next_index].area) {                // a resurrected slot is overwritten: its pixels keep their label
                     for (u32 p = cl[next_index].head; p != NONE;) { const u32 q = nx[p]; nx[p] = SEQ_ORPHAN; p = q; }
+                    ++orphans;
+                }
                 cl[next_index] = fresh;                                       // overwrite a freed slot or push
                 if (next_index >= len) len = next_index + 1;
                 seq_add(cl, nx, next_index, i, color, (i32)x, (i32)y);
@@ -127,6 +130,7 @@ __global__ void __launch_bounds__(SEQ_THREADS) k_seq_stage1(Dims d, ColorPolicy 
         }
     }
     meta[img].slots = len;
+    meta[img].pad[0] = orphans;
 }
 
 // Discarded key pixels get the INERT stage-1 label when a hierarchical stage follows (they are label 0 in the reference but in

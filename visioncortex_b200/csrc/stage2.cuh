@@ -57,7 +57,10 @@ struct S2 {
     u32 *bnd_off, *bcur;           // per stage-1 slot: its boundary pixels (a neighbour with another label, or the image edge) ...
     uint4 *bnd_nb;                 // ... each stored as the stage-1 labels of its four neighbours (NONE = outside the image)
     u32 *col;                      // average colour (ColorSum::average) of every live root, kept current by the merges
-    u32 *outputs;                  // total_slots: clusters_output per image at slot_base[img]
+    u32 *outputs;                  // clusters_output per image at out_mul * slot_base[img]
+    u32 out_mul;                   // 2 after a hierarchical stage: a cluster that is output as isolated (builder.rs:444-450) and grows
+                                   // afterwards -- clusters[0] merging into it, unclean key -- is output again at its new area, so
+                                   // an image can have more outputs than slots (at most one per pop: <= slots + merges <= 2 * slots)
     u64 *over;                     // total_slots: per-image overflow of the urgent list at slot_base[img]
     S2ImgState *ist;               // nimg
     u64 *keys; u32 *vals;          // epoch sort input/output
@@ -582,13 +585,13 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
             if (f & BF_SLOW) { J = q; break; }
             if (sh->bkey[q] > nkmin) { J = q; break; }
             if (f & BF_OUTONLY) {                                                     // builder.rs:429-432
-                if (lane == 0) { a.outputs[base + nout] = c; atomicMin(&a.outpos[base + c], nout); }
+                if (lane == 0) { a.outputs[a.out_mul * base + nout] = c; atomicMin(&a.outpos[base + c], nout); }
                 ++nout;
                 continue;
             }
             if (f & BF_ISOLATED) {                                                    // builder.rs:444-450
                 if (area == maxarea || a.cfg.can_discard) {
-                    if (lane == 0) { a.outputs[base + nout] = c; atomicMin(&a.outpos[base + c], nout); }
+                    if (lane == 0) { a.outputs[a.out_mul * base + nout] = c; atomicMin(&a.outpos[base + c], nout); }
                     ++nout;
                 }
                 continue;
@@ -627,7 +630,7 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
             }
             const bool hollow = (u64)nd <= a.cfg.hollow_neighbours;
             if (deepen) {                                                             // builder.rs:463-465
-                if (lane == 0) { a.outputs[base + nout] = c; atomicMin(&a.outpos[base + c], nout); }
+                if (lane == 0) { a.outputs[a.out_mul * base + nout] = c; atomicMin(&a.outpos[base + c], nout); }
                 ++nout;
             }
             // the target's record: already cached (modified earlier in the round), the S0 copy read by the candidate's
@@ -987,7 +990,7 @@ __device__ static __forceinline__ void s2_epoch_leader(const S2 &a, S2Shared *sh
         if (area > a.cfg.hierarchical) {                              // builder.rs:429-432
             if (tid == 0) {
                 const u32 pos = ist->nout++;
-                a.outputs[base + pos] = c;
+                a.outputs[a.out_mul * base + pos] = c;
                 if (a.outpos[base + c] == NONE) a.outpos[base + c] = pos;
             }
             __syncthreads();
@@ -1043,7 +1046,7 @@ __device__ static __forceinline__ void s2_epoch_leader(const S2 &a, S2Shared *sh
         if (ndist == 0) {                                             // builder.rs:444-450
             if (tid == 0 && (area == ist->maxarea || a.cfg.can_discard)) {
                 const u32 pos = ist->nout++;
-                a.outputs[base + pos] = c;
+                a.outputs[a.out_mul * base + pos] = c;
                 if (a.outpos[base + c] == NONE) a.outpos[base + c] = pos;
             }
             __syncthreads();
@@ -1096,7 +1099,7 @@ __device__ static __forceinline__ void s2_epoch_leader(const S2 &a, S2Shared *sh
             vcb_cluster_rec *rf = a.rec + base + c, *rt_ = a.rec + base + target;
             if (deepen) {                                             // builder.rs:463-465
                 const u32 pos = ist->nout++;
-                a.outputs[base + pos] = c;
+                a.outputs[a.out_mul * base + pos] = c;
                 if (a.outpos[base + c] == NONE) a.outpos[base + c] = pos;
             }
             // merge_cluster_into (builder.rs:495-539)

@@ -148,8 +148,13 @@ int run_color(vcb_ctx *c, const vcb_runner_config *cfg, const u8 *d_rgba, u32 w,
             return fail(c, VCB_ERR_UNSUPPORTED, "hierarchical stage after a resurrected slot was overwritten (builder.rs:347-348): a pixel's label and the cluster lists disagree");
         // unclean key under KeyingAction::Discard with a hierarchical stage: the discarded pixels are taken out of label 0
         br->inert_key = cfg->hierarchical != 0 && pol.has_key && !keep;
-        e = run_stage1_seq(c, d, pol, keep ? 1 : 0, br.get(), meta);
+        bool orphans = false;
+        e = run_stage1_seq(c, d, pol, keep ? 1 : 0, br.get(), meta, &orphans);
         if (e) return fail(c, e, "sequential resolver failed");
+        // the replay itself knows whether a resurrected slot was overwritten (with an unclean key the parallel pass's own check is
+        // not reliable); the reference's hierarchical stage then divides by zero on the empty cluster the orphan's label names
+        if (orphans && cfg->hierarchical != 0)
+            return fail(c, VCB_ERR_UNSUPPORTED, "hierarchical stage after a resurrected slot was overwritten (builder.rs:347-348): a pixel's label and the cluster lists disagree");
     }
     e = build_records(c, d, meta, br.get(), cfg->hierarchical == 0, keep, seq);
     if (e) return e;
@@ -485,7 +490,7 @@ int vcb_runner_run_batch_host(vcb_ctx *c, const vcb_runner_config *cfg, const ui
             }
             if (r.outputs) {
                 if (r.outputs_cap < br->nout[i]) r.status = VCB_ERR_NOMEM;
-                else if (br->nout[i]) rt::copy_d2h(c->st_d2h, r.outputs, br->outputs + s0, (size_t)br->nout[i] * 4);
+                else if (br->nout[i]) rt::copy_d2h(c->st_d2h, r.outputs, br->outputs + (size_t)br->out_mul * s0, (size_t)br->nout[i] * 4);
             }
         }
         return VCB_OK;
@@ -670,7 +675,7 @@ int vcb_clusters_outputs(const vcb_clusters *h, uint32_t *out) {
     const u32 n = br->nout[h->img];
     if (n == 0) return VCB_OK;
     if (!out) return VCB_ERR_INVALID_ARG;
-    rt::copy_d2h(br->ctx->st, out, br->outputs + br->slot_base[h->img], (size_t)n * 4);
+    rt::copy_d2h(br->ctx->st, out, br->outputs + (size_t)br->out_mul * br->slot_base[h->img], (size_t)n * 4);
     return check_stream(br->ctx);
 }
 
@@ -855,7 +860,7 @@ int vcb_clusters_components(const vcb_clusters *h, int hole, vcb_components **ou
     const u32 s0 = br->slot_base[h->img], nout = br->nout[h->img];
     std::vector<u32> outs(nout);
     std::vector<vcb_cluster_rec> recs(q.nslots);
-    if (nout) rt::copy_d2h(c->st, outs.data(), br->outputs + s0, (size_t)nout * 4);
+    if (nout) rt::copy_d2h(c->st, outs.data(), br->outputs + (size_t)br->out_mul * s0, (size_t)nout * 4);
     rt::copy_d2h(c->st, recs.data(), q.rec, (size_t)q.nslots * sizeof(vcb_cluster_rec));
     e = check_stream(c);
     if (e) return e;

@@ -174,7 +174,7 @@ def runner_run_batch_host(ctx: Context, images, cfg: RunnerConfigC, records_cap:
     h, w = imgs[0].shape[:2]
     cap = records_cap if records_cap is not None else w * h + 1
     if buffers is None:
-        buffers = [(np.empty(w * h, dtype=np.uint32), np.zeros(cap, dtype=CLUSTER_REC_DTYPE), np.empty(cap, dtype=np.uint32))
+        buffers = [(np.empty(w * h, dtype=np.uint32), np.zeros(cap, dtype=CLUSTER_REC_DTYPE), np.empty(2 * cap, dtype=np.uint32))
                    for _ in range(n)]
     ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
     res = (HostResultC * n)()

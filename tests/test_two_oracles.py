@@ -51,6 +51,13 @@ def run_pair(oracle, img, kw):
     try:
         want = R.runner_run(img, pcfg, color_image=True)
     except R.ReferencePanic as e:
+        # the Rust itself would panic here; the C++ oracle must say so too (status 3) when it is the division by zero in
+        # ColorSum::average -- the panic the hierarchical stage can really reach (orphan pixel of an overwritten slot)
+        if "divide by zero" in str(e):
+            from visioncortex_b200._ffi import VcbError
+            with pytest.raises(VcbError) as ce:
+                oracle.runner_run(img, ccfg, pools=False)
+            assert ce.value.status == 3
         return "panic", str(e)
     got = oracle.runner_run(img, ccfg, pools=True, color_image=True)
     return got, want

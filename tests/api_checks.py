@@ -125,3 +125,39 @@ def check_binary_api(ctx):
     cl = img.to_clusters(False, ctx=ctx)
     assert len(cl) == 1 and (cl.rect.left, cl.rect.top, cl.rect.right, cl.rect.bottom) == (1, 1, 3, 3)
     assert api.BinaryImage.new_w_h(0, 0).to_clusters(False, ctx=ctx).clusters == []
+
+
+def check_batch_queries(ctx, side=20):
+    """device-resident queries / components on the handles of a BATCH (image index > 0: per-image offsets into the labels, the
+    merge forest and the records) against the host mirror over the pools of the same handle."""
+    import ctypes as C
+
+    from parity import random_colour_image
+
+    rng = np.random.default_rng(31)
+    w, h = side, side - 3
+    imgs = [random_colour_image(rng, w, h) for _ in range(3)]
+    for cfg in (api.RunnerConfig(is_same_color_a=2, good_min_area=2, deepen_diff=8), api.RunnerConfig(hierarchical=0, is_same_color_a=2)):
+        n = len(imgs)
+        ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+        ws, hs = (C.c_uint32 * n)(*[w] * n), (C.c_uint32 * n)(*[h] * n)
+        outs = (C.c_void_p * n)()
+        ccfg = cfg.to_c()
+        ctx.lib.check(ctx.lib.fn("runner_run_batch")(ctx.handle, C.byref(ccfg), ptrs, ws, hs, n, outs), ctx.handle)
+        for k in range(n):
+            cl = api.Clusters(ctx, C.c_void_p(outs[k]), imgs[k].reshape(-1), w, h)
+            view = cl.view()
+            perims = cl.device_perimeters()
+            comps = cl.device_components(True)
+            for pos, idx in enumerate(int(v) for v in view.clusters_output):
+                c = view.get_cluster(idx)
+                assert int(perims[idx]) == c.perimeter(view), (k, idx)
+                assert cl.device_neighbours(idx) == c.neighbours(view), (k, idx)
+                im = c.to_image(view)
+                got = cl.device_to_image(idx, True)
+                assert (got.width, got.height) == (im.width, im.height) and np.array_equal(got.pixels, im.pixels), (k, idx)
+                want = R.to_clusters(im.pixels.reshape(im.height, im.width), False) if im.width * im.height else None
+                assert len(comps[pos]) == (len(want["records"]) if want else 0), (k, idx)
+                for (rect, pts), wr in zip(comps[pos], want["records"] if want else []):
+                    o, ln = int(wr["points_off"]), int(wr["points_len"])
+                    assert rect == tuple(int(v) for v in wr["rect"]) and np.array_equal(pts, want["points"][o:o + ln]), (k, idx)

@@ -3,7 +3,7 @@ through the C ABI.  CPU: the host-simulator build of the kernels; GPU: the produ
 import numpy as np
 import pytest
 
-from api_checks import check_binary_api, check_builder_contract, check_runner_api
+from api_checks import check_batch_queries, check_binary_api, check_builder_contract, check_runner_api
 from parity import random_colour_image
 
 HM = 0xFFFFFFFF
@@ -32,6 +32,7 @@ def test_api_on_simulator():
     check_runner_api(sim, np.zeros((0, 0, 4), dtype=np.uint8), hierarchical=0)
     check_builder_contract(sim)
     check_binary_api(sim)
+    check_batch_queries(sim, side=14)
 
 
 @pytest.mark.gpu
@@ -41,3 +42,4 @@ def test_api_on_gpu(gpu):
         check_runner_api(gpu, img, **CASES[k % len(CASES)])
     check_builder_contract(gpu)
     check_binary_api(gpu)
+    check_batch_queries(gpu, side=150)

@@ -141,6 +141,17 @@ typedef struct vcb_host_result {
     uint32_t         records_cap, outputs_cap;
     vcb_clusters_info info;             /* out */
     int              status;            /* out */
+    /* Optional compact records (set live_slots on EVERY result of the call, or on none).  After a hierarchical stage most slots
+     * of `clusters` are Cluster::default() (merged away in stage 1: every field zero); their 96-byte records are most of the
+     * device->host traffic of a batch.  With live_slots != NULL only the slots that are not default -- any of indices_len,
+     * holes_len, residue_sum.counter, merged_into, depth, num_holes non-zero -- are transferred: records[k] is the record of
+     * slot live_slots[k] (ascending), k < num_live <= records_cap (= capacity of both arrays); every slot not listed is default
+     * (its indices_off / holes_off, this library's own layout fields, are the running totals and can be rebuilt as exclusive scans).
+     * compact = 1 when the result came back in this form, 0 when all num_slots records were written as usual (runs without a
+     * hierarchical stage). */
+    uint32_t        *live_slots;        /* records_cap, or NULL */
+    uint32_t         num_live;          /* out */
+    uint32_t         compact;           /* out */
 } vcb_host_result;
 int vcb_runner_run_batch_host(vcb_ctx *ctx, const vcb_runner_config *cfg, const uint8_t *const *rgba, uint32_t width,
                               uint32_t height, size_t n, vcb_host_result *results);

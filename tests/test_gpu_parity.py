@@ -436,9 +436,17 @@ def test_host_to_host_batch(gpu, oracle):
     imgs = [synth.g2_scene(640, 360, seed=200 + k) for k in range(9)]
     for cfg in (c2_config(640, 360), make_config()):
         got = runner_run_batch_host(gpu, imgs, cfg, records_cap=640 * 360 // 2)
-        for k, im in enumerate(imgs):
-            ref = oracle.runner_run(im, cfg, pools=False)
-            assert_same_clusters(got[k], ref, pools=False, ctx=f"host batch image {k}")
+        refs = [oracle.runner_run(im, cfg, pools=False) for im in imgs]
+        for k in range(len(imgs)):
+            assert_same_clusters(got[k], refs[k], pools=False, ctx=f"host batch image {k}")
+        # compact records: only the slots that are not Cluster::default() travel (after a hierarchical stage; otherwise the
+        # call answers in the usual form and says so)
+        got = runner_run_batch_host(gpu, imgs, cfg, records_cap=640 * 360 // 2, compact=True)
+        for k in range(len(imgs)):
+            assert got[k]["compact"] == (1 if cfg.hierarchical else 0)
+            if cfg.hierarchical:
+                assert 0 < got[k]["num_live"] < got[k]["num_slots"]
+            assert_same_clusters(got[k], refs[k], pools=False, ctx=f"compact host batch image {k}")
 
 
 def test_empty_and_ragged_inputs(gpu, oracle):

@@ -222,3 +222,8 @@ def test_sim_chunked_batches_overlap_stage2(sim, oracle, monkeypatch):
     got = runner_run_batch_host(sim, imgs, cfg)
     for k in range(len(imgs)):
         assert_same_clusters(got[k], refs[k], pools=False, ctx=f"host batch image {k}")
+    # compact records (vcb_host_result.live_slots): only the slots that are not Cluster::default() travel
+    got = runner_run_batch_host(sim, imgs, cfg, compact=True)
+    for k in range(len(imgs)):
+        assert got[k]["compact"] == 1 and 0 < got[k]["num_live"] <= got[k]["num_slots"]
+        assert_same_clusters(got[k], refs[k], pools=False, ctx=f"compact host batch image {k}")

@@ -58,6 +58,9 @@ class HostResultC(C.Structure):
         ("outputs_cap", C.c_uint32),
         ("info", ClustersInfoC),
         ("status", C.c_int),
+        ("live_slots", C.c_void_p),
+        ("num_live", C.c_uint32),
+        ("compact", C.c_uint32),
     ]
 
 

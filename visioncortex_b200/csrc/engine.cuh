@@ -71,6 +71,7 @@ struct vcb_ctx {
     bool s2_overlap = false;          // the current call overlaps stage 2 with the following device batches
     int live_results = 0;             // result objects that still point at this context
     bool zombie = false;              // vcb_ctx_destroy was called while results were alive: destroyed by the last vcb_clusters_free
+    bool host_compact = false;        // vcb_runner_run_batch_host with live_slots: stage2_launch also compacts the records
     bool s2_tail = false;             // ... and this is its last device batch: no stage-1 kernels follow on the main stream
 #ifndef VCB_HOSTSIM
     cudaEvent_t events[16] = {};
@@ -96,6 +97,9 @@ struct BatchResult {
     std::vector<u32> hpool_base, pool1_base;
     bool hier = false;
     u32 *seq_nx = nullptr;            // sequential resolver: list links per pixel (0xFFFFFFFE = in no cluster's list)
+    vcb_cluster_rec *crec = nullptr;  // compact records of the host pipeline (LiveScan), with their slot indices and per-image offsets
+    u32 *cidx = nullptr, *coff = nullptr;
+    std::vector<u32> live_off;        // nimg + 1 (host copy of coff)
     bool inert_key = false;           // sequential resolver + Discard + hierarchical stage: discarded key pixels carry INERT in labels1
     u32 *pool = nullptr;              // concatenated Cluster.indices of all images (exact order), when materialised
     u8 *pixels = nullptr;             // retained copy of the input (Clusters.pixels, container.rs:8; take_image :34-40)
@@ -119,7 +123,7 @@ inline BatchResult::~BatchResult() {
     if (pending) stage2_finish(ctx, this, true);
     for (void *p : {(void *)labels, (void *)rec, (void *)outputs, (void *)d_slot_base, (void *)d_slot_img, (void *)pool,
                     (void *)pixels, (void *)labels1, (void *)mpar, (void *)outpos, (void *)childoff, (void *)holeoff, (void *)off1,
-                    (void *)hpool, (void *)pool1, (void *)seq_nx})
+                    (void *)hpool, (void *)pool1, (void *)seq_nx, (void *)crec, (void *)cidx, (void *)coff})
         rt::dev_free_async(ctx->st, p);
     // a context destroyed before its results lives on until the last of them is freed (include/vcb200.h)
     if (--ctx->live_results == 0 && ctx->zombie) ctx_destroy_now(ctx);
@@ -746,6 +750,16 @@ inline int stage2_launch(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg
     rt::launch(st, "k_holes_first", rt::SEQ, k_holes_first, dim3((d.nimg + 127) / 128), dim3(128), 0, (const vcb_cluster_rec *)res->rec, (const u32 *)res->d_slot_base, d.nimg, d_first);
     rt::launch(st, "k_holes_rebase", rt::SEQ, k_holes_rebase, dim3(gs), dim3(256), 0, res->rec, (const u32 *)res->d_slot_base, (const u32 *)res->d_slot_img, total, d_first);
     rt::copy_d2h(st, set->h_pinned, set->ist, d.nimg * sizeof(S2ImgState));
+    if (c->host_compact && total) {
+        res->crec = (vcb_cluster_rec *)rt::dev_malloc_async(c->st, (size_t)total * sizeof(vcb_cluster_rec));
+        res->cidx = (u32 *)rt::dev_malloc_async(c->st, (size_t)total * 4);
+        res->coff = (u32 *)rt::dev_malloc_async(c->st, ((size_t)d.nimg + 1) * 4);
+        if (!res->crec || !res->cidx || !res->coff) return VCB_ERR_NOMEM;
+        if (async) { rt::event_record(set->ev_in, c->st); rt::stream_wait(set->st, set->ev_in); }   // the allocations are ordered on c->st
+        prims::scan(st, "scan_live", LiveScan{res->rec, total, res->d_slot_base, res->d_slot_img, d.nimg, res->crec, res->cidx, res->coff},
+                    set->chunksum, total, c->sms * 8);
+        rt::copy_d2h(st, (char *)set->h_pinned + (size_t)d.nimg * sizeof(S2ImgState), res->coff, ((size_t)d.nimg + 1) * 4);
+    }
     if (async) rt::event_record(set->ev_done, set->st);
     res->s2args = a;
     res->pending = set;
@@ -775,6 +789,10 @@ inline int stage2_finish(vcb_ctx *c, BatchResult *res, bool sync_main) {
     }
     S2ImgState *h = (S2ImgState *)set->h_pinned;
     for (u32 i = 0; i < d.nimg; ++i) res->nout[i] = h[i].nout;
+    if (res->coff) {
+        const u32 *lo = (const u32 *)((const char *)set->h_pinned + (size_t)d.nimg * sizeof(S2ImgState));
+        res->live_off.assign(lo, lo + d.nimg + 1);
+    }
     if (std::getenv("VCB_S2_STATS"))
         std::fprintf(stderr, "[vcb] stage 2 image 0: merges %u, outputs %u, batch rounds %u (candidates %u, committed %u), single pops %u\n",
                      h[0].nmerge, h[0].nout, h[0].st_rounds, h[0].st_cands, h[0].st_committed, h[0].st_singles);

@@ -1365,6 +1365,24 @@ __global__ void __launch_bounds__(256) k_s2_labels4(S2 a, u32 *labels) {
     }
 }
 
+// Compact records for the host pipeline (vcb_host_result.live_slots): the slots that are not Cluster::default(), in slot order,
+// with their image-local index; coff[img] = position of the image's first live slot, coff[nimg] = total.
+struct LiveScan {
+    const vcb_cluster_rec *rec; u32 total; const u32 *slot_base; const u32 *slot_img; u32 nimg;
+    vcb_cluster_rec *crec; u32 *cidx; u32 *coff;
+    __device__ u32 count() const { return total; }
+    __device__ u32 value(u32 s) const {
+        const vcb_cluster_rec &r = rec[s];
+        return (r.indices_len | r.holes_len | r.residue_sum[4] | r.merged_into | r.depth | r.num_holes) ? 1u : 0u;
+    }
+    __device__ void emit(u32 s, u32 ex, u32 v) const {
+        const u32 img = slot_img[s], b0 = slot_base[img];
+        if (v) { crec[ex] = rec[s]; cidx[ex] = s - b0; }
+        if (s == b0) coff[img] = ex;
+        if (s == total - 1) coff[nimg] = ex + v;
+    }
+};
+
 struct HolesScan {
     vcb_cluster_rec *rec; u32 total;
     __device__ u32 count() const { return total; }

@@ -484,7 +484,16 @@ int vcb_runner_run_batch_host(vcb_ctx *c, const vcb_runner_config *cfg, const ui
             r.info.indices_total = 0; r.info.holes_total = 0;
             r.status = VCB_OK;
             if (r.cluster_indices) rt::copy_d2h(c->st_d2h, r.cluster_indices, br->labels + i * npx, (size_t)npx * 4);
-            if (r.records) {
+            r.num_live = 0; r.compact = 0;
+            if (r.records && r.live_slots && !br->live_off.empty()) {           // compact form: the slots that are not default
+                const u32 l0 = br->live_off[i], nl = br->live_off[i + 1] - l0;
+                r.num_live = nl; r.compact = 1;
+                if (r.records_cap < nl) r.status = VCB_ERR_NOMEM;
+                else if (nl) {
+                    rt::copy_d2h(c->st_d2h, r.records, br->crec + l0, (size_t)nl * sizeof(vcb_cluster_rec));
+                    rt::copy_d2h(c->st_d2h, r.live_slots, br->cidx + l0, (size_t)nl * 4);
+                }
+            } else if (r.records) {
                 if (r.records_cap < s1 - s0) r.status = VCB_ERR_NOMEM;
                 else rt::copy_d2h(c->st_d2h, r.records, br->rec + s0, (size_t)(s1 - s0) * sizeof(vcb_cluster_rec));
             }
@@ -497,6 +506,7 @@ int vcb_runner_run_batch_host(vcb_ctx *c, const vcb_runner_config *cfg, const ui
     };
     upload(0);
     c->s2_overlap = cfg->hierarchical != 0 && nchunks > 1;
+    c->host_compact = cfg->hierarchical != 0 && results[0].live_slots != nullptr;
     // The hierarchical stage of a sub-batch is a long latency-bound kernel on a side stream (S2Set): its results are fetched
     // `depth` sub-batches later, after that many further stage-1 passes have been queued behind it, so neither the host nor
     // the main stream ever waits for it.  Without a hierarchical stage the result is complete when run_color returns.
@@ -518,12 +528,16 @@ int vcb_runner_run_batch_host(vcb_ctx *c, const vcb_runner_config *cfg, const ui
     }
     while (rc == VCB_OK && next_dl < nchunks) rc = download(next_dl++);
     c->s2_overlap = false;
+    c->host_compact = false;
     if (rt::stream_sync(c->st_d2h) != 0 || rt::stream_sync(c->st_h2d) != 0) rc = rc ? rc : VCB_ERR_CUDA;
     if (rc == VCB_OK) {
         for (size_t i = 0; i < n; ++i) {
             vcb_host_result &r = results[i];
-            if (r.records && r.status == VCB_OK && r.info.num_slots) {
-                const vcb_cluster_rec &l = r.records[r.info.num_slots - 1];
+            // the last record carries the list totals (offsets are exclusive scans over the slots; in the compact form the slots
+            // behind the last live one add nothing)
+            const u32 nrec = r.compact ? r.num_live : r.info.num_slots;
+            if (r.records && r.status == VCB_OK && nrec) {
+                const vcb_cluster_rec &l = r.records[nrec - 1];
                 r.info.indices_total = l.indices_off + l.indices_len; r.info.holes_total = l.holes_off + l.holes_len;
             }
         }

@@ -163,7 +163,7 @@ def runner_run_banded(contexts, rgba: np.ndarray, cfg: RunnerConfigC, pools: boo
     return res
 
 
-def runner_run_batch_host(ctx: Context, images, cfg: RunnerConfigC, records_cap: int | None = None, buffers=None) -> list:
+def runner_run_batch_host(ctx: Context, images, cfg: RunnerConfigC, records_cap: int | None = None, buffers=None, compact: bool = False) -> list:
     """vcb_runner_run_batch_host: equally sized host images in, host result buffers out, with the copies of neighbouring
     sub-batches overlapping the compute.  `buffers` may hold preallocated (ideally pinned) arrays: a list of
     (labels u32[w*h], records CLUSTER_REC_DTYPE[cap], outputs u32[cap]) per image."""
@@ -178,6 +178,7 @@ def runner_run_batch_host(ctx: Context, images, cfg: RunnerConfigC, records_cap:
                    for _ in range(n)]
     ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
     res = (HostResultC * n)()
+    live = [np.empty(len(buffers[k][1]), dtype=np.uint32) for k in range(n)] if compact else None
     for k in range(n):
         lab, rec, out = buffers[k]
         res[k].cluster_indices = lab.ctypes.data
@@ -185,6 +186,8 @@ def runner_run_batch_host(ctx: Context, images, cfg: RunnerConfigC, records_cap:
         res[k].outputs = out.ctypes.data
         res[k].records_cap = len(rec)
         res[k].outputs_cap = len(out)
+        if compact:
+            res[k].live_slots = live[k].ctypes.data
     st = ctx.lib.fn("runner_run_batch_host")(ctx.handle, C.byref(cfg), ptrs, w, h, n, res)
     ctx.lib.check(st, ctx.handle)
     out_list = []
@@ -192,6 +195,20 @@ def runner_run_batch_host(ctx: Context, images, cfg: RunnerConfigC, records_cap:
         ctx.lib.check(res[k].status, ctx.handle)
         lab, rec, out = buffers[k]
         info = res[k].info
+        if res[k].compact:
+            # compact records (vcb_host_result.live_slots): every slot that is not listed is Cluster::default()
+            full = np.zeros(info.num_slots, dtype=CLUSTER_REC_DTYPE)
+            full[live[k][: res[k].num_live]] = rec[: res[k].num_live]
+            # indices_off / holes_off are this library's own layout fields (exclusive scans of the list lengths over the slots of
+            # the image), not fields of the reference's Cluster: rebuilt here for the default slots as well
+            for off, ln in (("indices_off", "indices_len"), ("holes_off", "holes_len")):
+                c = np.cumsum(full[ln].astype(np.uint64))
+                full[off][1:] = c[:-1]
+                full[off][0] = 0
+            records = full
+        else:
+            records = rec[: info.num_slots]
         out_list.append({"width": info.width, "height": info.height, "num_slots": info.num_slots, "cluster_indices": lab,
-                         "records": rec[: info.num_slots], "clusters_output": out[: info.num_outputs]})
+                         "records": records, "clusters_output": out[: info.num_outputs], "compact": int(res[k].compact),
+                         "num_live": int(res[k].num_live)})
     return out_list

@@ -544,12 +544,14 @@ __device__ static __forceinline__ bool s2_batch_round(const S2 &a, S2Shared *sh,
     {
         const u32 total = sh->bpoff[32];
         if (total) {
+            // (candidate q, member lo) of item `it`: the last q with bpoff[q] <= it, the last lo with bpre[q][lo] <= it - bpoff[q].
+            // A thread's items only move forward, so both are advanced from where the previous item left them instead of two
+            // binary searches (ten dependent shared-memory loads) per item.
+            u32 q = 0, lo = 0;
             for (u32 it = tid; it < total; it += blockDim.x) {
-                u32 lo = 0, hi = 32;                                 // candidate: last q with bpoff[q] <= it
-                while (hi - lo > 1) { const u32 mid = (lo + hi) / 2; if (sh->bpoff[mid] <= it) lo = mid; else hi = mid; }
-                const u32 q = lo, loc = it - sh->bpoff[q];
-                lo = 0; hi = 32;                                     // member: last i with bpre[q][i] <= loc
-                while (hi - lo > 1) { const u32 mid = (lo + hi) / 2; if (sh->bpre[q][mid] <= loc) lo = mid; else hi = mid; }
+                while (q < 31u && sh->bpoff[q + 1] <= it) { ++q; lo = 0; }
+                const u32 loc = it - sh->bpoff[q];
+                while (lo < 31u && sh->bpre[q][lo + 1] <= loc) ++lo;
                 const uint4 nbq = a.bnd_nb[sh->bb0[q][lo] + (loc - sh->bpre[q][lo])];
                 const u32 c = sh->bc[q];
                 const u32 f0 = nbq.x == NONE ? NONE : ldv(&a.fw[base + nbq.x]), f1 = nbq.y == NONE ? NONE : ldv(&a.fw[base + nbq.y]);

@@ -227,3 +227,21 @@ def test_sim_chunked_batches_overlap_stage2(sim, oracle, monkeypatch):
     for k in range(len(imgs)):
         assert got[k]["compact"] == 1 and 0 < got[k]["num_live"] <= got[k]["num_slots"]
         assert_same_clusters(got[k], refs[k], pools=False, ctx=f"compact host batch image {k}")
+
+
+def test_sim_stage2_with_gpu_block_sizes(sim, oracle, monkeypatch):
+    """the hierarchical stage with the block sizes the GPU launches (256 and 512 threads: four / two passes of the 32 candidates
+    of a round; the simulator's default is 128) and with the single-pop path only"""
+    rng = np.random.default_rng(57)
+    cases = [random_case(rng, max_side=22, keyed=(k == 1), hierarchical=0xFFFFFFFF) for k in range(3)]
+    for img, cfg in cases:
+        cfg.good_min_area = 2
+        cfg.deepen_diff = 8
+    refs = [oracle.runner_run(img, cfg, pools=True, color_image=True) for img, cfg in cases]
+    for threads, nobatch in (("256", None), ("512", None), ("256", "1")):
+        monkeypatch.setenv("VCB_S2_THREADS", threads)
+        if nobatch:
+            monkeypatch.setenv("VCB_S2_NOBATCH", nobatch)
+        for (img, cfg), ref in zip(cases, refs):
+            got = sim.runner_run(img, cfg, pools=True, color_image=True)
+            assert_same_clusters(got, ref, pools=True, ctx=f"threads {threads} nobatch {nobatch} {img.shape}")

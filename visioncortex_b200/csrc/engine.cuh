@@ -682,7 +682,10 @@ inline int stage2_launch(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg
     // few images: fat CTAs (and, in the rect-scan perimeter mode, a thread-block cluster per image whose other CTAs help with
     // the large perimeter scans); many images: one slim CTA per image, several per SM
 #ifdef VCB_HOSTSIM
-    const int s2_threads = 128;                                  // 4 warps: batch rounds of 4 candidates
+    // 4 warps by default (fast on the thread-per-CUDA-thread simulator); VCB_S2_THREADS selects the block sizes the GPU runs
+    // (256 / 512 / 1024), so that the same passes-per-round are exercised on the CPU as well
+    int s2_threads = 128;
+    if (const char *ev = std::getenv("VCB_S2_THREADS")) s2_threads = std::max(32, std::min(1024, std::atoi(ev) / 32 * 32));
     const u32 G = (d.nimg == 1 && a.cfg.rect_perim) ? 2u : 1u;
 #else
     int s2_threads = d.nimg * 8 <= (u32)c->sms ? 1024 : d.nimg * 2 <= (u32)c->sms ? 512 : 256;

@@ -689,6 +689,11 @@ inline int stage2_launch(vcb_ctx *c, const Dims &d, const vcb_runner_config *cfg
     const u32 G = (d.nimg == 1 && a.cfg.rect_perim) ? 2u : 1u;
 #else
     int s2_threads = d.nimg * 8 <= (u32)c->sms ? 1024 : d.nimg * 2 <= (u32)c->sms ? 512 : 256;
+    // a run that is one device batch with at most one image per two SMs (the per-rank share of an 8-GPU batch): nothing shares
+    // the SMs with the replay, so every CTA takes a whole SM -- 32 warps evaluate a round's 32 candidates in one pass (measured,
+    // 64 images: 512 / 1024 threads -> 17.8 / 16.3-16.7 ms per call; at 128 images the gain was not reproducible: 22.2 and
+    // 27.8 ms against 25.4-25.9 with 256 threads, so that size keeps 256)
+    if (!c->s2_overlap && d.nimg * 2 <= (u32)c->sms) s2_threads = 1024;
     // the last device batch of an overlapped call shares the SMs with nothing that follows: one fat CTA per SM (a round
     // evaluates its 32 candidates in one pass of 32 warps instead of four passes of 8) shortens the tail of the call
     static const int tail_threads = std::getenv("VCB_S2_TAIL_THREADS") ? std::atoi(std::getenv("VCB_S2_TAIL_THREADS")) : 512;   // measured: 256 -> 76.9 ms, 512 -> 72.6 ms, 1024 -> 76.1 ms per 512-image step

@@ -29,6 +29,9 @@ def test_api_on_simulator():
     rng = np.random.default_rng(8)
     for k, img in enumerate(_images(rng, 4, 18)):
         check_runner_api(sim, img, **CASES[k % len(CASES)])
+    # a wider image: cluster rects beyond 32 pixels put the batched components (row f1) into several size classes
+    wide = random_colour_image(np.random.default_rng(12), 70, 37)
+    check_runner_api(sim, wide, hierarchical=HM, is_same_color_a=5, good_min_area=2, deepen_diff=8)
     check_runner_api(sim, np.zeros((0, 0, 4), dtype=np.uint8), hierarchical=0)
     check_builder_contract(sim)
     check_binary_api(sim)
